@@ -1,0 +1,183 @@
+/*
+ * shasta_b200 — C ABI of the B200-native ShaSTA affinity-estimation hot path.
+ *
+ * The reference (tsadja/ShaSTA) has no native code on this path: everything below replaces ATen op
+ * sequences inside det3d/models/tracker/shasta.py:213-327 and the helpers it calls. Each entry point
+ * cites the reference lines it stands in for. Conventions:
+ *   - every pointer is a DEVICE pointer unless named host_*; float32, C-contiguous; no ownership transfer —
+ *     the caller (PyTorch on the Python side) allocates inputs, outputs, the packed-weight buffer and the
+ *     workspace (sizes from the *_bytes queries);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value 0 = ok, > 0 = cudaError_t of a failed launch, < 0 = argument error
+ *     (shasta_last_error_string() describes the last failure of the calling thread);
+ *   - M = max_obj, T = D = M + 2, F = 320 (5 points x 64 channels), num_feats = 3 (the only shipped value,
+ *     configs/nusc/<class>.py; anything else is rejected with SHASTA_ERR_UNSUPPORTED).
+ */
+#ifndef SHASTA_B200_H_
+#define SHASTA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHASTA_ABI_VERSION 1
+#define SHASTA_FEAT 320          /* share_conv_channel(64) * num_point(5), shasta.py:50-51 */
+#define SHASTA_CH 64
+#define SHASTA_PROJ 144          /* 40 (fuse_shape.0) + 72 (res_coeff.0) + 32 (fuse_det.0) first-layer outputs */
+
+#define SHASTA_ERR_ARG (-1)
+#define SHASTA_ERR_UNSUPPORTED (-2)
+#define SHASTA_ERR_ALIGN (-3)
+#define SHASTA_ERR_SIZE (-4)
+
+typedef void* shasta_stream_t;
+
+/* Device pointers to the head's parameters in PyTorch (out_features, in_features) row-major layout, i.e.
+ * exactly the tensors of the reference state_dict (shasta.py:49-106). Index i of aug_* is the anchor:
+ * 0 newborn, 1 false positive (both fed by the CURRENT frame), 2 dead track, 3 false negative (PREVIOUS). */
+typedef struct shasta_params {
+  int32_t max_obj;
+  int32_t num_feats;
+  const float* aug_shape_w0[4]; /* (5M, 320M)  aug_shape.i.0.weight */
+  const float* aug_shape_b0[4]; /* (5M)        */
+  const float* aug_shape_w2[4]; /* (320, 5M)   aug_shape.i.2.weight */
+  const float* aug_shape_b2[4]; /* (320)       */
+  const float* aug_dets_w0[4];  /* (7M/32, 7M) aug_dets.i.0.weight */
+  const float* aug_dets_b0[4];
+  const float* aug_dets_w2[4];  /* (7, 7M/32)  */
+  const float* aug_dets_b2[4];
+  const float* fuse_shape_w[4]; /* (40,640) (20,40) (10,20) (1,10)   fuse_shape.{0,2,4,6} */
+  const float* fuse_shape_b[4];
+  const float* fuse_det_w[3];   /* (32,6) (8,32) (1,8)               fuse_det.{0,2,4} */
+  const float* fuse_det_b[3];
+  const float* res_coeff_w[3];  /* (72,646) (18,72) (3,18)           res_coeff.{0,2,4} */
+  const float* res_coeff_b[3];
+  const float* aff_w[6];        /* (128,M+2) (64,128) (32,64) (64,32) (128,64) (M+2,128)  aff.{0,..,10} */
+  const float* aff_b[6];
+} shasta_params_t;
+
+/* BEV geometry of BEVFeatureExtractor (bird_eye_view.py:11-22). */
+typedef struct shasta_geom {
+  float pc_start_x, pc_start_y;
+  float voxel_x, voxel_y;
+  float out_stride;
+  int32_t height, width; /* of the (B,H,W,64) channels-last map */
+} shasta_geom_t;
+
+/* Workspace regions (float offsets via shasta_workspace_offset). Layouts:
+ *   FEAT_*  (B,T,320)  rows [0,M) gathered features, rows M,M+1 anchor shape vectors
+ *           FEAT_CUR rows M,M+1 = dead, fn ; FEAT_PREV rows M,M+1 = newborn, fp   (shasta.py:246-247)
+ *   BOX_*   (B,T,8)    augmented boxes [x,y,z,w,l,h,yaw,0]; BOX_CUR is back-projected (shasta.py:270-274)
+ *   HIDDEN_PART (S,B,4,5M) split-K partial sums of aug_shape.i.0
+ *   PROJ_PREV (B,T,144) ; PROJ_CUR (B,144,DP) k-major, DP = D rounded up to 64 ; first-layer projections
+ *   AUX_*   (B,T,8)    [x,y,z,log w,log l,log h,cos yaw,sin yaw] of the augmented boxes
+ *   COLNORM (B,D)      L2 norm over T of the squared-distance column (F.normalize, shasta.py:279)
+ *   RESIDUAL / LOGITS (B,T,RS) with RS = D rounded up to 4
+ *   ANCHOR_BOX (B,4,7) newborn, fp, dead_trk, fn                                  (shasta.py:260-267)
+ */
+enum shasta_region {
+  SHASTA_WS_FEAT_CUR = 0,
+  SHASTA_WS_FEAT_PREV = 1,
+  SHASTA_WS_BOX_CUR = 2,
+  SHASTA_WS_BOX_PREV = 3,
+  SHASTA_WS_HIDDEN_PART = 4,
+  SHASTA_WS_PROJ_PREV = 5,
+  SHASTA_WS_PROJ_CUR = 6,
+  SHASTA_WS_AUX_PREV = 7,
+  SHASTA_WS_AUX_CUR = 8,
+  SHASTA_WS_COLNORM = 9,
+  SHASTA_WS_RESIDUAL = 10,
+  SHASTA_WS_LOGITS = 11,
+  SHASTA_WS_ANCHOR_BOX = 12,
+  SHASTA_WS_NUM_REGIONS = 13
+};
+
+int shasta_abi_version(void);
+const char* shasta_last_error_string(void);
+
+/* Number of kernels the last shasta_forward_f32 call of this thread enqueued (bench.py's gpu_launches). */
+int shasta_last_launch_count(void);
+
+size_t shasta_packed_weight_bytes(int max_obj, int num_feats);
+size_t shasta_workspace_bytes(int batch, int max_obj);
+/* Float offset of a region inside the workspace, or (size_t)-1 for a bad region id. */
+size_t shasta_workspace_offset(int batch, int max_obj, int region);
+/* Row strides used inside the workspace: DP (PROJ_CUR) and RS (RESIDUAL/LOGITS). */
+int shasta_proj_cur_stride(int max_obj);
+int shasta_row_stride(int max_obj);
+int shasta_hidden_splits(int max_obj);
+
+/* Repack the small layers into the kernel-side cache `packed` (first-layer weights split per side and
+ * transposed k-major, block-diagonal second layer, transposed aff). The four big aug_shape.i.0 matrices are
+ * NOT copied: kernels stream them in place from `params`. Must be re-run when parameters change. */
+int shasta_pack_weights(const shasta_params_t* host_params, float* packed, size_t packed_bytes,
+                        shasta_stream_t stream);
+
+/* center_utils.py:92-121 bilinear_interpolate_torch: im (H,W,C), xs/ys (n) pixel coordinates -> out (n,C).
+ * Bit-exact restatement (clamped taps, weights from clamped ints, ((a+b)+c)+d without FMA). C % 4 == 0. */
+int shasta_bilinear_f32(const float* im, int height, int width, int channels, const float* xs,
+                        const float* ys, int n, float* out, shasta_stream_t stream);
+
+/* shasta.py:121-161 get_box_center (num_point = 5) + bird_eye_view.py:18-41 BEVFeatureExtractor.forward for one
+ * frame: bev (B,H,W,64), boxes (B,M,box_stride>=7) [x,y,z,w,l,h,yaw,..] -> feat rows [0,M) of a (B,*,320)
+ * array whose batch stride is feat_batch_stride floats. variant: 0 = vectorised LDG sampler,
+ * 1 = cp.async.bulk (TMA) shared-memory-staged sampler. */
+int shasta_gather_f32(const float* bev, const float* boxes, int box_stride, int batch, int max_obj,
+                      const shasta_geom_t* host_geom, float* feat, size_t feat_batch_stride, int variant,
+                      shasta_stream_t stream);
+
+/* shasta.py:241-247 + 260-274: the four anchor shape vectors |aug_shape.i(flat feature)| and anchor boxes
+ * aug_dets.i(flat boxes), the back-projected copy of the current boxes and the augmented (B,T,*) arrays.
+ * Reads FEAT_* rows [0,M) from the workspace; writes FEAT_* rows M,M+1, BOX_*, ANCHOR_BOX.
+ * det_boxes / prev_det_boxes are the raw (B,M,11) inputs and are NOT modified here. */
+int shasta_anchors_f32(const shasta_params_t* host_params, const float* det_boxes,
+                       const float* prev_det_boxes, int batch, float* workspace, shasta_stream_t stream);
+
+/* First layers of fuse_shape / res_coeff / fuse_det decomposed per object (shasta.py:286-316 without the
+ * T x D x 640/646 tensors): PROJ_PREV[t] = W1[:, prev part] . [f_prev[t]; box_prev[t,:3]],
+ * PROJ_CUR[d] = W1[:, cur part] . [f_cur[d]; box_cur[d,:3]] + b1; plus AUX_*, COLNORM, and the in-place
+ * back-projection of det_boxes[:,:,:2] (shasta.py:270) when det_boxes_inout != NULL. */
+int shasta_project_f32(const float* packed, int batch, int max_obj, float* workspace,
+                       float* det_boxes_inout, shasta_stream_t stream);
+
+/* Per-pair work (shasta.py:277-319): on-chip outer sum + ReLU, layers 2.. of the three pairwise MLPs,
+ * hand-designed residuals, weighted sum -> RESIDUAL (B,T,RS). variant 0 = fp32 CUDA-core tiles,
+ * 1 = tcgen05 3xTF32 tensor-core tiles (fp32-equivalent), 2 = tcgen05 bf16 tiles. */
+int shasta_pairwise_f32(const float* packed, int batch, int max_obj, float* workspace, int variant,
+                        shasta_stream_t stream);
+
+/* shasta.py:323-325: aff row-MLP over D, then matched1 = softmax over D of rows [0,M) -> (B,M,M+2) and
+ * matched2 = softmax over T of columns [0,M) -> (B,M+2,M). */
+int shasta_aff_softmax_f32(const float* packed, int batch, int max_obj, float* workspace, float* matched1,
+                           float* matched2, shasta_stream_t stream);
+
+/* Whole path, shasta.py:231-325 from the 64-channel channels-last maps: bev/prev_bev (B,H,W,64),
+ * det_boxes/prev_det_boxes (B,M,11). det_boxes[:,:,:2] is back-projected IN PLACE like the reference.
+ * Outputs matched1 (B,M,M+2), matched2 (B,M+2,M); the anchors stay in the workspace (ANCHOR_BOX).
+ * flags: bit0 = TMA-staged gather, bits 4-7 = pairwise variant. */
+int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, const float* bev,
+                       const float* prev_bev, float* det_boxes, const float* prev_det_boxes, int batch,
+                       const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes,
+                       float* matched1, float* matched2, uint32_t flags, shasta_stream_t stream);
+
+/* tools/nusc_shasta/eval.py:126-181 decode on the device, one thread block per frame pair: row/column argmax
+ * over the valid region + the two anchor entries and the 0.5 / 0.7 thresholds.
+ * n_prev/n_det (B) int32. Outputs (int32 unless noted), all sized for max_obj:
+ *   prev_state (B,M): 0 keep, 1 dead, 2 false negative, -1 padding ; prev_argmax (B,M)
+ *   fn_score   (B,M) float: 1 - P(dead) for false negatives
+ *   det_state  (B,M): 0 keep, 1 keep+newborn, 2 dropped false positive, -1 padding ; det_argmax (B,M)
+ *                     det_argmax indexes the KEPT previous rows followed by newborn, fp (as the reference's
+ *                     matched_dets does)
+ *   det_score  (B,M) float: 1 - P(fp)   (ref_detection_score) */
+int shasta_decode_f32(const float* matched1, const float* matched2, const int32_t* n_prev,
+                      const int32_t* n_det, int batch, int max_obj, int32_t* prev_state,
+                      int32_t* prev_argmax, float* fn_score, int32_t* det_state, int32_t* det_argmax,
+                      float* det_score, shasta_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHASTA_B200_H_ */

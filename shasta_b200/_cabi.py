@@ -1,0 +1,113 @@
+"""ctypes binding of libshasta_b200.so (the C ABI declared in include/shasta_b200.h).
+
+There is no CPU or eager-PyTorch fallback: if the library is missing the import of the compute path fails
+loudly (``ShastaLibraryError``), and every non-zero return code raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libshasta_b200.so")
+
+F32P = ctypes.POINTER(ctypes.c_float)
+
+
+class ShastaLibraryError(RuntimeError):
+    pass
+
+
+class ShastaParams(ctypes.Structure):
+    """Mirror of shasta_params_t."""
+    _fields_ = [
+        ("max_obj", ctypes.c_int32),
+        ("num_feats", ctypes.c_int32),
+        ("aug_shape_w0", ctypes.c_void_p * 4),
+        ("aug_shape_b0", ctypes.c_void_p * 4),
+        ("aug_shape_w2", ctypes.c_void_p * 4),
+        ("aug_shape_b2", ctypes.c_void_p * 4),
+        ("aug_dets_w0", ctypes.c_void_p * 4),
+        ("aug_dets_b0", ctypes.c_void_p * 4),
+        ("aug_dets_w2", ctypes.c_void_p * 4),
+        ("aug_dets_b2", ctypes.c_void_p * 4),
+        ("fuse_shape_w", ctypes.c_void_p * 4),
+        ("fuse_shape_b", ctypes.c_void_p * 4),
+        ("fuse_det_w", ctypes.c_void_p * 3),
+        ("fuse_det_b", ctypes.c_void_p * 3),
+        ("res_coeff_w", ctypes.c_void_p * 3),
+        ("res_coeff_b", ctypes.c_void_p * 3),
+        ("aff_w", ctypes.c_void_p * 6),
+        ("aff_b", ctypes.c_void_p * 6),
+    ]
+
+
+class ShastaGeom(ctypes.Structure):
+    """Mirror of shasta_geom_t."""
+    _fields_ = [
+        ("pc_start_x", ctypes.c_float), ("pc_start_y", ctypes.c_float),
+        ("voxel_x", ctypes.c_float), ("voxel_y", ctypes.c_float),
+        ("out_stride", ctypes.c_float),
+        ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+    ]
+
+
+# region ids (enum shasta_region)
+WS_FEAT_CUR, WS_FEAT_PREV, WS_BOX_CUR, WS_BOX_PREV, WS_HIDDEN_PART, WS_PROJ_PREV, WS_PROJ_CUR, WS_AUX_PREV, \
+    WS_AUX_CUR, WS_COLNORM, WS_RESIDUAL, WS_LOGITS, WS_ANCHOR_BOX = range(13)
+
+# every symbol include/shasta_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _sz, _u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_uint32
+SYMBOLS = {
+    "shasta_abi_version": (_i, []),
+    "shasta_last_error_string": (ctypes.c_char_p, []),
+    "shasta_last_launch_count": (_i, []),
+    "shasta_packed_weight_bytes": (_sz, [_i, _i]),
+    "shasta_workspace_bytes": (_sz, [_i, _i]),
+    "shasta_workspace_offset": (_sz, [_i, _i, _i]),
+    "shasta_proj_cur_stride": (_i, [_i]),
+    "shasta_row_stride": (_i, [_i]),
+    "shasta_hidden_splits": (_i, [_i]),
+    "shasta_pack_weights": (_i, [ctypes.POINTER(ShastaParams), _vp, _sz, _vp]),
+    "shasta_bilinear_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "shasta_gather_f32": (_i, [_vp, _vp, _i, _i, _i, ctypes.POINTER(ShastaGeom), _vp, _sz, _i, _vp]),
+    "shasta_anchors_f32": (_i, [ctypes.POINTER(ShastaParams), _vp, _vp, _i, _vp, _vp]),
+    "shasta_project_f32": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "shasta_pairwise_f32": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "shasta_aff_softmax_f32": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "shasta_forward_f32": (_i, [ctypes.POINTER(ShastaParams), _vp, _vp, _vp, _vp, _vp, _i,
+                                ctypes.POINTER(ShastaGeom), _vp, _sz, _vp, _vp, _u32, _vp]),
+    "shasta_decode_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library once; raises ShastaLibraryError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ShastaLibraryError(
+            "%s not found: build it with `python -m shasta_b200.build` (nvcc, sm_100a). "
+            "shasta_b200 has no CPU or PyTorch fallback for the affinity path." % LIB_PATH)
+    try:
+        handle = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise ShastaLibraryError("cannot load %s: %s" % (LIB_PATH, e))
+    for name, (res, args) in SYMBOLS.items():
+        try:
+            fn = getattr(handle, name)
+        except AttributeError:
+            raise ShastaLibraryError("%s does not export %s (stale build?)" % (LIB_PATH, name))
+        fn.restype = res
+        fn.argtypes = args
+    if handle.shasta_abi_version() != 1:
+        raise ShastaLibraryError("ABI version mismatch: library %d, binding 1" % handle.shasta_abi_version())
+    _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().shasta_last_error_string().decode("utf-8", "replace")
+        raise ShastaLibraryError("%s failed with code %d: %s" % (what, rc, msg))

@@ -1,0 +1,172 @@
+// Affinity row-MLP + augmented dual softmax.
+//
+//   matched  = aff(residual)            per ROW of the T x D residual: D -> 128 -> 64 -> 32 -> 64 -> 128 -> D
+//   matched1 = softmax(matched[:, :-2, :], dim=2)   real previous objects over {detections, dead, FN}
+//   matched2 = softmax(matched[:, :, :-2], dim=1)   real detections over {previous objects, newborn, FP}
+// Reference: shasta.py:94-109,323-325.
+//
+// aff_row_kernel: a CTA owns 16 rows; activations stay in shared memory between the six layers (k-major,
+// [width][16]); transposed weights stream from L2 with coalesced loads; the row softmax is done by the same CTA
+// with warp-shuffle reductions. col_softmax_kernel does the column direction over the L2-resident logits.
+#include "common.cuh"
+
+namespace shasta {
+
+constexpr int kAffRows = 16;
+constexpr int kAffThreads = 256;
+
+// out[j][r] = act(bias[j] + sum_k in[k][r] * WT[k][j]),  N compile-time (<= 128)
+template <int N, bool RELU>
+__device__ __forceinline__ void dense_fixed(const float* __restrict__ in, const float* __restrict__ WT,
+                                            const float* __restrict__ bias, float* __restrict__ out, int K) {
+  constexpr int G = kAffThreads / N;      // thread groups over rows
+  constexpr int RPT = kAffRows / G;       // rows per thread: 8, 4 or 2
+  const int j = threadIdx.x % N, g = threadIdx.x / N;
+  const int r0 = g * RPT;
+  float acc[RPT];
+  const float bj = __ldg(bias + j);
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) acc[r] = bj;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float w = __ldg(WT + (size_t)k * N + j);
+    const float* ip = in + k * kAffRows + r0;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) acc[r] = fmaf(ip[r], w, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) out[j * kAffRows + r0 + r] = RELU ? fmaxf(acc[r], 0.f) : acc[r];
+}
+
+__global__ void __launch_bounds__(kAffThreads)
+aff_row_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, const float* __restrict__ residual,
+               float* __restrict__ logits, float* __restrict__ matched1) {
+  extern __shared__ __align__(16) float sm[];
+  const int T = M + 2, D = M + 2, RS = row_stride(M);
+  float* bufA = sm;                          // [D][16]  input rows, later the logits
+  float* bufB = sm + (size_t)D * kAffRows;   // [128][16]
+  float* bufC = bufB + 128 * kAffRows;       // [128][16]
+  const long long row0 = (long long)blockIdx.x * kAffRows;
+  const long long nrows = (long long)B * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // stage 16 residual rows, transposed to [d][r]
+  for (int r = warp; r < kAffRows; r += kAffThreads / 32) {
+    const long long row = row0 + r;
+    const float* src = residual + (size_t)row * RS;
+    for (int d = lane; d < D; d += 32) bufA[d * kAffRows + r] = (row < nrows) ? __ldg(src + d) : 0.f;
+  }
+  __syncthreads();
+
+  dense_fixed<128, true>(bufA, packed + P.aff_w[0], packed + P.aff_b[0], bufB, D);
+  __syncthreads();
+  dense_fixed<64, true>(bufB, packed + P.aff_w[1], packed + P.aff_b[1], bufC, 128);
+  __syncthreads();
+  dense_fixed<32, true>(bufC, packed + P.aff_w[2], packed + P.aff_b[2], bufB, 64);
+  __syncthreads();
+  dense_fixed<64, true>(bufB, packed + P.aff_w[3], packed + P.aff_b[3], bufC, 32);
+  __syncthreads();
+  dense_fixed<128, true>(bufC, packed + P.aff_w[4], packed + P.aff_b[4], bufB, 64);
+  __syncthreads();
+
+  // last layer 128 -> D, all 16 rows per thread, logits to shared (bufA) and to global
+  {
+    const float* WT = packed + P.aff_w[5];
+    const float* bias = packed + P.aff_b[5];
+    for (int j = threadIdx.x; j < D; j += kAffThreads) {
+      float acc[kAffRows];
+      const float bj = __ldg(bias + j);
+#pragma unroll
+      for (int r = 0; r < kAffRows; ++r) acc[r] = bj;
+#pragma unroll 2
+      for (int k = 0; k < 128; ++k) {
+        const float w = __ldg(WT + (size_t)k * D + j);
+        const float4* ip = reinterpret_cast<const float4*>(bufB + k * kAffRows);
+#pragma unroll
+        for (int q = 0; q < kAffRows / 4; ++q) {
+          const float4 v = ip[q];
+          acc[q * 4 + 0] = fmaf(v.x, w, acc[q * 4 + 0]);
+          acc[q * 4 + 1] = fmaf(v.y, w, acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(v.z, w, acc[q * 4 + 2]);
+          acc[q * 4 + 3] = fmaf(v.w, w, acc[q * 4 + 3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kAffRows; ++r) {
+        bufA[j * kAffRows + r] = acc[r];
+        if (row0 + r < nrows) logits[(size_t)(row0 + r) * RS + j] = acc[r];
+      }
+    }
+  }
+  __syncthreads();
+
+  // row softmax over D for rows t < M  -> matched1 (B,M,M+2)
+  for (int r = warp; r < kAffRows; r += kAffThreads / 32) {
+    const long long row = row0 + r;
+    if (row >= nrows) continue;
+    const int b = (int)(row / T), t = (int)(row % T);
+    if (t >= M) continue;
+    float mx = -INFINITY;
+    for (int d = lane; d < D; d += 32) mx = fmaxf(mx, bufA[d * kAffRows + r]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int d = lane; d < D; d += 32) sum += expf(bufA[d * kAffRows + r] - mx);
+    sum = warp_sum(sum);
+    float* dst = matched1 + ((size_t)b * M + t) * D;
+    for (int d = lane; d < D; d += 32) dst[d] = __fdiv_rn(expf(bufA[d * kAffRows + r] - mx), sum);
+  }
+}
+
+// matched2[b][t][d] = softmax over t of logits[b][t][d], d < M.  block (32 columns, 8 row slices)
+__global__ void __launch_bounds__(256)
+col_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __restrict__ matched2) {
+  __shared__ float red[8][33];
+  const int T = M + 2, RS = row_stride(M);
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * 32 + threadIdx.x;
+  const int ty = threadIdx.y;
+  const bool valid = d < M;
+  const float* src = logits + (size_t)b * T * RS + d;
+  float mx = -INFINITY;
+  if (valid)
+    for (int t = ty; t < T; t += 8) mx = fmaxf(mx, src[(size_t)t * RS]);
+  red[ty][threadIdx.x] = mx;
+  __syncthreads();
+#pragma unroll
+  for (int y = 0; y < 8; ++y) mx = fmaxf(mx, red[y][threadIdx.x]);
+  __syncthreads();
+  float sum = 0.f;
+  if (valid)
+    for (int t = ty; t < T; t += 8) sum += expf(src[(size_t)t * RS] - mx);
+  red[ty][threadIdx.x] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) sum += red[y][threadIdx.x];
+  if (valid) {
+    float* dst = matched2 + (size_t)b * T * M + d;
+    for (int t = ty; t < T; t += 8) dst[(size_t)t * M] = __fdiv_rn(expf(src[(size_t)t * RS] - mx), sum);
+  }
+}
+
+int launch_aff_softmax(const float* packed, int B, int M, float* ws, const WsLayout& L, float* matched1,
+                       float* matched2, cudaStream_t s) {
+  const PackLayout P = pack_layout(M);
+  const int T = M + 2;
+  const size_t smem = sizeof(float) * ((size_t)T + 256) * kAffRows;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SHASTA_CUDA(cudaFuncSetAttribute(aff_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const long long nrows = (long long)B * T;
+  aff_row_kernel<<<(unsigned)((nrows + kAffRows - 1) / kAffRows), kAffThreads, smem, s>>>(
+      packed, P, B, M, ws + L.off[SHASTA_WS_RESIDUAL], ws + L.off[SHASTA_WS_LOGITS], matched1);
+  SHASTA_CHECK_LAUNCH("aff_row_kernel");
+  dim3 grid((M + 31) / 32, B), block(32, 8);
+  col_softmax_kernel<<<grid, block, 0, s>>>(B, M, ws + L.off[SHASTA_WS_LOGITS], matched2);
+  SHASTA_CHECK_LAUNCH("col_softmax_kernel");
+  return 0;
+}
+
+}  // namespace shasta

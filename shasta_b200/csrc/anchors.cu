@@ -1,0 +1,279 @@
+// Anchor generators: the four aug_shape MLPs (Linear 320M -> 5M, ReLU, Linear 5M -> 320,
+// abs) and the four aug_dets MLPs (Linear 7M -> 7M/32, ReLU, Linear -> 7, abs on dims 3:6), plus the augmented
+// (B,T,8) box arrays with the back-projected current boxes.   Reference: shasta.py:49-57,69-76,241-247,260-274.
+//
+// aug_shape.i.0 is the heavy part: 4 x (5M x 320M) fp32 weights (1.03 GB at M = 200) streamed in place from the
+// PyTorch parameters. anchor_hidden_kernel is a split-K weight-streaming kernel: a CTA owns 32 weight rows x 2048
+// columns, each warp 4 rows, each lane a float4 column slice with 8-16 independent 16-byte loads in flight; the
+// activations of up to 8 frame pairs sit in shared memory. Larger batches re-walk the same weight tile from L2.
+// Partial sums go to HIDDEN_PART and are reduced in a fixed order (bit-reproducible) by anchor_finish_kernel.
+#include "common.cuh"
+
+namespace shasta {
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+struct AnchorW0 {
+  const float* w0[4];
+};
+
+template <int BT>
+__global__ void __launch_bounds__(256, 2)
+anchor_hidden_kernel(AnchorW0 w, const float* __restrict__ feat_cur, const float* __restrict__ feat_prev, int B,
+                     int M, float* __restrict__ part) {
+  constexpr int U = (BT >= 8) ? 2 : 4;  // k-steps whose weight loads are issued together
+  __shared__ __align__(16) float xs[BT][kAnchorKChunk];
+  const int K = kF * M, N5 = 5 * M;
+  const size_t xstride = (size_t)(M + 2) * kF;
+  const int s = blockIdx.x, i = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * kAnchorRowsPerCta + warp * 4;
+  const float* __restrict__ W = w.w0[i];
+  const float* __restrict__ X = (i < 2) ? feat_cur : feat_prev;
+  const int kbeg = s * kAnchorKRange;
+  const int kend = min(K, kbeg + kAnchorKRange);
+
+  const float4* wrow[4];
+  bool rvalid[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    rvalid[r] = (n0 + r) < N5;
+    wrow[r] = reinterpret_cast<const float4*>(W + (size_t)(rvalid[r] ? n0 + r : 0) * K);
+  }
+
+  for (int b0 = 0; b0 < B; b0 += BT) {
+    float acc[4][BT];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int t = 0; t < BT; ++t) acc[r][t] = 0.f;
+
+    for (int kc = kbeg; kc < kend; kc += kAnchorKChunk) {
+      __syncthreads();
+      // stage the activations of this chunk: one float4 per thread per frame pair
+      {
+        const int k = kc + threadIdx.x * 4;
+#pragma unroll
+        for (int t = 0; t < BT; ++t) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < kend && b0 + t < B)
+            v = __ldg(reinterpret_cast<const float4*>(X + (size_t)(b0 + t) * xstride + k));
+          reinterpret_cast<float4*>(&xs[t][0])[threadIdx.x] = v;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u0 = 0; u0 < 8; u0 += U) {
+        float4 wv[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int k4 = lane + 32 * (u0 + u);
+          const int k = kc + 4 * k4;
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            wv[u][r] = (k < kend && rvalid[r]) ? ldg_stream(wrow[r] + (k >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int k4 = lane + 32 * (u0 + u);
+#pragma unroll
+          for (int t = 0; t < BT; ++t) {
+            const float4 x = reinterpret_cast<const float4*>(&xs[t][0])[k4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              acc[r][t] = fmaf(wv[u][r].x, x.x, acc[r][t]);
+              acc[r][t] = fmaf(wv[u][r].y, x.y, acc[r][t]);
+              acc[r][t] = fmaf(wv[u][r].z, x.z, acc[r][t]);
+              acc[r][t] = fmaf(wv[u][r].w, x.w, acc[r][t]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int t = 0; t < BT; ++t) {
+        const float v = warp_sum(acc[r][t]);
+        if (lane == 0 && rvalid[r] && b0 + t < B)
+          part[(((size_t)s * B + (b0 + t)) * 4 + i) * N5 + (n0 + r)] = v;
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct AnchorFinishArgs {
+  const float* b0[4];
+  const float* w2[4];
+  const float* b2[4];
+  const float* dw0[4];
+  const float* db0[4];
+  const float* dw2[4];
+  const float* db2[4];
+};
+
+constexpr int kFinishBG = 4;  // frame pairs per CTA
+
+// grid: x = 5 roles (anchor 0..3, 4 = real-box copy / back-projection), y = output slices, z = frame-pair groups
+__global__ void __launch_bounds__(256)
+anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, const float* __restrict__ det_boxes,
+                     const float* __restrict__ prev_boxes, int B, int M, float* __restrict__ feat_cur,
+                     float* __restrict__ feat_prev, float* __restrict__ box_cur, float* __restrict__ box_prev,
+                     float* __restrict__ anchor_box) {
+  extern __shared__ __align__(16) float sm[];
+  const int T = M + 2, N5 = 5 * M, H7 = (7 * M) / 32;
+  const int role = blockIdx.x;
+  const int bg0 = blockIdx.z * kFinishBG;
+  const int nb = min(kFinishBG, B - bg0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (role == 4) {
+    // real rows of the augmented box arrays; current boxes back-projected: x - vx*dt, y - vy*dt (shasta.py:270)
+    const int per = nb * M;
+    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < per; idx += gridDim.y * blockDim.x) {
+      const int b = bg0 + idx / M, m = idx % M;
+      const float* d = det_boxes + ((size_t)b * M + m) * 11;
+      const float* p = prev_boxes + ((size_t)b * M + m) * 11;
+      float* oc = box_cur + ((size_t)b * T + m) * 8;
+      float* op = box_prev + ((size_t)b * T + m) * 8;
+      const float dt = d[9];
+      oc[0] = __fsub_rn(d[0], __fmul_rn(d[7], dt));
+      oc[1] = __fsub_rn(d[1], __fmul_rn(d[8], dt));
+#pragma unroll
+      for (int c = 2; c < 7; ++c) oc[c] = d[c];
+      oc[7] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 7; ++c) op[c] = p[c];
+      op[7] = 0.f;
+    }
+    return;
+  }
+
+  const int i = role;
+  float* hid = sm;                      // [kFinishBG][N5]
+  float* hd = sm + kFinishBG * N5;      // [kFinishBG][max(H7,1)]
+
+  // ---- hidden = relu(sum over splits + bias)        aug_shape.i.0 + ReLU
+  for (int idx = threadIdx.x; idx < nb * N5; idx += blockDim.x) {
+    const int bg = idx / N5, n = idx % N5;
+    const int b = bg0 + bg;
+    float sum = 0.f;
+    for (int s = 0; s < S; ++s) sum += part[(((size_t)s * B + b) * 4 + i) * N5 + n];
+    hid[bg * N5 + n] = fmaxf(sum + a.b0[i][n], 0.f);
+  }
+  __syncthreads();
+
+  // ---- aug_shape.i.2 + abs -> anchor row of the augmented feature array
+  {
+    const int jper = (kF + gridDim.y - 1) / gridDim.y;
+    const int jbeg = blockIdx.y * jper, jend = min(kF, jbeg + jper);
+    float* fdst = (i < 2) ? feat_prev : feat_cur;  // newborn/fp extend the T axis, dead/fn the D axis
+    const int row = M + (i & 1);
+    for (int j = jbeg + warp; j < jend; j += 8) {
+      const float* wr = a.w2[i] + (size_t)j * N5;
+      float acc[kFinishBG];
+#pragma unroll
+      for (int g = 0; g < kFinishBG; ++g) acc[g] = 0.f;
+      for (int n = lane; n < N5; n += 32) {
+        const float wv = __ldg(wr + n);
+#pragma unroll
+        for (int g = 0; g < kFinishBG; ++g) acc[g] = fmaf(wv, hid[g * N5 + n], acc[g]);
+      }
+#pragma unroll
+      for (int g = 0; g < kFinishBG; ++g) {
+        const float v = warp_sum(acc[g]);
+        if (lane == 0 && g < nb)
+          fdst[((size_t)(bg0 + g) * T + row) * kF + j] = fabsf(v + a.b2[i][j]);
+      }
+    }
+  }
+
+  // ---- aug_dets.i (only the first output slice does it)
+  if (blockIdx.y == 0) {
+    const float* src = (i < 2) ? det_boxes : prev_boxes;
+    const int K7 = 7 * M;
+    for (int o = warp; o < nb * H7; o += 8) {
+      const int bg = o / H7, h = o % H7;
+      const float* wr = a.dw0[i] + (size_t)h * K7;
+      const float* bx = src + (size_t)(bg0 + bg) * M * 11;
+      float acc = 0.f;
+      for (int k = lane; k < K7; k += 32) acc = fmaf(__ldg(wr + k), bx[(k / 7) * 11 + (k % 7)], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) hd[bg * H7 + h] = fmaxf(acc + a.db0[i][h], 0.f);
+    }
+    __syncthreads();
+    if (threadIdx.x < nb * 8) {
+      const int bg = threadIdx.x >> 3, c = threadIdx.x & 7;
+      const int b = bg0 + bg;
+      float v = 0.f;
+      if (c < 7) {
+        v = a.db2[i][c];
+        float acc = 0.f;
+        for (int h = 0; h < H7; ++h) acc = fmaf(a.dw2[i][c * H7 + h], hd[bg * H7 + h], acc);
+        v = acc + v;
+        if (c >= 3 && c < 6) v = fabsf(v);
+        anchor_box[((size_t)b * 4 + i) * 7 + c] = v;
+      }
+      float* bdst = (i < 2) ? box_prev : box_cur;
+      bdst[((size_t)b * T + M + (i & 1)) * 8 + c] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
+                   const WsLayout& L, cudaStream_t s) {
+  const int M = p.max_obj;
+  const int S = hidden_splits(M);
+  const int N5 = 5 * M;
+  float* feat_cur = ws + L.off[SHASTA_WS_FEAT_CUR];
+  float* feat_prev = ws + L.off[SHASTA_WS_FEAT_PREV];
+  float* part = ws + L.off[SHASTA_WS_HIDDEN_PART];
+
+  AnchorW0 w;
+  for (int i = 0; i < 4; ++i) w.w0[i] = p.aug_shape_w0[i];
+  dim3 grid(S, (N5 + kAnchorRowsPerCta - 1) / kAnchorRowsPerCta, 4);
+  if (B >= 8 || B > 4)
+    anchor_hidden_kernel<8><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
+  else if (B > 2)
+    anchor_hidden_kernel<4><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
+  else if (B == 2)
+    anchor_hidden_kernel<2><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
+  else
+    anchor_hidden_kernel<1><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
+  SHASTA_CHECK_LAUNCH("anchor_hidden_kernel");
+
+  AnchorFinishArgs a;
+  for (int i = 0; i < 4; ++i) {
+    a.b0[i] = p.aug_shape_b0[i];
+    a.w2[i] = p.aug_shape_w2[i];
+    a.b2[i] = p.aug_shape_b2[i];
+    a.dw0[i] = p.aug_dets_w0[i];
+    a.db0[i] = p.aug_dets_b0[i];
+    a.dw2[i] = p.aug_dets_w2[i];
+    a.db2[i] = p.aug_dets_b2[i];
+  }
+  const int H7 = (7 * M) / 32;
+  const size_t smem = sizeof(float) * ((size_t)kFinishBG * N5 + (size_t)kFinishBG * (H7 > 0 ? H7 : 1));
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SHASTA_CUDA(cudaFuncSetAttribute(anchor_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int groups = (B + kFinishBG - 1) / kFinishBG;
+  const int slices = (groups >= 32) ? 1 : (groups >= 8 ? 4 : 8);
+  dim3 fgrid(5, slices, groups);
+  anchor_finish_kernel<<<fgrid, 256, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev,
+                                                ws + L.off[SHASTA_WS_BOX_CUR], ws + L.off[SHASTA_WS_BOX_PREV],
+                                                ws + L.off[SHASTA_WS_ANCHOR_BOX]);
+  SHASTA_CHECK_LAUNCH("anchor_finish_kernel");
+  return 0;
+}
+
+}  // namespace shasta

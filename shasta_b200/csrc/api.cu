@@ -1,0 +1,287 @@
+// extern "C" surface declared in include/shasta_b200.h: argument checks, workspace carving, launch sequencing.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace shasta {
+
+static thread_local char g_error[512] = "";
+thread_local int g_launch_count = 0;
+static thread_local int g_last_forward_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+static int check_dims(int batch, int max_obj) {
+  if (batch < 0 || batch > 65535) {
+    set_error("batch %d out of range [0, 65535]", batch);
+    return SHASTA_ERR_SIZE;
+  }
+  if (max_obj < 1 || max_obj > 4096) {
+    set_error("max_obj %d out of range [1, 4096]", max_obj);
+    return SHASTA_ERR_SIZE;
+  }
+  return 0;
+}
+
+static int check_params(const shasta_params_t* p) {
+  if (p == nullptr) {
+    set_error("params is NULL");
+    return SHASTA_ERR_ARG;
+  }
+  if (p->num_feats != kNF) {
+    set_error("num_feats %d unsupported: only num_feats = 3 (every shipped config) is implemented", p->num_feats);
+    return SHASTA_ERR_UNSUPPORTED;
+  }
+  int rc = check_dims(0, p->max_obj);
+  if (rc) return rc;
+  const void* const* ptrs = reinterpret_cast<const void* const*>(&p->aug_shape_w0[0]);
+  const size_t n = (sizeof(shasta_params_t) - offsetof(shasta_params_t, aug_shape_w0)) / sizeof(void*);
+  for (size_t i = 0; i < n; ++i) {
+    if (ptrs[i] == nullptr) {
+      set_error("params pointer #%zu is NULL", i);
+      return SHASTA_ERR_ARG;
+    }
+  }
+  for (int i = 0; i < 4; ++i)
+    if (((uintptr_t)p->aug_shape_w0[i] & 15) != 0) {
+      set_error("aug_shape.%d.0.weight must be 16-byte aligned", i);
+      return SHASTA_ERR_ALIGN;
+    }
+  return 0;
+}
+
+static int check_geom(const shasta_geom_t* g) {
+  if (g == nullptr || g->height < 1 || g->width < 1 || !(g->voxel_x > 0.f) || !(g->voxel_y > 0.f) ||
+      !(g->out_stride > 0.f)) {
+    set_error("invalid BEV geometry");
+    return SHASTA_ERR_ARG;
+  }
+  return 0;
+}
+
+#define NOT_NULL(p)                         \
+  do {                                      \
+    if ((p) == nullptr) {                   \
+      shasta::set_error(#p " is NULL");     \
+      return SHASTA_ERR_ARG;                \
+    }                                       \
+  } while (0)
+
+#define ALIGNED16(p)                                       \
+  do {                                                     \
+    if (((uintptr_t)(p) & 15) != 0) {                      \
+      shasta::set_error(#p " must be 16-byte aligned");    \
+      return SHASTA_ERR_ALIGN;                             \
+    }                                                      \
+  } while (0)
+
+}  // namespace shasta
+
+using namespace shasta;
+
+extern "C" {
+
+int shasta_abi_version(void) { return SHASTA_ABI_VERSION; }
+const char* shasta_last_error_string(void) { return g_error; }
+int shasta_last_launch_count(void) { return g_last_forward_launches; }
+
+size_t shasta_packed_weight_bytes(int max_obj, int num_feats) {
+  if (num_feats != kNF || max_obj < 1) return 0;
+  return pack_layout(max_obj).total * sizeof(float);
+}
+
+size_t shasta_workspace_bytes(int batch, int max_obj) {
+  if (batch < 0 || max_obj < 1) return 0;
+  return ws_layout(batch, max_obj).total * sizeof(float);
+}
+
+size_t shasta_workspace_offset(int batch, int max_obj, int region) {
+  if (region < 0 || region >= SHASTA_WS_NUM_REGIONS || batch < 0 || max_obj < 1) return (size_t)-1;
+  return ws_layout(batch, max_obj).off[region];
+}
+
+int shasta_proj_cur_stride(int max_obj) { return proj_cur_stride(max_obj); }
+int shasta_row_stride(int max_obj) { return row_stride(max_obj); }
+int shasta_hidden_splits(int max_obj) { return hidden_splits(max_obj); }
+
+int shasta_pack_weights(const shasta_params_t* host_params, float* packed, size_t packed_bytes,
+                        shasta_stream_t stream) {
+  int rc = check_params(host_params);
+  if (rc) return rc;
+  NOT_NULL(packed);
+  ALIGNED16(packed);
+  if (packed_bytes < shasta_packed_weight_bytes(host_params->max_obj, host_params->num_feats)) {
+    set_error("packed buffer too small");
+    return SHASTA_ERR_SIZE;
+  }
+  return launch_pack(*host_params, packed, (cudaStream_t)stream);
+}
+
+int shasta_bilinear_f32(const float* im, int height, int width, int channels, const float* xs, const float* ys,
+                        int n, float* out, shasta_stream_t stream) {
+  NOT_NULL(im);
+  NOT_NULL(out);
+  if (n < 0 || height < 1 || width < 1 || channels < 4 || (channels & 3)) {
+    set_error("bilinear: need n >= 0, H,W >= 1, C a positive multiple of 4");
+    return SHASTA_ERR_ARG;
+  }
+  if (n > 0) {
+    NOT_NULL(xs);
+    NOT_NULL(ys);
+  }
+  ALIGNED16(im);
+  ALIGNED16(out);
+  return launch_bilinear(im, height, width, channels, xs, ys, n, out, (cudaStream_t)stream);
+}
+
+int shasta_gather_f32(const float* bev, const float* boxes, int box_stride, int batch, int max_obj,
+                      const shasta_geom_t* host_geom, float* feat, size_t feat_batch_stride, int variant,
+                      shasta_stream_t stream) {
+  int rc = check_dims(batch, max_obj);
+  if (rc) return rc;
+  rc = check_geom(host_geom);
+  if (rc) return rc;
+  NOT_NULL(bev);
+  NOT_NULL(boxes);
+  NOT_NULL(feat);
+  ALIGNED16(bev);
+  ALIGNED16(feat);
+  if (box_stride < 7 || feat_batch_stride < (size_t)max_obj * kF || (feat_batch_stride & 3)) {
+    set_error("gather: box_stride must be >= 7 and feat_batch_stride >= M*320 and a multiple of 4");
+    return SHASTA_ERR_ARG;
+  }
+  return launch_gather(bev, boxes, feat, nullptr, nullptr, nullptr, 1, box_stride, batch, max_obj, *host_geom,
+                       feat_batch_stride, variant, (cudaStream_t)stream);
+}
+
+int shasta_anchors_f32(const shasta_params_t* host_params, const float* det_boxes, const float* prev_det_boxes,
+                       int batch, float* workspace, shasta_stream_t stream) {
+  int rc = check_params(host_params);
+  if (rc) return rc;
+  rc = check_dims(batch, host_params->max_obj);
+  if (rc) return rc;
+  NOT_NULL(det_boxes);
+  NOT_NULL(prev_det_boxes);
+  NOT_NULL(workspace);
+  ALIGNED16(workspace);
+  if (batch == 0) return 0;
+  return launch_anchors(*host_params, det_boxes, prev_det_boxes, batch, workspace,
+                        ws_layout(batch, host_params->max_obj), (cudaStream_t)stream);
+}
+
+int shasta_project_f32(const float* packed, int batch, int max_obj, float* workspace, float* det_boxes_inout,
+                       shasta_stream_t stream) {
+  int rc = check_dims(batch, max_obj);
+  if (rc) return rc;
+  NOT_NULL(packed);
+  NOT_NULL(workspace);
+  ALIGNED16(packed);
+  ALIGNED16(workspace);
+  if (batch == 0) return 0;
+  return launch_project(packed, batch, max_obj, workspace, ws_layout(batch, max_obj), det_boxes_inout,
+                        (cudaStream_t)stream);
+}
+
+int shasta_pairwise_f32(const float* packed, int batch, int max_obj, float* workspace, int variant,
+                        shasta_stream_t stream) {
+  int rc = check_dims(batch, max_obj);
+  if (rc) return rc;
+  NOT_NULL(packed);
+  NOT_NULL(workspace);
+  ALIGNED16(packed);
+  ALIGNED16(workspace);
+  if (batch == 0) return 0;
+  return launch_pairwise(packed, batch, max_obj, workspace, ws_layout(batch, max_obj), variant,
+                         (cudaStream_t)stream);
+}
+
+int shasta_aff_softmax_f32(const float* packed, int batch, int max_obj, float* workspace, float* matched1,
+                           float* matched2, shasta_stream_t stream) {
+  int rc = check_dims(batch, max_obj);
+  if (rc) return rc;
+  NOT_NULL(packed);
+  NOT_NULL(workspace);
+  NOT_NULL(matched1);
+  NOT_NULL(matched2);
+  ALIGNED16(packed);
+  ALIGNED16(workspace);
+  if (batch == 0) return 0;
+  return launch_aff_softmax(packed, batch, max_obj, workspace, ws_layout(batch, max_obj), matched1, matched2,
+                            (cudaStream_t)stream);
+}
+
+int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, const float* bev,
+                       const float* prev_bev, float* det_boxes, const float* prev_det_boxes, int batch,
+                       const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes, float* matched1,
+                       float* matched2, uint32_t flags, shasta_stream_t stream) {
+  int rc = check_params(host_params);
+  if (rc) return rc;
+  const int M = host_params->max_obj;
+  rc = check_dims(batch, M);
+  if (rc) return rc;
+  rc = check_geom(host_geom);
+  if (rc) return rc;
+  NOT_NULL(packed);
+  NOT_NULL(bev);
+  NOT_NULL(prev_bev);
+  NOT_NULL(det_boxes);
+  NOT_NULL(prev_det_boxes);
+  NOT_NULL(workspace);
+  NOT_NULL(matched1);
+  NOT_NULL(matched2);
+  ALIGNED16(packed);
+  ALIGNED16(bev);
+  ALIGNED16(prev_bev);
+  ALIGNED16(workspace);
+  if (workspace_bytes < shasta_workspace_bytes(batch, M)) {
+    set_error("workspace too small: %zu < %zu bytes", workspace_bytes, shasta_workspace_bytes(batch, M));
+    return SHASTA_ERR_SIZE;
+  }
+  g_launch_count = 0;
+  g_last_forward_launches = 0;
+  if (batch == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const WsLayout L = ws_layout(batch, M);
+  const size_t fstride = (size_t)(M + 2) * kF;
+  // a1-a2: both frames in one launch (blockIdx.y selects the frame)
+  rc = launch_gather(bev, det_boxes, workspace + L.off[SHASTA_WS_FEAT_CUR], prev_bev, prev_det_boxes,
+                     workspace + L.off[SHASTA_WS_FEAT_PREV], 2, 11, batch, M, *host_geom, fstride, (int)(flags & 1u), s);
+  if (rc) return rc;
+  rc = launch_anchors(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, s);  // a3-a4
+  if (rc) return rc;
+  rc = launch_project(packed, batch, M, workspace, L, det_boxes, s);  // first layers, aux, colnorm, back-projection
+  if (rc) return rc;
+  rc = launch_pairwise(packed, batch, M, workspace, L, (int)((flags >> 4) & 15u), s);  // a5-a9
+  if (rc) return rc;
+  rc = launch_aff_softmax(packed, batch, M, workspace, L, matched1, matched2, s);  // a10-a11
+  if (rc) return rc;
+  g_last_forward_launches = g_launch_count;
+  return 0;
+}
+
+int shasta_decode_f32(const float* matched1, const float* matched2, const int32_t* n_prev, const int32_t* n_det,
+                      int batch, int max_obj, int32_t* prev_state, int32_t* prev_argmax, float* fn_score,
+                      int32_t* det_state, int32_t* det_argmax, float* det_score, shasta_stream_t stream) {
+  int rc = check_dims(batch, max_obj);
+  if (rc) return rc;
+  NOT_NULL(matched1);
+  NOT_NULL(matched2);
+  NOT_NULL(n_prev);
+  NOT_NULL(n_det);
+  NOT_NULL(prev_state);
+  NOT_NULL(prev_argmax);
+  NOT_NULL(fn_score);
+  NOT_NULL(det_state);
+  NOT_NULL(det_argmax);
+  NOT_NULL(det_score);
+  return launch_decode(matched1, matched2, n_prev, n_det, batch, max_obj, prev_state, prev_argmax, fn_score,
+                       det_state, det_argmax, det_score, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+// Shared definitions of the shasta_b200 kernels: workspace / packed-weight layouts and small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/shasta_b200.h"
+
+namespace shasta {
+
+constexpr int kF = SHASTA_FEAT;     // 320
+constexpr int kC = SHASTA_CH;       // 64
+constexpr int kProj = SHASTA_PROJ;  // 144
+constexpr int kProjShape = 112;     // first-layer outputs that read the 320-wide shape feature (40 + 72)
+constexpr int kNF = 3;
+
+// ---- anchors split-K geometry ------------------------------------------------------------------
+constexpr int kAnchorKRange = 2048;   // floats of K one CTA of the hidden kernel covers
+constexpr int kAnchorKChunk = 1024;   // floats of K staged in shared memory at a time
+constexpr int kAnchorRowsPerCta = 32; // 8 warps x 4 weight rows
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+__host__ __device__ inline int hidden_splits(int M) { return (kF * M + kAnchorKRange - 1) / kAnchorKRange; }
+__host__ __device__ inline int proj_cur_stride(int M) { return round_up(M + 2, 64); }
+__host__ __device__ inline int row_stride(int M) { return round_up(M + 2, 4); }
+
+// ---- workspace layout (float offsets, every region 256-byte aligned) ----------------------------
+struct WsLayout {
+  size_t off[SHASTA_WS_NUM_REGIONS];
+  size_t total;  // floats
+};
+
+__host__ inline WsLayout ws_layout(int B, int M) {
+  WsLayout L;
+  const size_t T = (size_t)M + 2;
+  size_t sz[SHASTA_WS_NUM_REGIONS];
+  sz[SHASTA_WS_FEAT_CUR] = (size_t)B * T * kF;
+  sz[SHASTA_WS_FEAT_PREV] = (size_t)B * T * kF;
+  sz[SHASTA_WS_BOX_CUR] = (size_t)B * T * 8;
+  sz[SHASTA_WS_BOX_PREV] = (size_t)B * T * 8;
+  sz[SHASTA_WS_HIDDEN_PART] = (size_t)hidden_splits(M) * B * 4 * (5 * (size_t)M);
+  sz[SHASTA_WS_PROJ_PREV] = (size_t)B * T * kProj;
+  sz[SHASTA_WS_PROJ_CUR] = (size_t)B * kProj * proj_cur_stride(M);
+  sz[SHASTA_WS_AUX_PREV] = (size_t)B * T * 8;
+  sz[SHASTA_WS_AUX_CUR] = (size_t)B * T * 8;
+  sz[SHASTA_WS_COLNORM] = (size_t)B * T;
+  sz[SHASTA_WS_RESIDUAL] = (size_t)B * T * row_stride(M);
+  sz[SHASTA_WS_LOGITS] = (size_t)B * T * row_stride(M);
+  sz[SHASTA_WS_ANCHOR_BOX] = (size_t)B * 4 * 7;
+  size_t o = 0;
+  for (int i = 0; i < SHASTA_WS_NUM_REGIONS; ++i) {
+    L.off[i] = o;
+    o += (sz[i] + 63) / 64 * 64;
+  }
+  L.total = o;
+  return L;
+}
+
+// ---- packed small-layer weights (float offsets) ------------------------------------------------
+// All matrices are stored k-major ("transposed": [in][out]) so that consecutive threads / vector lanes
+// read consecutive outputs.
+struct PackLayout {
+  size_t p1_prev;   // [320][112]  cols 0..39 fuse_shape.0.W[:, 0:320]^T ; 40..111 res_coeff.0.W[:, 0:320]^T
+  size_t p1_cur;    // [320][112]  fuse_shape.0.W[:, 320:640]^T ; res_coeff.0.W[:, 323:643]^T
+  size_t pb_prev;   // [3][144]    box columns of res_coeff.0 (320:323) and fuse_det.0 (0:3); cols 0..39 zero
+  size_t pb_cur;    // [3][144]    res_coeff.0 (643:646), fuse_det.0 (3:6)
+  size_t pbias;     // [144]       first-layer biases (added on the current-frame side)
+  size_t l2a, l2a_b;  // [40][20], [20]   fuse_shape.2
+  size_t l2b, l2b_b;  // [72][20], [20]   res_coeff.2 (18 outputs, padded)
+  size_t l2c, l2c_b;  // [32][8],  [8]    fuse_det.2
+  size_t l3a, l3a_b;  // [20][12], [12]   fuse_shape.4 (10 outputs, padded)
+  size_t l4a, l4a_b;  // [12], [4]        fuse_shape.6
+  size_t l3b, l3b_b;  // [20][4], [4]     res_coeff.4 (18 inputs padded to 20, 3 outputs padded to 4)
+  size_t l3c, l3c_b;  // [8], [4]         fuse_det.4
+  size_t pair_end;    // end of the block the pairwise kernel stages in shared memory (from l2a)
+  size_t aff_w[6];    // aff.{0..10}.weight^T : [in][out]
+  size_t aff_b[6];
+  size_t total;       // floats
+};
+
+__host__ inline PackLayout pack_layout(int M) {
+  PackLayout P;
+  const size_t D = (size_t)M + 2;
+  size_t o = 0;
+  auto take = [&](size_t n) {
+    size_t r = o;
+    o += (n + 3) / 4 * 4;
+    return r;
+  };
+  P.p1_prev = take(kF * kProjShape);
+  P.p1_cur = take(kF * kProjShape);
+  P.pb_prev = take(3 * kProj);
+  P.pb_cur = take(3 * kProj);
+  P.pbias = take(kProj);
+  P.l2a = take(40 * 20);
+  P.l2a_b = take(20);
+  P.l2b = take(72 * 20);
+  P.l2b_b = take(20);
+  P.l2c = take(32 * 8);
+  P.l2c_b = take(8);
+  P.l3a = take(20 * 12);
+  P.l3a_b = take(12);
+  P.l4a = take(12);
+  P.l4a_b = take(4);
+  P.l3b = take(20 * 4);
+  P.l3b_b = take(4);
+  P.l3c = take(8);
+  P.l3c_b = take(4);
+  P.pair_end = o;
+  const size_t win[6] = {D, 128, 64, 32, 64, 128};
+  const size_t wout[6] = {128, 64, 32, 64, 128, D};
+  for (int i = 0; i < 6; ++i) {
+    P.aff_w[i] = take(win[i] * wout[i]);
+    P.aff_b[i] = take(wout[i]);
+  }
+  P.total = o;
+  return P;
+}
+
+// ---- error plumbing -----------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern thread_local int g_launch_count;
+
+#define SHASTA_CHECK_LAUNCH(name)                                               \
+  do {                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                       \
+    if (e__ != cudaSuccess) {                                                   \
+      shasta::set_error("%s launch failed: %s", name, cudaGetErrorString(e__)); \
+      return (int)e__;                                                          \
+    }                                                                           \
+    ++shasta::g_launch_count;                                                   \
+  } while (0)
+
+#define SHASTA_CUDA(call)                                                       \
+  do {                                                                          \
+    cudaError_t e__ = (call);                                                   \
+    if (e__ != cudaSuccess) {                                                   \
+      shasta::set_error("%s failed: %s", #call, cudaGetErrorString(e__));       \
+      return (int)e__;                                                          \
+    }                                                                           \
+  } while (0)
+
+// ---- device helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Launchers implemented in the individual .cu files (host side, return 0 or a cudaError_t).
+int launch_pack(const shasta_params_t& p, float* packed, cudaStream_t s);
+int launch_bilinear(const float* im, int H, int W, int C, const float* xs, const float* ys, int n, float* out,
+                    cudaStream_t s);
+int launch_gather(const float* bev0, const float* boxes0, float* feat0, const float* bev1, const float* boxes1,
+                  float* feat1, int nframes, int box_stride, int B, int M, const shasta_geom_t& g,
+                  size_t feat_batch_stride, int variant, cudaStream_t s);
+int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
+                   const WsLayout& L, cudaStream_t s);
+int launch_project(const float* packed, int B, int M, float* ws, const WsLayout& L, float* det_boxes_inout,
+                   cudaStream_t s);
+int launch_pairwise(const float* packed, int B, int M, float* ws, const WsLayout& L, int variant,
+                    cudaStream_t s);
+int launch_aff_softmax(const float* packed, int B, int M, float* ws, const WsLayout& L, float* matched1,
+                       float* matched2, cudaStream_t s);
+int launch_decode(const float* m1, const float* m2, const int32_t* n_prev, const int32_t* n_det, int B, int M,
+                  int32_t* prev_state, int32_t* prev_argmax, float* fn_score, int32_t* det_state,
+                  int32_t* det_argmax, float* det_score, cudaStream_t s);
+
+}  // namespace shasta

@@ -1,0 +1,255 @@
+// Box-point bilinear gather.
+//
+// Restates, op for op in fp32 and without FMA contraction, what the reference does in
+//   det3d/models/tracker/shasta.py:143-159            (5 sample points per box)
+//   det3d/core/bbox/box_torch_ops.py:24-59,145-158,184-203 (corner math)
+//   det3d/models/second_stage/bird_eye_view.py:18-41   (metric -> pixel, 5-point regroup)
+//   det3d/core/utils/center_utils.py:92-121            (clamped bilinear interpolation)
+// Two samplers: (0) half-warp per point, four 16-byte LDGs per lane (each tap is one 256-byte channel run);
+// (1) the same taps staged into shared memory by cp.async.bulk (TMA bulk copies, one mbarrier per CTA).
+#include "common.cuh"
+
+namespace shasta {
+
+struct Taps {
+  int x0, x1, y0, y1;
+  float wa, wb, wc, wd;
+};
+
+// center_utils.py:100-119 — clamp first, then weights from the CLAMPED integers.
+__device__ __forceinline__ Taps make_taps(float x, float y, int H, int W) {
+  float fx = floorf(x), fy = floorf(y);
+  // keep the float->int conversion defined for far-out / NaN coordinates; after the clamp below the result is
+  // the same as the reference's int64 floor for every finite input
+  fx = (fx >= -2.0f) ? fminf(fx, (float)W + 1.0f) : -2.0f;
+  fy = (fy >= -2.0f) ? fminf(fy, (float)H + 1.0f) : -2.0f;
+  int x0 = (int)fx, y0 = (int)fy;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  Taps t;
+  t.x0 = min(max(x0, 0), W - 1);
+  t.x1 = min(max(x1, 0), W - 1);
+  t.y0 = min(max(y0, 0), H - 1);
+  t.y1 = min(max(y1, 0), H - 1);
+  const float dx1 = __fsub_rn((float)t.x1, x), dx0 = __fsub_rn(x, (float)t.x0);
+  const float dy1 = __fsub_rn((float)t.y1, y), dy0 = __fsub_rn(y, (float)t.y0);
+  t.wa = __fmul_rn(dx1, dy1);
+  t.wb = __fmul_rn(dx1, dy0);
+  t.wc = __fmul_rn(dx0, dy1);
+  t.wd = __fmul_rn(dx0, dy0);
+  return t;
+}
+
+// ((Ia*wa + Ib*wb) + Ic*wc) + Id*wd, separate multiplies and adds (center_utils.py:120).
+__device__ __forceinline__ float blend(float a, float b, float c, float d, const Taps& t) {
+  float r = __fadd_rn(__fmul_rn(a, t.wa), __fmul_rn(b, t.wb));
+  r = __fadd_rn(r, __fmul_rn(c, t.wc));
+  return __fadd_rn(r, __fmul_rn(d, t.wd));
+}
+
+__device__ __forceinline__ float4 blend4(float4 a, float4 b, float4 c, float4 d, const Taps& t) {
+  return make_float4(blend(a.x, b.x, c.x, d.x, t), blend(a.y, b.y, c.y, d.y, t), blend(a.z, b.z, c.z, d.z, t),
+                     blend(a.w, b.w, c.w, d.w, t));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage kernel: bilinear_interpolate_torch on explicit pixel coordinates, any C % 4 == 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void bilinear_kernel(const float* __restrict__ im, int H, int W, int C, const float* __restrict__ xs,
+                                const float* __restrict__ ys, int n, float* __restrict__ out) {
+  const int cq = C >> 2;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)n * cq) return;
+  const int pt = (int)(gid / cq), q = (int)(gid % cq);
+  const Taps t = make_taps(xs[pt], ys[pt], H, W);
+  const float4* base = reinterpret_cast<const float4*>(im);
+  const float4 a = __ldg(base + ((size_t)t.y0 * W + t.x0) * cq + q);
+  const float4 b = __ldg(base + ((size_t)t.y1 * W + t.x0) * cq + q);
+  const float4 c = __ldg(base + ((size_t)t.y0 * W + t.x1) * cq + q);
+  const float4 d = __ldg(base + ((size_t)t.y1 * W + t.x1) * cq + q);
+  reinterpret_cast<float4*>(out)[(size_t)pt * cq + q] = blend4(a, b, c, d, t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sample point p (0 centre, 1 front, 2 back, 3 left, 4 right) of a box, in BEV pixel coordinates.
+// ------------------------------------------------------------------------------------------------
+struct GatherJob {
+  const float* bev[2];
+  const float* boxes[2];
+  float* feat[2];
+};
+
+__device__ __forceinline__ void box_point_pixels(const float* __restrict__ bx, int p, const shasta_geom_t& g,
+                                                 float& xs, float& ys) {
+  const float cx = bx[0], cy = bx[1];
+  float px = cx, py = cy;
+  if (p != 0) {
+    const float w = bx[3], l = bx[4], yaw = bx[6];
+    const float s = sinf(yaw), c = cosf(yaw);
+    // clockwise corners from the minimum point: (-.5,-.5) (-.5,.5) (.5,.5) (.5,-.5)   box_torch_ops.py:43-57
+    // front = (c0+c1)/2, back = (c2+c3)/2, left = (c0+c3)/2, right = (c1+c2)/2          shasta.py:151-154
+    const int ia = (p == 1) ? 0 : (p == 2) ? 2 : (p == 3) ? 0 : 1;
+    const int ib = (p == 1) ? 1 : (p == 2) ? 3 : (p == 3) ? 3 : 2;
+    float rx[2], ry[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = e ? ib : ia;
+      const float nx = (k >= 2) ? 0.5f : -0.5f;
+      const float ny = (k == 1 || k == 2) ? 0.5f : -0.5f;
+      const float lx = __fmul_rn(w, nx), ly = __fmul_rn(l, ny);
+      // einsum('aij,jka->aik') with rot_mat_T = [[cos,-sin],[sin,cos]]      box_torch_ops.py:155-158
+      rx[e] = __fadd_rn(__fadd_rn(__fmul_rn(lx, c), __fmul_rn(ly, s)), cx);
+      ry[e] = __fadd_rn(__fadd_rn(__fmul_rn(lx, -s), __fmul_rn(ly, c)), cy);
+    }
+    px = __fmul_rn(__fadd_rn(rx[0], rx[1]), 0.5f);
+    py = __fmul_rn(__fadd_rn(ry[0], ry[1]), 0.5f);
+  }
+  // bird_eye_view.py:19-20: subtract, divide by the voxel size, divide by the stride (two true divisions)
+  xs = __fdiv_rn(__fdiv_rn(__fsub_rn(px, g.pc_start_x), g.voxel_x), g.out_stride);
+  ys = __fdiv_rn(__fdiv_rn(__fsub_rn(py, g.pc_start_y), g.voxel_y), g.out_stride);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Variant 0: half-warp per point, direct vector loads.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGatherThreads = 256;
+constexpr int kPointsPerCta0 = kGatherThreads / 16;
+
+__global__ void __launch_bounds__(kGatherThreads)
+gather_ldg_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, size_t feat_batch_stride) {
+  const int f = blockIdx.y;
+  const float* __restrict__ bev = job.bev[f];
+  const float* __restrict__ boxes = job.boxes[f];
+  float* __restrict__ feat = job.feat[f];
+  const int lane16 = threadIdx.x & 15;
+  const long long gp = (long long)blockIdx.x * kPointsPerCta0 + (threadIdx.x >> 4);
+  const long long total = (long long)B * M * 5;
+  if (gp >= total) return;
+  const int b = (int)(gp / (5 * M));
+  const int rem = (int)(gp % (5 * M));
+  const int m = rem / 5, p = rem % 5;
+  float xs, ys;
+  box_point_pixels(boxes + ((size_t)b * M + m) * box_stride, p, g, xs, ys);
+  const Taps t = make_taps(xs, ys, g.height, g.width);
+  const float4* base = reinterpret_cast<const float4*>(bev) + (size_t)b * g.height * g.width * (kC / 4);
+  const float4 a = __ldg(base + ((size_t)t.y0 * g.width + t.x0) * (kC / 4) + lane16);
+  const float4 bb = __ldg(base + ((size_t)t.y1 * g.width + t.x0) * (kC / 4) + lane16);
+  const float4 c = __ldg(base + ((size_t)t.y0 * g.width + t.x1) * (kC / 4) + lane16);
+  const float4 d = __ldg(base + ((size_t)t.y1 * g.width + t.x1) * (kC / 4) + lane16);
+  float4* dst = reinterpret_cast<float4*>(feat + (size_t)b * feat_batch_stride + (size_t)m * kF + p * kC);
+  dst[lane16] = blend4(a, bb, c, d, t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Variant 1: taps staged by cp.async.bulk (TMA bulk copy engine) into shared memory.
+// One CTA = 32 points = 128 bulk copies of 256 B, completion tracked by one mbarrier.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPointsPerCta1 = 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__global__ void __launch_bounds__(kGatherThreads)
+gather_bulk_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, size_t feat_batch_stride) {
+  __shared__ __align__(128) float s_taps[kPointsPerCta1][4][kC];  // 32 KB
+  __shared__ Taps s_t[kPointsPerCta1];
+  __shared__ long long s_dst[kPointsPerCta1];
+  __shared__ __align__(8) unsigned long long s_bar;
+
+  const int f = blockIdx.y;
+  const float* __restrict__ bev = job.bev[f];
+  const float* __restrict__ boxes = job.boxes[f];
+  float* __restrict__ feat = job.feat[f];
+  const long long total = (long long)B * M * 5;
+  const long long gp0 = (long long)blockIdx.x * kPointsPerCta1;
+  const int npts = (int)min((long long)kPointsPerCta1, total - gp0);
+  const uint32_t bar = smem_u32(&s_bar);
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                 "r"((uint32_t)(npts * 4 * kC * sizeof(float)))
+                 : "memory");
+  }
+  __syncthreads();
+
+  if (threadIdx.x < npts) {
+    const long long gp = gp0 + threadIdx.x;
+    const int b = (int)(gp / (5 * M));
+    const int rem = (int)(gp % (5 * M));
+    const int m = rem / 5, p = rem % 5;
+    float xs, ys;
+    box_point_pixels(boxes + ((size_t)b * M + m) * box_stride, p, g, xs, ys);
+    const Taps t = make_taps(xs, ys, g.height, g.width);
+    s_t[threadIdx.x] = t;
+    s_dst[threadIdx.x] = (long long)((size_t)b * feat_batch_stride + (size_t)m * kF + p * kC);
+    const float* base = bev + (size_t)b * g.height * g.width * kC;
+    const float* src[4] = {base + ((size_t)t.y0 * g.width + t.x0) * kC, base + ((size_t)t.y1 * g.width + t.x0) * kC,
+                           base + ((size_t)t.y0 * g.width + t.x1) * kC, base + ((size_t)t.y1 * g.width + t.x1) * kC};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(&s_taps[threadIdx.x][k][0])),
+          "l"(src[k]), "r"((uint32_t)(kC * sizeof(float))), "r"(bar)
+          : "memory");
+    }
+  }
+  __syncthreads();  // s_t / s_dst visible to everyone
+
+  // wait for all bulk copies of this CTA (phase 0)
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar)
+        : "memory");
+  }
+
+  for (int item = threadIdx.x; item < npts * 16; item += kGatherThreads) {
+    const int pt = item >> 4, q = item & 15;
+    const Taps t = s_t[pt];
+    const float4 a = reinterpret_cast<const float4*>(&s_taps[pt][0][0])[q];
+    const float4 bb = reinterpret_cast<const float4*>(&s_taps[pt][1][0])[q];
+    const float4 c = reinterpret_cast<const float4*>(&s_taps[pt][2][0])[q];
+    const float4 d = reinterpret_cast<const float4*>(&s_taps[pt][3][0])[q];
+    reinterpret_cast<float4*>(feat + s_dst[pt])[q] = blend4(a, bb, c, d, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+int launch_bilinear(const float* im, int H, int W, int C, const float* xs, const float* ys, int n, float* out,
+                    cudaStream_t s) {
+  if (n == 0) return 0;
+  const long long items = (long long)n * (C / 4);
+  const int threads = 256;
+  bilinear_kernel<<<(unsigned)((items + threads - 1) / threads), threads, 0, s>>>(im, H, W, C, xs, ys, n, out);
+  SHASTA_CHECK_LAUNCH("bilinear_kernel");
+  return 0;
+}
+
+int launch_gather(const float* bev0, const float* boxes0, float* feat0, const float* bev1, const float* boxes1,
+                  float* feat1, int nframes, int box_stride, int B, int M, const shasta_geom_t& g,
+                  size_t feat_batch_stride, int variant, cudaStream_t s) {
+  GatherJob job;
+  job.bev[0] = bev0, job.boxes[0] = boxes0, job.feat[0] = feat0;
+  job.bev[1] = bev1, job.boxes[1] = boxes1, job.feat[1] = feat1;
+  const long long total = (long long)B * M * 5;
+  if (total == 0) return 0;
+  if (variant == 1) {
+    dim3 grid((unsigned)((total + kPointsPerCta1 - 1) / kPointsPerCta1), nframes);
+    gather_bulk_kernel<<<grid, kGatherThreads, 0, s>>>(job, box_stride, B, M, g, feat_batch_stride);
+    SHASTA_CHECK_LAUNCH("gather_bulk_kernel");
+  } else {
+    dim3 grid((unsigned)((total + kPointsPerCta0 - 1) / kPointsPerCta0), nframes);
+    gather_ldg_kernel<<<grid, kGatherThreads, 0, s>>>(job, box_stride, B, M, g, feat_batch_stride);
+    SHASTA_CHECK_LAUNCH("gather_ldg_kernel");
+  }
+  return 0;
+}
+
+}  // namespace shasta

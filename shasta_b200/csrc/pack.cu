@@ -1,0 +1,74 @@
+// Kernel-side weight cache: transposed / split / padded copies of the small layers (see PackLayout in common.cuh).
+// The PyTorch parameters stay the source of truth in (out,in) layout (state_dict contract).
+#include "common.cuh"
+
+namespace shasta {
+
+// dst[k * dst_ld + j] = src[j * src_ld + k]   for j < nj (output rows of the Linear), k < nk (input columns)
+__global__ void transpose_block_kernel(float* __restrict__ dst, int dst_ld, const float* __restrict__ src, int src_ld,
+                                       int nj, int nk) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nj * nk) return;
+  const int k = (int)(idx / nj), j = (int)(idx % nj);
+  dst[(size_t)k * dst_ld + j] = src[(size_t)j * src_ld + k];
+}
+
+static int tblock(float* dst, int dst_ld, const float* src, int src_ld, int nj, int nk, cudaStream_t s) {
+  const long long n = (long long)nj * nk;
+  if (n == 0) return 0;
+  transpose_block_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, dst_ld, src, src_ld, nj, nk);
+  SHASTA_CHECK_LAUNCH("transpose_block_kernel");
+  return 0;
+}
+
+#define TB(...)                       \
+  do {                                \
+    int rc__ = tblock(__VA_ARGS__);   \
+    if (rc__) return rc__;            \
+  } while (0)
+
+int launch_pack(const shasta_params_t& p, float* packed, cudaStream_t s) {
+  const int M = p.max_obj, D = M + 2;
+  const PackLayout P = pack_layout(M);
+  SHASTA_CUDA(cudaMemsetAsync(packed, 0, P.total * sizeof(float), s));
+  const int FS_IN = 2 * kF;            // 640
+  const int RC_IN = 2 * kF + 2 * kNF;  // 646
+  // first layer, shape-feature columns                                          shasta.py:60,87
+  TB(packed + P.p1_prev + 0, kProjShape, p.fuse_shape_w[0] + 0, FS_IN, 40, kF, s);
+  TB(packed + P.p1_prev + 40, kProjShape, p.res_coeff_w[0] + 0, RC_IN, 72, kF, s);
+  TB(packed + P.p1_cur + 0, kProjShape, p.fuse_shape_w[0] + kF, FS_IN, 40, kF, s);
+  TB(packed + P.p1_cur + 40, kProjShape, p.res_coeff_w[0] + kF + kNF, RC_IN, 72, kF, s);
+  // first layer, box columns: res_coeff.0 [320:323] / [643:646]; fuse_det.0 [0:3] / [3:6]     shasta.py:79,87,310-312
+  TB(packed + P.pb_prev + 40, kProj, p.res_coeff_w[0] + kF, RC_IN, 72, kNF, s);
+  TB(packed + P.pb_prev + 112, kProj, p.fuse_det_w[0] + 0, 2 * kNF, 32, kNF, s);
+  TB(packed + P.pb_cur + 40, kProj, p.res_coeff_w[0] + 2 * kF + kNF, RC_IN, 72, kNF, s);
+  TB(packed + P.pb_cur + 112, kProj, p.fuse_det_w[0] + kNF, 2 * kNF, 32, kNF, s);
+  TB(packed + P.pbias + 0, kProj, p.fuse_shape_b[0], 1, 40, 1, s);
+  TB(packed + P.pbias + 40, kProj, p.res_coeff_b[0], 1, 72, 1, s);
+  TB(packed + P.pbias + 112, kProj, p.fuse_det_b[0], 1, 32, 1, s);
+  // second / third / fourth pairwise layers
+  TB(packed + P.l2a, 20, p.fuse_shape_w[1], 40, 20, 40, s);
+  TB(packed + P.l2a_b, 20, p.fuse_shape_b[1], 1, 20, 1, s);
+  TB(packed + P.l2b, 20, p.res_coeff_w[1], 72, 18, 72, s);
+  TB(packed + P.l2b_b, 20, p.res_coeff_b[1], 1, 18, 1, s);
+  TB(packed + P.l2c, 8, p.fuse_det_w[1], 32, 8, 32, s);
+  TB(packed + P.l2c_b, 8, p.fuse_det_b[1], 1, 8, 1, s);
+  TB(packed + P.l3a, 12, p.fuse_shape_w[2], 20, 10, 20, s);
+  TB(packed + P.l3a_b, 12, p.fuse_shape_b[2], 1, 10, 1, s);
+  TB(packed + P.l4a, 1, p.fuse_shape_w[3], 10, 1, 10, s);    // (1,10) -> [10]
+  TB(packed + P.l4a_b, 4, p.fuse_shape_b[3], 1, 1, 1, s);
+  TB(packed + P.l3b, 4, p.res_coeff_w[2], 18, 3, 18, s);
+  TB(packed + P.l3b_b, 4, p.res_coeff_b[2], 1, 3, 1, s);
+  TB(packed + P.l3c, 1, p.fuse_det_w[2], 8, 1, 8, s);        // (1,8) -> [8]
+  TB(packed + P.l3c_b, 4, p.fuse_det_b[2], 1, 1, 1, s);
+  // aff, transposed to [in][out]                                               shasta.py:94-106
+  const int win[6] = {D, 128, 64, 32, 64, 128};
+  const int wout[6] = {128, 64, 32, 64, 128, D};
+  for (int i = 0; i < 6; ++i) {
+    TB(packed + P.aff_w[i], wout[i], p.aff_w[i], win[i], wout[i], win[i], s);
+    TB(packed + P.aff_b[i], wout[i], p.aff_b[i], 1, wout[i], 1, s);
+  }
+  return 0;
+}
+
+}  // namespace shasta

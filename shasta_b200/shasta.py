@@ -1,0 +1,285 @@
+"""``Shasta`` — the affinity head behind the reference's TRACK registry (det3d/models/tracker/shasta.py:9-327).
+
+Drop-in contract kept: class name, constructor arguments, sub-module construction through the
+builder, parameter / state_dict names in PyTorch ``(out, in)`` layout, ``forward(example, train_mode=True)`` returning
+``(matched1 (B,M,M+2), matched2 (B,M+2,M), example)``, the in-place back-projection of ``example["det_boxes"]``,
+``example['bev_feature']`` and the ``newborn / fp / dead_trk / fn`` attributes.
+
+What changed is everything under ``forward``: from the 64-channel channels-last BEV maps onward the path is five
+hand-written CUDA kernels (gather, anchors, per-object projections, pairwise tiles, aff + dual softmax) reached
+through the C ABI in ``include/shasta_b200.h``. There is no PyTorch/CPU fallback for that part.
+"""
+import ctypes
+
+import torch
+from torch import nn
+
+from . import _cabi
+from . import registry as builder
+from .registry import TRACK
+
+FLAG_TMA_GATHER = 1
+PAIRWISE_FFMA, PAIRWISE_TF32X3, PAIRWISE_BF16 = 0, 1, 2
+
+
+class _Workspace:
+    """Per-(device, batch) scratch the kernels carve into regions (see enum shasta_region)."""
+
+    def __init__(self, batch, max_obj, device):
+        lib = _cabi.lib()
+        self.batch, self.max_obj = batch, max_obj
+        self.nbytes = lib.shasta_workspace_bytes(batch, max_obj)
+        self.buf = torch.empty(max(self.nbytes // 4, 1), dtype=torch.float32, device=device)
+
+    def region(self, rid, numel):
+        off = _cabi.lib().shasta_workspace_offset(self.batch, self.max_obj, rid)
+        return self.buf[off:off + numel]
+
+
+@TRACK.register_module
+class Shasta(nn.Module):
+    def __init__(
+        self,
+        reader,
+        backbone,
+        neck,
+        bev_extractor,
+        train_cfg=None,
+        test_cfg=None,
+        pretrained=None,
+        max_obj=100,
+        num_feats=7,
+        in_channels=512,
+        share_conv_channel=64,
+        num_point=5,
+    ):
+        super().__init__()
+        if num_point != 5 or share_conv_channel != 64:
+            raise NotImplementedError(
+                "shasta_b200 implements num_point=5, share_conv_channel=64 (every shipped config); got "
+                "num_point=%r share_conv_channel=%r" % (num_point, share_conv_channel))
+        if num_feats != 3:
+            raise NotImplementedError(
+                "shasta_b200 implements num_feats=3 (configs/nusc/*.py); got %r" % (num_feats,))
+        # frozen CenterPoint trunk: built through the registry exactly like the reference (shasta.py:28-31);
+        # it is outside this package, a cfg of None leaves the slot empty
+        self.reader = builder.build_reader(reader) if reader is not None else None
+        self.backbone = builder.build_backbone(backbone) if backbone is not None else None
+        self.neck = builder.build_neck(neck) if neck is not None else None
+        self.bev_extractor = builder.build_second_stage_module(bev_extractor)
+
+        self.train_cfg = train_cfg
+        self.test_cfg = test_cfg
+        self.num_feats = num_feats
+        self.max_obj = max_obj
+        self.num_point = num_point
+
+        # ---- parameters: identical module tree => identical state_dict keys (shasta.py:42-106) ----
+        self.shared_conv = nn.Sequential(
+            nn.Conv2d(in_channels, share_conv_channel, kernel_size=3, padding=1, bias=True),
+            nn.BatchNorm2d(share_conv_channel),
+            nn.ReLU(inplace=True),
+        )
+        F = share_conv_channel * num_point
+        self.aug_shape_input = max_obj * F
+        self.aug_shape_output = F
+
+        def mlp(widths):
+            layers = []
+            for i in range(len(widths) - 1):
+                layers.append(nn.Linear(widths[i], widths[i + 1]))
+                if i + 2 < len(widths):
+                    layers.append(nn.ReLU(inplace=True))
+            return nn.Sequential(*layers)
+
+        self.aug_shape = nn.ModuleList([mlp([max_obj * F, (max_obj * F) // 64, F]) for _ in range(4)])
+        self.fuse_shape = mlp([2 * F, F // 8, F // 16, F // 32, 1])
+        self.aug_input = max_obj * 7
+        self.aug_dets = nn.ModuleList([mlp([max_obj * 7, (max_obj * 7) // 32, 7]) for _ in range(4)])
+        self.fuse_det = mlp([num_feats * 2, 32, 8, 1])
+        self.res_coeff = mlp([num_feats * 2 + 2 * F, 32 + F // 8, 8 + F // 32, 3])
+        self.aff = mlp([max_obj + 2, 128, 64, 32, 64, 128, max_obj + 2])
+        self.softmax1 = nn.Softmax(dim=2)  # kept for module-tree parity; the kernels do both softmaxes
+        self.softmax2 = nn.Softmax(dim=1)
+
+        self.init_weights(pretrained=pretrained)
+
+        # kernel-side state (never part of the state_dict)
+        self.kernel_flags = 0
+        self._packed = None
+        self._pack_key = None
+        self._cparams = None
+        self._ws = {}
+
+    # ------------------------------------------------------------------------------------------
+    def init_weights(self, pretrained=None):
+        """shasta.py:111-119: best-effort load, failures are printed and ignored."""
+        if pretrained is None:
+            return
+        try:
+            checkpoint = torch.load(pretrained, map_location="cpu")
+            load_matching_state_dict(self, checkpoint.get("state_dict", checkpoint))
+            print("init weight from {}".format(pretrained))
+        except Exception:  # noqa: BLE001 - reference behaviour
+            print("no pretrained model at {}".format(pretrained))
+
+    @property
+    def with_neck(self):
+        return getattr(self, "neck", None) is not None
+
+    def extract_feat(self, data):
+        """shasta.py:164-210 — the frozen spconv trunk; not part of this package. Callers either provide the
+        64-channel maps in ``example`` or attach a trunk (reader/backbone/neck) that yields (B,512,H,W) maps."""
+        if self.backbone is None:
+            raise RuntimeError(
+                "Shasta.extract_feat: no trunk attached; put 'bev_feature' and 'prev_bev_feature' (B,H,W,64) into "
+                "the example or build the model with reader/backbone/neck configs")
+        feats = self.reader(data["voxels"], data["num_points"])
+        prev_feats = self.reader(data["prev_voxels"], data["prev_num_points"])
+        x, vf = self.backbone(feats, data["coordinates"], len(data["points"]), data["shape"][0])
+        px, pvf = self.backbone(prev_feats, data["prev_coordinates"], len(data["prev_points"]), data["prev_shape"][0])
+        if self.with_neck:
+            x, px = self.neck(x), self.neck(px)
+        return x, vf, px, pvf
+
+    # ------------------------------------------------------------------------------------------
+    def _head_params(self):
+        seqs = [("aug_shape", self.aug_shape, (0, 2)), ("aug_dets", self.aug_dets, (0, 2))]
+        out = {}
+        for name, mods, idxs in seqs:
+            for i in range(4):
+                for li in idxs:
+                    out["%s.%d.%d" % (name, i, li)] = mods[i][li]
+        for name, seq, idxs in (("fuse_shape", self.fuse_shape, (0, 2, 4, 6)), ("fuse_det", self.fuse_det, (0, 2, 4)),
+                                ("res_coeff", self.res_coeff, (0, 2, 4)), ("aff", self.aff, (0, 2, 4, 6, 8, 10))):
+            for li in idxs:
+                out["%s.%d" % (name, li)] = seq[li]
+        return out
+
+    def _ensure_packed(self, device):
+        layers = self._head_params()
+        key = tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version)
+                    for l in layers.values())
+        if key == self._pack_key and self._packed is not None and self._packed.device == device:
+            return
+        lib = _cabi.lib()
+        for name, l in layers.items():
+            for t in (l.weight, l.bias):
+                if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise _cabi.ShastaLibraryError(
+                        "parameter %s must be a contiguous float32 tensor on %s (got %s %s)" %
+                        (name, device, t.dtype, t.device))
+        p = _cabi.ShastaParams()
+        p.max_obj, p.num_feats = self.max_obj, self.num_feats
+        for i in range(4):
+            p.aug_shape_w0[i] = layers["aug_shape.%d.0" % i].weight.data_ptr()
+            p.aug_shape_b0[i] = layers["aug_shape.%d.0" % i].bias.data_ptr()
+            p.aug_shape_w2[i] = layers["aug_shape.%d.2" % i].weight.data_ptr()
+            p.aug_shape_b2[i] = layers["aug_shape.%d.2" % i].bias.data_ptr()
+            p.aug_dets_w0[i] = layers["aug_dets.%d.0" % i].weight.data_ptr()
+            p.aug_dets_b0[i] = layers["aug_dets.%d.0" % i].bias.data_ptr()
+            p.aug_dets_w2[i] = layers["aug_dets.%d.2" % i].weight.data_ptr()
+            p.aug_dets_b2[i] = layers["aug_dets.%d.2" % i].bias.data_ptr()
+        for n, li in enumerate((0, 2, 4, 6)):
+            p.fuse_shape_w[n] = layers["fuse_shape.%d" % li].weight.data_ptr()
+            p.fuse_shape_b[n] = layers["fuse_shape.%d" % li].bias.data_ptr()
+        for n, li in enumerate((0, 2, 4)):
+            p.fuse_det_w[n] = layers["fuse_det.%d" % li].weight.data_ptr()
+            p.fuse_det_b[n] = layers["fuse_det.%d" % li].bias.data_ptr()
+            p.res_coeff_w[n] = layers["res_coeff.%d" % li].weight.data_ptr()
+            p.res_coeff_b[n] = layers["res_coeff.%d" % li].bias.data_ptr()
+        for n, li in enumerate((0, 2, 4, 6, 8, 10)):
+            p.aff_w[n] = layers["aff.%d" % li].weight.data_ptr()
+            p.aff_b[n] = layers["aff.%d" % li].bias.data_ptr()
+        nbytes = lib.shasta_packed_weight_bytes(self.max_obj, self.num_feats)
+        packed = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            rc = lib.shasta_pack_weights(ctypes.byref(p), packed.data_ptr(), nbytes,
+                                         ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+        _cabi.check(rc, "shasta_pack_weights")
+        self._packed, self._pack_key, self._cparams = packed, key, p
+
+    def _workspace(self, batch, device):
+        k = (batch, device)
+        ws = self._ws.get(k)
+        if ws is None:
+            if len(self._ws) > 8:
+                self._ws.clear()
+            ws = self._ws[k] = _Workspace(batch, self.max_obj, device)
+        return ws
+
+    # ------------------------------------------------------------------------------------------
+    def affinity(self, bev, prev_bev, det_boxes, prev_det_boxes):
+        """Hot path from the channels-last maps: (B,H,W,64) x2, (B,M,11) x2 -> matched1, matched2.
+        ``det_boxes[:, :, :2]`` is back-projected in place (shasta.py:270)."""
+        for name, t in (("bev_feature", bev), ("prev_bev_feature", prev_bev), ("det_boxes", det_boxes),
+                        ("prev_det_boxes", prev_det_boxes)):
+            if not t.is_cuda:
+                raise _cabi.ShastaLibraryError("%s must be a CUDA tensor: shasta_b200 has no CPU path" % name)
+            if t.dtype != torch.float32:
+                raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+        device = bev.device
+        B, H, W, C = bev.shape
+        M = self.max_obj
+        if C != 64 or prev_bev.shape != bev.shape:
+            raise ValueError("bev maps must both be (B,H,W,64); got %s / %s" % (tuple(bev.shape), tuple(prev_bev.shape)))
+        if tuple(det_boxes.shape) != (B, M, 11) or tuple(prev_det_boxes.shape) != (B, M, 11):
+            raise ValueError("boxes must be (B=%d, max_obj=%d, 11); got %s / %s" %
+                             (B, M, tuple(det_boxes.shape), tuple(prev_det_boxes.shape)))
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            from .training import affinity_with_grad  # built on the same kernels (forward) + backward kernels
+            return affinity_with_grad(self, bev, prev_bev, det_boxes, prev_det_boxes)
+        bev = bev if bev.is_contiguous() else bev.contiguous()
+        prev_bev = prev_bev if prev_bev.is_contiguous() else prev_bev.contiguous()
+        prev_c = prev_det_boxes if prev_det_boxes.is_contiguous() else prev_det_boxes.contiguous()
+        det_c = det_boxes if det_boxes.is_contiguous() else det_boxes.contiguous()
+
+        lib = _cabi.lib()
+        self._ensure_packed(device)
+        ws = self._workspace(B, device)
+        m1 = torch.empty((B, M, M + 2), dtype=torch.float32, device=device)
+        m2 = torch.empty((B, M + 2, M), dtype=torch.float32, device=device)
+        geom = self.bev_extractor.geom(H, W)
+        with torch.cuda.device(device):
+            rc = lib.shasta_forward_f32(
+                ctypes.byref(self._cparams), self._packed.data_ptr(), bev.data_ptr(), prev_bev.data_ptr(),
+                det_c.data_ptr(), prev_c.data_ptr(), B, ctypes.byref(geom), ws.buf.data_ptr(), ws.nbytes,
+                m1.data_ptr(), m2.data_ptr(), int(self.kernel_flags),
+                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+        _cabi.check(rc, "shasta_forward_f32")
+        if det_c is not det_boxes:
+            det_boxes[:, :, :2] = det_c[:, :, :2]
+        anchors = ws.region(_cabi.WS_ANCHOR_BOX, B * 4 * 7).view(B, 4, 7)
+        self.newborn, self.fp = anchors[:, 0:1, :], anchors[:, 1:2, :]
+        self.dead_trk, self.fn = anchors[:, 2:3, :], anchors[:, 3:4, :]
+        return m1, m2
+
+    def forward(self, example, train_mode=True, **kwargs):
+        """shasta.py:213-327. ``example`` needs ``det_boxes`` and ``prev_det_boxes`` (B,M,11) and either the
+        precomputed channels-last maps (``bev_feature`` + ``prev_bev_feature``, the metric's timed-region entry)
+        or inputs for an attached trunk."""
+        if "bev_feature" in example and "prev_bev_feature" in example:
+            bev, prev_bev = example["bev_feature"], example["prev_bev_feature"]
+        else:
+            bev_map, _, prev_bev_map, _ = self.extract_feat(example)
+            bev = self.shared_conv(bev_map).permute(0, 2, 3, 1).contiguous()
+            prev_bev = self.shared_conv(prev_bev_map).permute(0, 2, 3, 1).contiguous()
+            example["bev_feature"] = bev
+        matched1, matched2 = self.affinity(bev, prev_bev, example["det_boxes"], example["prev_det_boxes"])
+        return matched1, matched2, example
+
+
+def load_matching_state_dict(module, state_dict):
+    """det3d/torchie/trainer/checkpoint.py:67-107 semantics: copy tensors whose name AND shape match, skip the
+    rest silently; returns the list of skipped keys."""
+    own = module.state_dict()
+    skipped = []
+    with torch.no_grad():
+        for name, value in state_dict.items():
+            if name.startswith("module."):
+                name = name[len("module."):]
+            if name in own and tuple(own[name].shape) == tuple(value.shape):
+                own[name].copy_(value)
+            else:
+                skipped.append(name)
+    return skipped
