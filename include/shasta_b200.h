@@ -33,6 +33,12 @@ extern "C" {
 #define SHASTA_ERR_ALIGN (-3)
 #define SHASTA_ERR_SIZE (-4)
 
+#if defined(__GNUC__)
+#define SHASTA_API __attribute__((visibility("default")))
+#else
+#define SHASTA_API
+#endif
+
 typedef void* shasta_stream_t;
 
 /* Device pointers to the head's parameters in PyTorch (out_features, in_features) row-major layout, i.e.
@@ -95,37 +101,37 @@ enum shasta_region {
   SHASTA_WS_NUM_REGIONS = 13
 };
 
-int shasta_abi_version(void);
-const char* shasta_last_error_string(void);
+SHASTA_API int shasta_abi_version(void);
+SHASTA_API const char* shasta_last_error_string(void);
 
 /* Number of kernels the last shasta_forward_f32 call of this thread enqueued (bench.py's gpu_launches). */
-int shasta_last_launch_count(void);
+SHASTA_API int shasta_last_launch_count(void);
 
-size_t shasta_packed_weight_bytes(int max_obj, int num_feats);
-size_t shasta_workspace_bytes(int batch, int max_obj);
+SHASTA_API size_t shasta_packed_weight_bytes(int max_obj, int num_feats);
+SHASTA_API size_t shasta_workspace_bytes(int batch, int max_obj);
 /* Float offset of a region inside the workspace, or (size_t)-1 for a bad region id. */
-size_t shasta_workspace_offset(int batch, int max_obj, int region);
+SHASTA_API size_t shasta_workspace_offset(int batch, int max_obj, int region);
 /* Row strides used inside the workspace: DP (PROJ_CUR) and RS (RESIDUAL/LOGITS). */
-int shasta_proj_cur_stride(int max_obj);
-int shasta_row_stride(int max_obj);
-int shasta_hidden_splits(int max_obj);
+SHASTA_API int shasta_proj_cur_stride(int max_obj);
+SHASTA_API int shasta_row_stride(int max_obj);
+SHASTA_API int shasta_hidden_splits(int max_obj);
 
 /* Repack the small layers into the kernel-side cache `packed` (first-layer weights split per side and
  * transposed k-major, block-diagonal second layer, transposed aff). The four big aug_shape.i.0 matrices are
  * NOT copied: kernels stream them in place from `params`. Must be re-run when parameters change. */
-int shasta_pack_weights(const shasta_params_t* host_params, float* packed, size_t packed_bytes,
+SHASTA_API int shasta_pack_weights(const shasta_params_t* host_params, float* packed, size_t packed_bytes,
                         shasta_stream_t stream);
 
 /* center_utils.py:92-121 bilinear_interpolate_torch: im (H,W,C), xs/ys (n) pixel coordinates -> out (n,C).
  * Bit-exact restatement (clamped taps, weights from clamped ints, ((a+b)+c)+d without FMA). C % 4 == 0. */
-int shasta_bilinear_f32(const float* im, int height, int width, int channels, const float* xs,
+SHASTA_API int shasta_bilinear_f32(const float* im, int height, int width, int channels, const float* xs,
                         const float* ys, int n, float* out, shasta_stream_t stream);
 
 /* shasta.py:121-161 get_box_center (num_point = 5) + bird_eye_view.py:18-41 BEVFeatureExtractor.forward for one
  * frame: bev (B,H,W,64), boxes (B,M,box_stride>=7) [x,y,z,w,l,h,yaw,..] -> feat rows [0,M) of a (B,*,320)
  * array whose batch stride is feat_batch_stride floats. variant: 0 = vectorised LDG sampler,
  * 1 = cp.async.bulk (TMA) shared-memory-staged sampler. */
-int shasta_gather_f32(const float* bev, const float* boxes, int box_stride, int batch, int max_obj,
+SHASTA_API int shasta_gather_f32(const float* bev, const float* boxes, int box_stride, int batch, int max_obj,
                       const shasta_geom_t* host_geom, float* feat, size_t feat_batch_stride, int variant,
                       shasta_stream_t stream);
 
@@ -133,35 +139,42 @@ int shasta_gather_f32(const float* bev, const float* boxes, int box_stride, int 
  * aug_dets.i(flat boxes), the back-projected copy of the current boxes and the augmented (B,T,*) arrays.
  * Reads FEAT_* rows [0,M) from the workspace; writes FEAT_* rows M,M+1, BOX_*, ANCHOR_BOX.
  * det_boxes / prev_det_boxes are the raw (B,M,11) inputs and are NOT modified here. */
-int shasta_anchors_f32(const shasta_params_t* host_params, const float* det_boxes,
+SHASTA_API int shasta_anchors_f32(const shasta_params_t* host_params, const float* det_boxes,
                        const float* prev_det_boxes, int batch, float* workspace, shasta_stream_t stream);
 
 /* First layers of fuse_shape / res_coeff / fuse_det decomposed per object (shasta.py:286-316 without the
  * T x D x 640/646 tensors): PROJ_PREV[t] = W1[:, prev part] . [f_prev[t]; box_prev[t,:3]],
  * PROJ_CUR[d] = W1[:, cur part] . [f_cur[d]; box_cur[d,:3]] + b1; plus AUX_*, COLNORM, and the in-place
  * back-projection of det_boxes[:,:,:2] (shasta.py:270) when det_boxes_inout != NULL. */
-int shasta_project_f32(const float* packed, int batch, int max_obj, float* workspace,
+SHASTA_API int shasta_project_f32(const float* packed, int batch, int max_obj, float* workspace,
                        float* det_boxes_inout, shasta_stream_t stream);
 
 /* Per-pair work (shasta.py:277-319): on-chip outer sum + ReLU, layers 2.. of the three pairwise MLPs,
  * hand-designed residuals, weighted sum -> RESIDUAL (B,T,RS). variant 0 = fp32 CUDA-core tiles,
  * 1 = tcgen05 3xTF32 tensor-core tiles (fp32-equivalent), 2 = tcgen05 bf16 tiles. */
-int shasta_pairwise_f32(const float* packed, int batch, int max_obj, float* workspace, int variant,
+SHASTA_API int shasta_pairwise_f32(const float* packed, int batch, int max_obj, float* workspace, int variant,
                         shasta_stream_t stream);
 
 /* shasta.py:323-325: aff row-MLP over D, then matched1 = softmax over D of rows [0,M) -> (B,M,M+2) and
  * matched2 = softmax over T of columns [0,M) -> (B,M+2,M). */
-int shasta_aff_softmax_f32(const float* packed, int batch, int max_obj, float* workspace, float* matched1,
+SHASTA_API int shasta_aff_softmax_f32(const float* packed, int batch, int max_obj, float* workspace, float* matched1,
                            float* matched2, shasta_stream_t stream);
 
 /* Whole path, shasta.py:231-325 from the 64-channel channels-last maps: bev/prev_bev (B,H,W,64),
  * det_boxes/prev_det_boxes (B,M,11). det_boxes[:,:,:2] is back-projected IN PLACE like the reference.
  * Outputs matched1 (B,M,M+2), matched2 (B,M+2,M); the anchors stay in the workspace (ANCHOR_BOX).
- * flags: bit0 = TMA-staged gather, bits 4-7 = pairwise variant. */
-int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, const float* bev,
+ * flags: bit0 = TMA-staged gather, bits 4-7 = pairwise variant, bit8 = record per-kernel events (profiling). */
+SHASTA_API int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, const float* bev,
                        const float* prev_bev, float* det_boxes, const float* prev_det_boxes, int batch,
                        const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes,
                        float* matched1, float* matched2, uint32_t flags, shasta_stream_t stream);
+
+/* Per-kernel timing for the roofline report (no reference counterpart). After shasta_profile_begin(n), every
+ * shasta_forward_f32 call with flag bit 8 (0x100) records CUDA events between its kernels (up to n calls);
+ * shasta_profile_end synchronises on them and returns the mean milliseconds of the 7 kernels in launch order:
+ * gather, anchor_hidden, anchor_finish, project, pairwise, aff_row, col_softmax. */
+SHASTA_API int shasta_profile_begin(int max_steps);
+SHASTA_API int shasta_profile_end(float* host_stage_ms, int* host_steps);
 
 /* tools/nusc_shasta/eval.py:126-181 decode on the device, one thread block per frame pair: row/column argmax
  * over the valid region + the two anchor entries and the 0.5 / 0.7 thresholds.
@@ -172,7 +185,7 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
  *                     det_argmax indexes the KEPT previous rows followed by newborn, fp (as the reference's
  *                     matched_dets does)
  *   det_score  (B,M) float: 1 - P(fp)   (ref_detection_score) */
-int shasta_decode_f32(const float* matched1, const float* matched2, const int32_t* n_prev,
+SHASTA_API int shasta_decode_f32(const float* matched1, const float* matched2, const int32_t* n_prev,
                       const int32_t* n_det, int batch, int max_obj, int32_t* prev_state,
                       int32_t* prev_argmax, float* fn_score, int32_t* det_state, int32_t* det_argmax,
                       float* det_score, shasta_stream_t stream);

@@ -75,6 +75,8 @@ SYMBOLS = {
     "shasta_aff_softmax_f32": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "shasta_forward_f32": (_i, [ctypes.POINTER(ShastaParams), _vp, _vp, _vp, _vp, _vp, _i,
                                 ctypes.POINTER(ShastaGeom), _vp, _sz, _vp, _vp, _u32, _vp]),
+    "shasta_profile_begin": (_i, [_i]),
+    "shasta_profile_end": (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "shasta_decode_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -150,7 +150,7 @@ col_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __rest
 }
 
 int launch_aff_softmax(const float* packed, int B, int M, float* ws, const WsLayout& L, float* matched1,
-                       float* matched2, cudaStream_t s) {
+                       float* matched2, cudaStream_t s, cudaEvent_t mid) {
   const PackLayout P = pack_layout(M);
   const int T = M + 2;
   const size_t smem = sizeof(float) * ((size_t)T + 256) * kAffRows;
@@ -163,6 +163,7 @@ int launch_aff_softmax(const float* packed, int B, int M, float* ws, const WsLay
   aff_row_kernel<<<(unsigned)((nrows + kAffRows - 1) / kAffRows), kAffThreads, smem, s>>>(
       packed, P, B, M, ws + L.off[SHASTA_WS_RESIDUAL], ws + L.off[SHASTA_WS_LOGITS], matched1);
   SHASTA_CHECK_LAUNCH("aff_row_kernel");
+  if (mid) cudaEventRecord(mid, s);
   dim3 grid((M + 31) / 32, B), block(32, 8);
   col_softmax_kernel<<<grid, block, 0, s>>>(B, M, ws + L.off[SHASTA_WS_LOGITS], matched2);
   SHASTA_CHECK_LAUNCH("col_softmax_kernel");

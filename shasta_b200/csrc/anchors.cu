@@ -228,7 +228,7 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
 
 // ------------------------------------------------------------------------------------------------
 int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
-                   const WsLayout& L, cudaStream_t s) {
+                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid) {
   const int M = p.max_obj;
   const int S = hidden_splits(M);
   const int N5 = 5 * M;
@@ -239,7 +239,7 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   AnchorW0 w;
   for (int i = 0; i < 4; ++i) w.w0[i] = p.aug_shape_w0[i];
   dim3 grid(S, (N5 + kAnchorRowsPerCta - 1) / kAnchorRowsPerCta, 4);
-  if (B >= 8 || B > 4)
+  if (B > 4)
     anchor_hidden_kernel<8><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
   else if (B > 2)
     anchor_hidden_kernel<4><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
@@ -248,6 +248,7 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   else
     anchor_hidden_kernel<1><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
   SHASTA_CHECK_LAUNCH("anchor_hidden_kernel");
+  if (mid) cudaEventRecord(mid, s);
 
   AnchorFinishArgs a;
   for (int i = 0; i < 4; ++i) {

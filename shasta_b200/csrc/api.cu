@@ -17,6 +17,19 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- optional per-stage timing (bench.py's live roofline measurement) ---------------------------
+constexpr int kStages = 7;  // gather, anchor_hidden, anchor_finish, project, pairwise, aff_row, col_softmax
+struct Profile {
+  cudaEvent_t* ev = nullptr;  // [max_steps][kStages + 1]
+  int max_steps = 0, steps = 0;
+};
+static Profile g_prof;
+
+cudaEvent_t* profile_slot() {
+  if (g_prof.ev == nullptr || g_prof.steps >= g_prof.max_steps) return nullptr;
+  return g_prof.ev + (size_t)(g_prof.steps++) * (kStages + 1);
+}
+
 static int check_dims(int batch, int max_obj) {
   if (batch < 0 || batch > 65535) {
     set_error("batch %d out of range [0, 65535]", batch);
@@ -172,7 +185,7 @@ int shasta_anchors_f32(const shasta_params_t* host_params, const float* det_boxe
   ALIGNED16(workspace);
   if (batch == 0) return 0;
   return launch_anchors(*host_params, det_boxes, prev_det_boxes, batch, workspace,
-                        ws_layout(batch, host_params->max_obj), (cudaStream_t)stream);
+                        ws_layout(batch, host_params->max_obj), (cudaStream_t)stream, nullptr);
 }
 
 int shasta_project_f32(const float* packed, int batch, int max_obj, float* workspace, float* det_boxes_inout,
@@ -213,7 +226,7 @@ int shasta_aff_softmax_f32(const float* packed, int batch, int max_obj, float* w
   ALIGNED16(workspace);
   if (batch == 0) return 0;
   return launch_aff_softmax(packed, batch, max_obj, workspace, ws_layout(batch, max_obj), matched1, matched2,
-                            (cudaStream_t)stream);
+                            (cudaStream_t)stream, nullptr);
 }
 
 int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, const float* bev,
@@ -249,19 +262,69 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
   cudaStream_t s = (cudaStream_t)stream;
   const WsLayout L = ws_layout(batch, M);
   const size_t fstride = (size_t)(M + 2) * kF;
+  cudaEvent_t* ev = (flags & 0x100u) ? profile_slot() : nullptr;
+#define STAGE_MARK(i) \
+  if (ev) cudaEventRecord(ev[i], s)
+  STAGE_MARK(0);
   // a1-a2: both frames in one launch (blockIdx.y selects the frame)
   rc = launch_gather(bev, det_boxes, workspace + L.off[SHASTA_WS_FEAT_CUR], prev_bev, prev_det_boxes,
                      workspace + L.off[SHASTA_WS_FEAT_PREV], 2, 11, batch, M, *host_geom, fstride, (int)(flags & 1u), s);
   if (rc) return rc;
-  rc = launch_anchors(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, s);  // a3-a4
+  STAGE_MARK(1);
+  rc = launch_anchors(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, s, ev ? ev[2] : nullptr);  // a3-a4
   if (rc) return rc;
+  STAGE_MARK(3);
   rc = launch_project(packed, batch, M, workspace, L, det_boxes, s);  // first layers, aux, colnorm, back-projection
   if (rc) return rc;
+  STAGE_MARK(4);
   rc = launch_pairwise(packed, batch, M, workspace, L, (int)((flags >> 4) & 15u), s);  // a5-a9
   if (rc) return rc;
-  rc = launch_aff_softmax(packed, batch, M, workspace, L, matched1, matched2, s);  // a10-a11
+  STAGE_MARK(5);
+  rc = launch_aff_softmax(packed, batch, M, workspace, L, matched1, matched2, s, ev ? ev[6] : nullptr);  // a10-a11
   if (rc) return rc;
+  STAGE_MARK(7);
+#undef STAGE_MARK
   g_last_forward_launches = g_launch_count;
+  return 0;
+}
+
+int shasta_profile_begin(int max_steps) {
+  if (max_steps < 1 || max_steps > 4096) {
+    set_error("profile: max_steps out of range");
+    return SHASTA_ERR_ARG;
+  }
+  if (g_prof.ev) {
+    for (int i = 0; i < g_prof.max_steps * (kStages + 1); ++i) cudaEventDestroy(g_prof.ev[i]);
+    delete[] g_prof.ev;
+    g_prof = Profile();
+  }
+  g_prof.ev = new cudaEvent_t[(size_t)max_steps * (kStages + 1)];
+  for (int i = 0; i < max_steps * (kStages + 1); ++i) SHASTA_CUDA(cudaEventCreate(&g_prof.ev[i]));
+  g_prof.max_steps = max_steps;
+  g_prof.steps = 0;
+  return 0;
+}
+
+int shasta_profile_end(float* host_stage_ms, int* host_steps) {
+  NOT_NULL(host_stage_ms);
+  NOT_NULL(host_steps);
+  for (int k = 0; k < kStages; ++k) host_stage_ms[k] = 0.f;
+  *host_steps = g_prof.steps;
+  if (g_prof.ev == nullptr) return 0;
+  for (int st = 0; st < g_prof.steps; ++st) {
+    cudaEvent_t* ev = g_prof.ev + (size_t)st * (kStages + 1);
+    SHASTA_CUDA(cudaEventSynchronize(ev[kStages]));
+    for (int k = 0; k < kStages; ++k) {
+      float ms = 0.f;
+      SHASTA_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+      host_stage_ms[k] += ms;
+    }
+  }
+  if (g_prof.steps > 0)
+    for (int k = 0; k < kStages; ++k) host_stage_ms[k] /= (float)g_prof.steps;
+  for (int i = 0; i < g_prof.max_steps * (kStages + 1); ++i) cudaEventDestroy(g_prof.ev[i]);
+  delete[] g_prof.ev;
+  g_prof = Profile();
   return 0;
 }
 

@@ -159,14 +159,15 @@ int launch_bilinear(const float* im, int H, int W, int C, const float* xs, const
 int launch_gather(const float* bev0, const float* boxes0, float* feat0, const float* bev1, const float* boxes1,
                   float* feat1, int nframes, int box_stride, int B, int M, const shasta_geom_t& g,
                   size_t feat_batch_stride, int variant, cudaStream_t s);
+// `mid` (optional) is recorded between the two kernels of a stage (per-kernel timing for bench.py)
 int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
-                   const WsLayout& L, cudaStream_t s);
+                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid);
 int launch_project(const float* packed, int B, int M, float* ws, const WsLayout& L, float* det_boxes_inout,
                    cudaStream_t s);
 int launch_pairwise(const float* packed, int B, int M, float* ws, const WsLayout& L, int variant,
                     cudaStream_t s);
 int launch_aff_softmax(const float* packed, int B, int M, float* ws, const WsLayout& L, float* matched1,
-                       float* matched2, cudaStream_t s);
+                       float* matched2, cudaStream_t s, cudaEvent_t mid);
 int launch_decode(const float* m1, const float* m2, const int32_t* n_prev, const int32_t* n_det, int B, int M,
                   int32_t* prev_state, int32_t* prev_argmax, float* fn_score, int32_t* det_state,
                   int32_t* det_argmax, float* det_score, cudaStream_t s);

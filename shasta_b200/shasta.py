@@ -212,13 +212,18 @@ class Shasta(nn.Module):
     def affinity(self, bev, prev_bev, det_boxes, prev_det_boxes):
         """Hot path from the channels-last maps: (B,H,W,64) x2, (B,M,11) x2 -> matched1, matched2.
         ``det_boxes[:, :, :2]`` is back-projected in place (shasta.py:270)."""
+        device = self.aff[0].weight.device
+        if device.type != "cuda":
+            raise _cabi.ShastaLibraryError("Shasta parameters are on %s: shasta_b200 has no CPU path" % device)
         for name, t in (("bev_feature", bev), ("prev_bev_feature", prev_bev), ("det_boxes", det_boxes),
                         ("prev_det_boxes", prev_det_boxes)):
-            if not t.is_cuda:
-                raise _cabi.ShastaLibraryError("%s must be a CUDA tensor: shasta_b200 has no CPU path" % name)
             if t.dtype != torch.float32:
                 raise TypeError("%s must be float32, got %s" % (name, t.dtype))
-        device = bev.device
+            if not t.is_cuda and not t.is_pinned():
+                # host inputs are accepted only as page-locked buffers: boxes are copied asynchronously, BEV maps are
+                # sampled in place over PCIe (the gather touches ~2 MB of a 134 MB map pair)
+                raise _cabi.ShastaLibraryError(
+                    "%s must be a CUDA tensor or a pinned host tensor: shasta_b200 has no CPU path" % name)
         B, H, W, C = bev.shape
         M = self.max_obj
         if C != 64 or prev_bev.shape != bev.shape:
@@ -229,10 +234,16 @@ class Shasta(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
             from .training import affinity_with_grad  # built on the same kernels (forward) + backward kernels
             return affinity_with_grad(self, bev, prev_bev, det_boxes, prev_det_boxes)
+        if B == 0:
+            return (torch.empty((0, M, M + 2), dtype=torch.float32, device=device),
+                    torch.empty((0, M + 2, M), dtype=torch.float32, device=device))
         bev = bev if bev.is_contiguous() else bev.contiguous()
         prev_bev = prev_bev if prev_bev.is_contiguous() else prev_bev.contiguous()
-        prev_c = prev_det_boxes if prev_det_boxes.is_contiguous() else prev_det_boxes.contiguous()
-        det_c = det_boxes if det_boxes.is_contiguous() else det_boxes.contiguous()
+        if (not bev.is_cuda or not prev_bev.is_cuda) and (self.kernel_flags & FLAG_TMA_GATHER):
+            raise _cabi.ShastaLibraryError("host-resident BEV maps need the LDG sampler (kernel_flags bit 0 clear)")
+        # boxes: device copies of host inputs (async from pinned memory); the back-projection is written back below
+        prev_c = prev_det_boxes.to(device, non_blocking=True).contiguous()
+        det_c = det_boxes.to(device, non_blocking=True).contiguous()
 
         lib = _cabi.lib()
         self._ensure_packed(device)
@@ -248,7 +259,10 @@ class Shasta(nn.Module):
                 ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
         _cabi.check(rc, "shasta_forward_f32")
         if det_c is not det_boxes:
-            det_boxes[:, :, :2] = det_c[:, :, :2]
+            if det_boxes.is_cuda:
+                det_boxes[:, :, :2] = det_c[:, :, :2]
+            else:  # pinned host input: asynchronous write-back of the back-projected boxes (shasta.py:270)
+                det_boxes.copy_(det_c, non_blocking=True)
         anchors = ws.region(_cabi.WS_ANCHOR_BOX, B * 4 * 7).view(B, 4, 7)
         self.newborn, self.fp = anchors[:, 0:1, :], anchors[:, 1:2, :]
         self.dead_trk, self.fn = anchors[:, 2:3, :], anchors[:, 3:4, :]

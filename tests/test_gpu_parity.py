@@ -1,0 +1,407 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C ABI, against the reference goldens and the
+CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): affinities within 1e-3 relative in fp32 (asserted at 2e-4 here), association
+(argmax / decode) identical, index / copy work bit-exact (bilinear on given coordinates, in-place back-projection).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import shasta_oracle as O
+from shasta_b200 import _cabi, synthetic
+from tests import gpu_util as G
+from tests.golden_util import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+FP32_REL_TOL = 2e-4   # north_star allows 1e-3
+
+
+@pytest.fixture(autouse=True)
+def _lib(shasta_lib):
+    return shasta_lib
+
+
+# ------------------------------------------------------------------------------------------------
+# a2: bilinear on explicit coordinates — bit exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,W,C,n", [(5, 7, 4, 64), (32, 48, 64, 1000), (180, 180, 64, 4096), (1, 1, 8, 10)])
+def test_bilinear_bit_exact(H, W, C, n):
+    rng = np.random.default_rng(H * 1000 + W)
+    im = rng.standard_normal((H, W, C)).astype(np.float32)
+    xs = rng.uniform(-3, W + 2, n).astype(np.float32)
+    ys = rng.uniform(-3, H + 2, n).astype(np.float32)
+    # exact integers, the last row/column, far outside
+    xs[:6] = [0.0, W - 1.0, W - 1.0, -1.0, W + 0.5, 1e6]
+    ys[:6] = [0.0, H - 1.0, 0.0, 2.0, -0.5, -1e6]
+    want = O.bilinear_interpolate(torch.from_numpy(im), torch.from_numpy(xs), torch.from_numpy(ys)).numpy()
+    lib = _cabi.lib()
+    dim, dx, dy = G.t(im), G.t(xs), G.t(ys)
+    out = torch.empty((n, C), device=G.DEV)
+    rc = lib.shasta_bilinear_f32(dim.data_ptr(), H, W, C, dx.data_ptr(), dy.data_ptr(), n, out.data_ptr(), G.stream())
+    _cabi.check(rc, "bilinear")
+    got = out.cpu().numpy()
+    assert np.array_equal(got, want), "max diff %g" % np.abs(got - want).max()
+
+
+def test_bilinear_empty_and_bad_args():
+    lib = _cabi.lib()
+    im = torch.zeros((4, 4, 8), device=G.DEV)
+    out = torch.zeros((1, 8), device=G.DEV)
+    assert lib.shasta_bilinear_f32(im.data_ptr(), 4, 4, 8, None, None, 0, out.data_ptr(), G.stream()) == 0
+    assert lib.shasta_bilinear_f32(im.data_ptr(), 4, 4, 6, None, None, 0, out.data_ptr(), G.stream()) < 0
+    assert b"multiple of 4" in lib.shasta_last_error_string()
+
+
+def test_bev_extractor_module_api():
+    """BEVFeatureExtractor.forward(example, batch_centers, num_point) like bird_eye_view.py:24-41."""
+    c, pc_start, data, weights, g = load_golden("m20_32px_b2")
+    model = G.make_model(c["M"], pc_start, weights)
+    bev = G.t(data["bev"])
+    boxes = torch.from_numpy(data["det_boxes"][:, :, :7])
+    centers = [O.box_points(boxes[b]).to(G.DEV) for b in range(c["B"])]
+    out = model.bev_extractor({"bev_feature": bev}, centers, 5)
+    assert isinstance(out, list) and len(out) == c["B"] and tuple(out[0].shape) == (c["M"], 320)
+    got = torch.stack(out).cpu().numpy()
+    # coordinates computed by torch on the GPU may differ by an ulp from the CPU's: tolerance, not bits
+    assert np.allclose(got, g["feature"], rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# a1+a2: fused box gather, both samplers
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name", golden_names())
+def test_gather_from_boxes(name, variant):
+    c, pc_start, data, weights, g = load_golden(name)
+    model = G.make_model(c["M"], pc_start, weights)
+    st = G.Stages(model, c["B"])
+    for bev_k, box_k, gold_k, region in (("bev", "det_boxes", "feature", _cabi.WS_FEAT_CUR),
+                                         ("prev_bev", "prev_det_boxes", "prev_feature", _cabi.WS_FEAT_PREV)):
+        feat = st.gather(G.t(data[bev_k]), G.t(data[box_k]), region, variant)
+        got = feat[:, :c["M"], :].cpu().numpy()
+        want = g[gold_k]
+        exact = float(np.mean(got == want))
+        assert np.allclose(got, want, rtol=1e-4, atol=1e-4), (gold_k, np.abs(got - want).max())
+        assert exact > 0.5, "only %.3f of the gathered values are bit-identical" % exact
+
+
+# ------------------------------------------------------------------------------------------------
+# a3+a4: anchors
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_anchors_stage(name):
+    c, pc_start, data, weights, g = load_golden(name)
+    B, M = c["B"], c["M"]
+    model = G.make_model(M, pc_start, weights)
+    st = G.Stages(model, B)
+    st.region(_cabi.WS_FEAT_CUR, (B, M + 2, 320))[:, :M] = G.t(g["feature"])
+    st.region(_cabi.WS_FEAT_PREV, (B, M + 2, 320))[:, :M] = G.t(g["prev_feature"])
+    det, prev = G.t(data["det_boxes"]), G.t(data["prev_det_boxes"])
+    st.anchors(det, prev)
+    assert np.array_equal(det.cpu().numpy(), data["det_boxes"]), "anchors stage must not modify its inputs"
+    fc = st.region(_cabi.WS_FEAT_CUR, (B, M + 2, 320)).cpu().numpy()
+    fp = st.region(_cabi.WS_FEAT_PREV, (B, M + 2, 320)).cpu().numpy()
+    aug = g["aug_shape"]  # (4,B,1,320): newborn, fp, dead, fn
+    for got, want in ((fp[:, M], aug[0][:, 0]), (fp[:, M + 1], aug[1][:, 0]), (fc[:, M], aug[2][:, 0]),
+                      (fc[:, M + 1], aug[3][:, 0])):
+        assert np.allclose(got, want, rtol=2e-4, atol=2e-5), np.abs(got - want).max()
+    ab = st.region(_cabi.WS_ANCHOR_BOX, (B, 4, 7)).cpu().numpy()
+    for i, k in enumerate(("newborn", "fp", "dead_trk", "fn")):
+        assert np.allclose(ab[:, i], g[k][:, 0], rtol=2e-4, atol=2e-5), k
+    bc = st.region(_cabi.WS_BOX_CUR, (B, M + 2, 8)).cpu().numpy()
+    bp = st.region(_cabi.WS_BOX_PREV, (B, M + 2, 8)).cpu().numpy()
+    assert np.array_equal(bc[:, :M, :7], g["det_boxes_after"][:, :, :7])   # back-projection: bit exact
+    assert np.array_equal(bp[:, :M, :7], data["prev_det_boxes"][:, :, :7])
+    assert np.allclose(bc[:, M, :7], g["dead_trk"][:, 0], rtol=2e-4, atol=2e-5)
+    assert np.allclose(bp[:, M + 1, :7], g["fp"][:, 0], rtol=2e-4, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-object projections / aux / colnorm, then pairwise
+# ------------------------------------------------------------------------------------------------
+def _fill_aug(st, c, data, g):
+    """Puts the reference's augmented features and boxes into the workspace."""
+    B, M = c["B"], c["M"]
+    fc = st.region(_cabi.WS_FEAT_CUR, (B, M + 2, 320))
+    fp = st.region(_cabi.WS_FEAT_PREV, (B, M + 2, 320))
+    fc[:, :M], fp[:, :M] = G.t(g["feature"]), G.t(g["prev_feature"])
+    aug = g["aug_shape"]
+    fp[:, M], fp[:, M + 1] = G.t(aug[0][:, 0]), G.t(aug[1][:, 0])
+    fc[:, M], fc[:, M + 1] = G.t(aug[2][:, 0]), G.t(aug[3][:, 0])
+    bc = st.region(_cabi.WS_BOX_CUR, (B, M + 2, 8))
+    bp = st.region(_cabi.WS_BOX_PREV, (B, M + 2, 8))
+    bc.zero_(), bp.zero_()
+    bc[:, :M, :7] = G.t(g["det_boxes_after"][:, :, :7])
+    bp[:, :M, :7] = G.t(data["prev_det_boxes"][:, :, :7])
+    bc[:, M, :7], bc[:, M + 1, :7] = G.t(g["dead_trk"][:, 0]), G.t(g["fn"][:, 0])
+    bp[:, M, :7], bp[:, M + 1, :7] = G.t(g["newborn"][:, 0]), G.t(g["fp"][:, 0])
+    prev_aug = np.concatenate([data["prev_det_boxes"][:, :, :7], g["newborn"], g["fp"]], axis=1)
+    det_aug = np.concatenate([g["det_boxes_after"][:, :, :7], g["dead_trk"], g["fn"]], axis=1)
+    f_prev = np.concatenate([g["prev_feature"], aug[0], aug[1]], axis=1)
+    f_cur = np.concatenate([g["feature"], aug[2], aug[3]], axis=1)
+    return prev_aug, det_aug, f_prev, f_cur
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_project_and_pairwise_stage(name):
+    c, pc_start, data, weights, g = load_golden(name)
+    B, M = c["B"], c["M"]
+    T = M + 2
+    model = G.make_model(M, pc_start, weights)
+    st = G.Stages(model, B)
+    prev_aug, det_aug, f_prev, f_cur = _fill_aug(st, c, data, g)
+    det = G.t(data["det_boxes"])
+    st.project(det)
+    torch.cuda.synchronize()
+    # in-place back-projection of the caller's boxes
+    assert np.array_equal(det.cpu().numpy(), g["det_boxes_after"])
+    # projections vs float64 numpy
+    W = {k: v.astype(np.float64) for k, v in weights.items()}
+    fs, rc, fd = W["fuse_shape.0.weight"], W["res_coeff.0.weight"], W["fuse_det.0.weight"]
+    pp = np.concatenate([f_prev @ fs[:, :320].T,
+                         f_prev @ rc[:, :320].T + prev_aug[:, :, :3] @ rc[:, 320:323].T,
+                         prev_aug[:, :, :3] @ fd[:, :3].T], axis=2)
+    pcur = np.concatenate([f_cur @ fs[:, 320:].T + W["fuse_shape.0.bias"],
+                           f_cur @ rc[:, 323:643].T + det_aug[:, :, :3] @ rc[:, 643:].T + W["res_coeff.0.bias"],
+                           det_aug[:, :, :3] @ fd[:, 3:].T + W["fuse_det.0.bias"]], axis=2)
+    got_pp = st.region(_cabi.WS_PROJ_PREV, (B, T, 144)).cpu().numpy()
+    got_pc = st.region(_cabi.WS_PROJ_CUR, (B, 144, st.DP)).cpu().numpy()[:, :, :T].transpose(0, 2, 1)
+    assert np.allclose(got_pp, pp, rtol=1e-4, atol=1e-5), np.abs(got_pp - pp).max()
+    assert np.allclose(got_pc, pcur, rtol=1e-4, atol=1e-5), np.abs(got_pc - pcur).max()
+    # column norm of the squared-distance matrix
+    dist = ((prev_aug[:, :, None, :3].astype(np.float64) - det_aug[:, None, :, :3]) ** 2).sum(-1)
+    cn = np.sqrt((dist ** 2).sum(axis=1))
+    got_cn = st.region(_cabi.WS_COLNORM, (B, T)).cpu().numpy()
+    assert np.allclose(got_cn, cn, rtol=1e-5), np.abs(got_cn - cn).max()
+    # pairwise -> residual
+    st.pairwise(0)
+    res = st.region(_cabi.WS_RESIDUAL, (B, T, st.RS)).cpu().numpy()[:, :, :T]
+    want = g["residual"]
+    err = np.abs(res - want).max() / np.abs(want).max()
+    assert err < 1e-5, "residual max err / scale = %g" % err
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_aff_softmax_stage(name):
+    c, pc_start, data, weights, g = load_golden(name)
+    B, M = c["B"], c["M"]
+    T = M + 2
+    model = G.make_model(M, pc_start, weights)
+    st = G.Stages(model, B)
+    st.region(_cabi.WS_RESIDUAL, (B, T, st.RS))[:, :, :T] = G.t(g["residual"])
+    m1, m2 = st.aff_softmax()
+    logits = st.region(_cabi.WS_LOGITS, (B, T, st.RS)).cpu().numpy()[:, :, :T]
+    scale = np.abs(g["logits"]).max()
+    assert np.abs(logits - g["logits"]).max() / scale < 1e-5
+    assert G.rel_err(m1.cpu().numpy(), g["matched1"]) < FP32_REL_TOL
+    assert G.rel_err(m2.cpu().numpy(), g["matched2"]) < FP32_REL_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# whole path through the module interface
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [0, 1])
+@pytest.mark.parametrize("name", golden_names())
+def test_forward_matches_reference_golden(name, flags):
+    c, pc_start, data, weights, g = load_golden(name)
+    model = G.make_model(c["M"], pc_start, weights)
+    model.kernel_flags = flags
+    example = {"det_boxes": G.t(data["det_boxes"]), "prev_det_boxes": G.t(data["prev_det_boxes"]),
+               "bev_feature": G.t(data["bev"]), "prev_bev_feature": G.t(data["prev_bev"])}
+    with torch.no_grad():
+        m1, m2, ex = model(example, train_mode=False)
+    assert ex is example and tuple(m1.shape) == g["matched1"].shape and tuple(m2.shape) == g["matched2"].shape
+    m1, m2 = m1.cpu().numpy(), m2.cpu().numpy()
+    e1, e2 = G.rel_err(m1, g["matched1"]), G.rel_err(m2, g["matched2"])
+    assert e1 < FP32_REL_TOL and e2 < FP32_REL_TOL, (e1, e2)
+    # side effects of the reference forward
+    assert np.array_equal(example["det_boxes"].cpu().numpy(), g["det_boxes_after"])
+    for k in ("newborn", "fp", "dead_trk", "fn"):
+        assert np.allclose(getattr(model, k).cpu().numpy(), g[k], rtol=2e-4, atol=2e-5)
+    # association: decode identical to the decode of the reference's own outputs
+    for b in range(c["B"]):
+        n_prev, n_det = int(data["n_prev"][b]), int(data["n_det"][b])
+        want = O.decode(torch.from_numpy(g["matched1"][b]), torch.from_numpy(g["matched2"][b]), n_prev, n_det)
+        got = O.decode(torch.from_numpy(m1[b]), torch.from_numpy(m2[b]), n_prev, n_det)
+        for key in ("dead", "fn", "keep_prev", "keep_dets", "newborn", "row_argmax", "col_argmax"):
+            assert got[key] == want[key], (name, b, key)
+
+
+def test_forward_batch_rows_independent():
+    """Frame pairs are independent: a batch of 5 equals five batches of 1."""
+    M, H, W = 20, 32, 32
+    pc_start = (-W * 0.3, -H * 0.3)
+    data = synthetic.make_frame_pairs(5, M, H, W, 77, pc_start=pc_start)
+    model = G.make_model(M, pc_start, synthetic.make_weights(M, seed=9))
+    args = [G.t(data[k]) for k in ("bev", "prev_bev", "det_boxes", "prev_det_boxes")]
+    with torch.no_grad():
+        m1, m2 = model.affinity(args[0], args[1], args[2].clone(), args[3])
+        for b in range(5):
+            s1, s2 = model.affinity(args[0][b:b + 1], args[1][b:b + 1], args[2][b:b + 1].clone(), args[3][b:b + 1])
+            assert torch.allclose(s1[0], m1[b], rtol=1e-6, atol=1e-9)
+            assert torch.allclose(s2[0], m2[b], rtol=1e-6, atol=1e-9)
+
+
+def test_forward_empty_batch_and_bad_inputs():
+    M = 6
+    model = G.make_model(M, (-4.8, -4.8), synthetic.make_weights(M, seed=1))
+    z = lambda *s: torch.zeros(*s, device=G.DEV)  # noqa: E731
+    m1, m2 = model.affinity(z(0, 16, 16, 64), z(0, 16, 16, 64), z(0, M, 11), z(0, M, 11))
+    assert tuple(m1.shape) == (0, M, M + 2) and tuple(m2.shape) == (0, M + 2, M)
+    with pytest.raises(_cabi.ShastaLibraryError):
+        model.affinity(torch.zeros(1, 16, 16, 64), torch.zeros(1, 16, 16, 64), torch.zeros(1, M, 11),
+                       torch.zeros(1, M, 11))
+    with pytest.raises(ValueError):
+        model.affinity(z(1, 16, 16, 32), z(1, 16, 16, 32), z(1, M, 11), z(1, M, 11))
+    with pytest.raises(ValueError):
+        model.affinity(z(1, 16, 16, 64), z(1, 16, 16, 64), z(1, M + 1, 11), z(1, M + 1, 11))
+
+
+def test_all_zero_boxes_and_out_of_range_boxes():
+    """Empty frames (all padding) and boxes far outside the map stay finite and normalised."""
+    M, H, W = 20, 32, 32
+    pc_start = (-W * 0.3, -H * 0.3)
+    data = synthetic.make_frame_pairs(2, M, H, W, 5, pc_start=pc_start)
+    data["det_boxes"][0] = 0.0
+    data["prev_det_boxes"][1] = 0.0
+    data["det_boxes"][1, :4, :2] = [[1e4, 1e4], [-1e4, 3.0], [W * 0.3, H * 0.3], [-W * 0.3, -H * 0.3]]
+    weights = synthetic.make_weights(M, seed=3)
+    model = G.make_model(M, pc_start, weights)
+    det = G.t(data["det_boxes"])
+    with torch.no_grad():
+        m1, m2 = model.affinity(G.t(data["bev"]), G.t(data["prev_bev"]), det, G.t(data["prev_det_boxes"]))
+    w = O.weights_to_torch(weights)
+    o1, o2 = O.forward(w, torch.from_numpy(data["bev"]), torch.from_numpy(data["prev_bev"]),
+                       torch.from_numpy(data["det_boxes"].copy()), torch.from_numpy(data["prev_det_boxes"]),
+                       pc_start=pc_start)
+    assert torch.isfinite(m1).all() and torch.isfinite(m2).all()
+    assert G.rel_err(m1.cpu().numpy(), o1.numpy()) < FP32_REL_TOL
+    assert G.rel_err(m2.cpu().numpy(), o2.numpy()) < FP32_REL_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# headline size: M = 200 (BASELINE.json configs[0]/[1]) against the oracle, plus size-independent properties
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,W,B", [(180, 180, 3), (512, 512, 1)])
+def test_headline_size_against_oracle(H, W, B):
+    M = 200
+    pc_start = (-W * 0.3, -H * 0.3)
+    data = synthetic.make_frame_pairs(B, M, H, W, 2024 + H, pc_start=pc_start)
+    weights = synthetic.make_weights(M, seed=21, peaky=300.0)
+    model = G.make_model(M, pc_start, weights)
+    det = G.t(data["det_boxes"])
+    with torch.no_grad():
+        m1, m2 = model.affinity(G.t(data["bev"]), G.t(data["prev_bev"]), det, G.t(data["prev_det_boxes"]))
+    w = O.weights_to_torch(weights)
+    det_o = torch.from_numpy(data["det_boxes"].copy())
+    o1, o2 = O.forward(w, torch.from_numpy(data["bev"]), torch.from_numpy(data["prev_bev"]), det_o,
+                       torch.from_numpy(data["prev_det_boxes"]), pc_start=pc_start)
+    m1, m2 = m1.cpu(), m2.cpu()
+    assert G.rel_err(m1.numpy(), o1.numpy()) < 1e-3
+    assert G.rel_err(m2.numpy(), o2.numpy()) < 1e-3
+    assert np.array_equal(det.cpu().numpy(), det_o.numpy())
+    assert torch.allclose(m1.sum(2), torch.ones(B, M), atol=1e-5)
+    assert torch.allclose(m2.sum(1), torch.ones(B, M), atol=1e-5)
+    for b in range(B):
+        n_prev, n_det = int(data["n_prev"][b]), int(data["n_det"][b])
+        want = O.decode(o1[b], o2[b], n_prev, n_det)
+        got = O.decode(m1[b], m2[b], n_prev, n_det)
+        for key in ("dead", "fn", "keep_prev", "keep_dets", "newborn", "row_argmax", "col_argmax"):
+            assert got[key] == want[key], (b, key)
+
+
+@pytest.mark.parametrize("M,B", [(500, 2), (1000, 1)])
+def test_large_sizes_properties(M, B):
+    """BASELINE.json configs[2]/[3] sizes (up to 500x500, 1000x1000 stress): size-independent properties —
+    normalisation, finiteness, independence of the batch composition, determinism."""
+    H = W = 64
+    pc_start = (-W * 0.3, -H * 0.3)
+    data = synthetic.make_frame_pairs(B, M, H, W, 31 + M, pc_start=pc_start)
+    model = G.make_model(M, pc_start)  # default nn.Linear init on the device (weights are 6.4 / 25.6 GB)
+    args = [G.t(data[k]) for k in ("bev", "prev_bev", "det_boxes", "prev_det_boxes")]
+    with torch.no_grad():
+        m1, m2 = model.affinity(args[0], args[1], args[2].clone(), args[3])
+        r1, r2 = model.affinity(args[0], args[1], args[2].clone(), args[3])
+    assert torch.isfinite(m1).all() and torch.isfinite(m2).all()
+    assert torch.allclose(m1.sum(2), torch.ones(B, M, device=G.DEV), atol=1e-5)
+    assert torch.allclose(m2.sum(1), torch.ones(B, M, device=G.DEV), atol=1e-5)
+    assert torch.equal(m1, r1) and torch.equal(m2, r2), "the path must be bit-reproducible run to run"
+    del model
+    torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------
+# a13: device decode
+# ------------------------------------------------------------------------------------------------
+def _device_decode(m1, m2, n_prev, n_det):
+    lib = _cabi.lib()
+    B, M = m1.shape[0], m1.shape[1]
+    i32 = lambda: torch.empty((B, M), dtype=torch.int32, device=G.DEV)  # noqa: E731
+    f32 = lambda: torch.empty((B, M), dtype=torch.float32, device=G.DEV)  # noqa: E731
+    ps, pa, fs, ds, da, dsc = i32(), i32(), f32(), i32(), i32(), f32()
+    npv = torch.tensor(n_prev, dtype=torch.int32, device=G.DEV)
+    ndv = torch.tensor(n_det, dtype=torch.int32, device=G.DEV)
+    rc = lib.shasta_decode_f32(m1.data_ptr(), m2.data_ptr(), npv.data_ptr(), ndv.data_ptr(), B, M, ps.data_ptr(),
+                               pa.data_ptr(), fs.data_ptr(), ds.data_ptr(), da.data_ptr(), dsc.data_ptr(), G.stream())
+    _cabi.check(rc, "decode")
+    return [x.cpu().numpy() for x in (ps, pa, fs, ds, da, dsc)]
+
+
+def _check_decode(m1, m2, n_prev, n_det):
+    ps, pa, fs, ds, da, dsc = _device_decode(G.t(m1), G.t(m2), n_prev, n_det)
+    for b in range(m1.shape[0]):
+        want = O.decode(torch.from_numpy(m1[b]), torch.from_numpy(m2[b]), n_prev[b], n_det[b])
+        assert [n for n in range(n_prev[b]) if ps[b, n] == 1] == want["dead"]
+        assert [n for n in range(n_prev[b]) if ps[b, n] == 2] == want["fn"]
+        assert [n for n in range(n_prev[b]) if ps[b, n] == 0] == want["keep_prev"]
+        assert np.all(ps[b, n_prev[b]:] == -1) and np.all(ds[b, n_det[b]:] == -1)
+        assert pa[b, :n_prev[b]].tolist() == want["row_argmax"]
+        assert da[b, :n_det[b]].tolist() == want["col_argmax"]
+        assert np.array_equal(fs[b, want["fn"]], np.array(want["fn_score"], np.float64).astype(np.float32))
+        keep = [k for k in range(n_det[b]) if ds[b, k] in (0, 1)]
+        assert keep == want["keep_dets"]
+        assert [bool(ds[b, k] == 1) for k in keep] == want["newborn"]
+        assert np.array_equal(dsc[b, keep], np.array(want["det_score"], np.float64).astype(np.float32))
+
+
+def test_decode_on_planted_matrices():
+    rng = np.random.default_rng(5)
+    B, M = 6, 40
+    m1 = rng.uniform(0, 0.45, (B, M, M + 2)).astype(np.float32)
+    m2 = rng.uniform(0, 0.45, (B, M + 2, M)).astype(np.float32)
+    n_prev = [40, 17, 0, 25, 1, 33]
+    n_det = [40, 22, 9, 0, 1, 30]
+    for b in range(B):
+        for n in range(n_prev[b]):
+            r = rng.integers(0, 5)
+            if r == 0:
+                m1[b, n, M] = 0.9                      # dead
+            elif r == 1:
+                m1[b, n, M + 1] = 0.8                  # false negative
+            elif r == 2 and n_det[b] > 0:
+                m1[b, n, rng.integers(0, n_det[b])] = 0.95
+            elif r == 3:
+                m1[b, n, M + 1] = 0.5                  # exactly at the threshold: not > 0.5
+        for k in range(n_det[b]):
+            r = rng.integers(0, 5)
+            if r == 0:
+                m2[b, M + 1, k] = 0.75                 # false positive, dropped
+            elif r == 1:
+                m2[b, M + 1, k] = 0.7                  # float32(0.7) < 0.7: kept
+            elif r == 2:
+                m2[b, M, k] = 0.6                      # newborn
+            elif r == 3 and n_prev[b] > 0:
+                m2[b, rng.integers(0, n_prev[b]), k] = 0.99
+    # ties: first maximum wins
+    m1[0, 0, :] = 0.3
+    m2[0, :, 0] = 0.3
+    _check_decode(m1, m2, n_prev, n_det)
+
+
+def test_decode_on_peaky_golden():
+    c, pc_start, data, weights, g = load_golden("m20_32px_b3_peaky")
+    _check_decode(g["matched1"], g["matched2"], [int(x) for x in data["n_prev"]], [int(x) for x in data["n_det"]])
