@@ -101,6 +101,13 @@ enum shasta_region {
   SHASTA_WS_NUM_REGIONS = 13
 };
 
+/* Runtime options (process-wide, not thread-safe; meant for tests and benchmarks).
+ *   SHASTA_OPT_ANCHOR_PATH: 0 = auto (streaming CUDA-core kernel up to 8 frame pairs, tcgen05 3xTF32 GEMM above),
+ *                           1 = always the streaming kernel, 2 = always the tcgen05 kernel. */
+enum shasta_option { SHASTA_OPT_ANCHOR_PATH = 0, SHASTA_OPT_COUNT = 4 };
+SHASTA_API int shasta_set_option(int option, int value);
+SHASTA_API int shasta_get_option(int option);
+
 SHASTA_API int shasta_abi_version(void);
 SHASTA_API const char* shasta_last_error_string(void);
 

@@ -54,9 +54,14 @@ class ShastaGeom(ctypes.Structure):
 WS_FEAT_CUR, WS_FEAT_PREV, WS_BOX_CUR, WS_BOX_PREV, WS_HIDDEN_PART, WS_PROJ_PREV, WS_PROJ_CUR, WS_AUX_PREV, \
     WS_AUX_CUR, WS_COLNORM, WS_RESIDUAL, WS_LOGITS, WS_ANCHOR_BOX = range(13)
 
+OPT_ANCHOR_PATH = 0
+ANCHOR_AUTO, ANCHOR_STREAM, ANCHOR_TC = 0, 1, 2
+
 # every symbol include/shasta_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _sz, _u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_uint32
 SYMBOLS = {
+    "shasta_set_option": (_i, [_i, _i]),
+    "shasta_get_option": (_i, [_i]),
     "shasta_abi_version": (_i, []),
     "shasta_last_error_string": (ctypes.c_char_p, []),
     "shasta_last_launch_count": (_i, []),

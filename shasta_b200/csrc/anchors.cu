@@ -227,27 +227,42 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
 }
 
 // ------------------------------------------------------------------------------------------------
+int anchor_tc_splits(int M, int B);  // anchors_tc.cu
+int launch_anchor_hidden_tc(const shasta_params_t& p, const float* feat_cur, const float* feat_prev, int B, int S,
+                            float* part, cudaStream_t s);
+
 int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
                    const WsLayout& L, cudaStream_t s, cudaEvent_t mid) {
   const int M = p.max_obj;
-  const int S = hidden_splits(M);
   const int N5 = 5 * M;
   float* feat_cur = ws + L.off[SHASTA_WS_FEAT_CUR];
   float* feat_prev = ws + L.off[SHASTA_WS_FEAT_PREV];
   float* part = ws + L.off[SHASTA_WS_HIDDEN_PART];
 
-  AnchorW0 w;
-  for (int i = 0; i < 4; ++i) w.w0[i] = p.aug_shape_w0[i];
-  dim3 grid(S, (N5 + kAnchorRowsPerCta - 1) / kAnchorRowsPerCta, 4);
-  if (B > 4)
-    anchor_hidden_kernel<8><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
-  else if (B > 2)
-    anchor_hidden_kernel<4><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
-  else if (B == 2)
-    anchor_hidden_kernel<2><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
-  else
-    anchor_hidden_kernel<1><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
-  SHASTA_CHECK_LAUNCH("anchor_hidden_kernel");
+  // small batches are pure weight streaming (HBM-bound on CUDA cores); from 9 frame pairs on the 3xTF32
+  // tensor-core GEMM wins.  option 0: 0 = auto, 1 = always streaming kernel, 2 = always tensor-core kernel
+  const int mode = g_options[SHASTA_OPT_ANCHOR_PATH];
+  const bool use_tc = (mode == 2) || (mode == 0 && B > 8);
+  int S;
+  if (use_tc) {
+    S = anchor_tc_splits(M, B);
+    int rc = launch_anchor_hidden_tc(p, feat_cur, feat_prev, B, S, part, s);
+    if (rc) return rc;
+  } else {
+    S = hidden_splits(M);
+    AnchorW0 w;
+    for (int i = 0; i < 4; ++i) w.w0[i] = p.aug_shape_w0[i];
+    dim3 grid(S, (N5 + kAnchorRowsPerCta - 1) / kAnchorRowsPerCta, 4);
+    if (B > 4)
+      anchor_hidden_kernel<8><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
+    else if (B > 2)
+      anchor_hidden_kernel<4><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
+    else if (B == 2)
+      anchor_hidden_kernel<2><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
+    else
+      anchor_hidden_kernel<1><<<grid, 256, 0, s>>>(w, feat_cur, feat_prev, B, M, part);
+    SHASTA_CHECK_LAUNCH("anchor_hidden_kernel");
+  }
   if (mid) cudaEventRecord(mid, s);
 
   AnchorFinishArgs a;

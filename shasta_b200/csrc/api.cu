@@ -9,6 +9,7 @@ namespace shasta {
 static thread_local char g_error[512] = "";
 thread_local int g_launch_count = 0;
 static thread_local int g_last_forward_launches = 0;
+int g_options[SHASTA_OPT_COUNT] = {0, 0, 0, 0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -101,6 +102,16 @@ using namespace shasta;
 extern "C" {
 
 int shasta_abi_version(void) { return SHASTA_ABI_VERSION; }
+
+int shasta_set_option(int option, int value) {
+  if (option < 0 || option >= SHASTA_OPT_COUNT) {
+    set_error("unknown option %d", option);
+    return SHASTA_ERR_ARG;
+  }
+  g_options[option] = value;
+  return 0;
+}
+int shasta_get_option(int option) { return (option < 0 || option >= SHASTA_OPT_COUNT) ? -1 : g_options[option]; }
 const char* shasta_last_error_string(void) { return g_error; }
 int shasta_last_launch_count(void) { return g_last_forward_launches; }
 

@@ -117,6 +117,9 @@ __host__ inline PackLayout pack_layout(int M) {
   return P;
 }
 
+// ---- runtime options (shasta_set_option) ---------------------------------------------------------
+extern int g_options[SHASTA_OPT_COUNT];
+
 // ---- error plumbing -----------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 extern thread_local int g_launch_count;

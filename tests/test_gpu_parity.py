@@ -92,8 +92,68 @@ def test_gather_from_boxes(name, variant):
 # ------------------------------------------------------------------------------------------------
 # a3+a4: anchors
 # ------------------------------------------------------------------------------------------------
+@pytest.fixture
+def force_tc_anchors():
+    lib = _cabi.lib()
+    lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, _cabi.ANCHOR_TC)
+    yield
+    lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, _cabi.ANCHOR_AUTO)
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_anchors_stage(name):
+    _anchors_stage(name)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_anchors_stage_tcgen05(name, force_tc_anchors):
+    """Same check with the tcgen05 3xTF32 GEMM forced (tiles far larger than these shapes: exercises the TMA
+    out-of-bounds zero fill on rows, the split-K partials and the TMEM epilogue masks)."""
+    _anchors_stage(name)
+
+
+@pytest.mark.parametrize("B", [12, 130])
+def test_anchor_paths_agree_at_m200(B):
+    """Streaming CUDA-core kernel vs tcgen05 kernel on the headline shape (K = 64000, 4 x 1000 rows), one and two
+    batch tiles."""
+    M = 200
+    lib = _cabi.lib()
+    model = G.make_model(M, (-54.0, -54.0))
+    st = G.Stages(model, B)
+    gen = torch.Generator(device=G.DEV).manual_seed(B)
+    fc = st.region(_cabi.WS_FEAT_CUR, (B, M + 2, 320))
+    fp = st.region(_cabi.WS_FEAT_PREV, (B, M + 2, 320))
+    fc[:, :M] = torch.randn((B, M, 320), device=G.DEV, generator=gen).relu_()
+    fp[:, :M] = torch.randn((B, M, 320), device=G.DEV, generator=gen).relu_()
+    boxes = torch.randn((B, M, 11), device=G.DEV, generator=gen)
+    out = {}
+    for mode in (_cabi.ANCHOR_STREAM, _cabi.ANCHOR_TC):
+        lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, mode)
+        try:
+            st.anchors(boxes, boxes)
+        finally:
+            lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, _cabi.ANCHOR_AUTO)
+        torch.cuda.synchronize()
+        out[mode] = torch.cat([fc[:, M:], fp[:, M:]], dim=1).clone()
+    a, b = out[_cabi.ANCHOR_STREAM].cpu().numpy(), out[_cabi.ANCHOR_TC].cpu().numpy()
+    assert np.isfinite(b).all()
+    # float64 reference of all four anchors: rows [dead, fn] of FEAT_CUR then [newborn, fp] of FEAT_PREV
+    xc = fc[:, :M].reshape(B, -1).double()
+    xp = fp[:, :M].reshape(B, -1).double()
+    ref = []
+    for i, x in ((2, xp), (3, xp), (0, xc), (1, xc)):
+        l0, l2 = model.aug_shape[i][0], model.aug_shape[i][2]
+        h = torch.relu(x @ l0.weight.double().T + l0.bias.double())
+        ref.append(torch.abs(h @ l2.weight.double().T + l2.bias.double()))
+    ref = torch.stack(ref, dim=1).cpu().numpy()
+    scale = np.abs(ref).max()
+    err_stream = np.abs(a - ref).max() / scale
+    err_tc = np.abs(b - ref).max() / scale
+    print("anchor L1+L2 max err / scale vs float64: streaming fp32 %.3g, tcgen05 3xTF32 %.3g" % (err_stream, err_tc))
+    assert err_stream < 1e-4 and err_tc < 1e-4, (err_stream, err_tc)
+
+
+def _anchors_stage(name):
     c, pc_start, data, weights, g = load_golden(name)
     B, M = c["B"], c["M"]
     model = G.make_model(M, pc_start, weights)
@@ -204,6 +264,11 @@ def test_aff_softmax_stage(name):
 # ------------------------------------------------------------------------------------------------
 # whole path through the module interface
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_forward_matches_reference_golden_tcgen05_anchors(name, force_tc_anchors):
+    test_forward_matches_reference_golden(name, 0)
+
+
 @pytest.mark.parametrize("flags", [0, 1])
 @pytest.mark.parametrize("name", golden_names())
 def test_forward_matches_reference_golden(name, flags):
