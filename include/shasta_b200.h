@@ -103,8 +103,10 @@ enum shasta_region {
 
 /* Runtime options (process-wide, not thread-safe; meant for tests and benchmarks).
  *   SHASTA_OPT_ANCHOR_PATH: 0 = auto (streaming CUDA-core kernel up to 8 frame pairs, tcgen05 3xTF32 GEMM above),
- *                           1 = always the streaming kernel, 2 = always the tcgen05 kernel. */
-enum shasta_option { SHASTA_OPT_ANCHOR_PATH = 0, SHASTA_OPT_COUNT = 4 };
+ *                           1 = always the streaming kernel, 2 = always the tcgen05 kernel.
+ *   SHASTA_OPT_TC_RAW_HI:   0 = the tcgen05 kernels write tf32-exact high parts back to shared memory (safe),
+ *                           1 = feed the raw fp32 tile as the high part (relies on kind::tf32 truncating). */
+enum shasta_option { SHASTA_OPT_ANCHOR_PATH = 0, SHASTA_OPT_TC_RAW_HI = 1, SHASTA_OPT_COUNT = 4 };
 SHASTA_API int shasta_set_option(int option, int value);
 SHASTA_API int shasta_get_option(int option);
 

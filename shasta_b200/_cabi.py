@@ -55,6 +55,7 @@ WS_FEAT_CUR, WS_FEAT_PREV, WS_BOX_CUR, WS_BOX_PREV, WS_HIDDEN_PART, WS_PROJ_PREV
     WS_AUX_CUR, WS_COLNORM, WS_RESIDUAL, WS_LOGITS, WS_ANCHOR_BOX = range(13)
 
 OPT_ANCHOR_PATH = 0
+OPT_TC_RAW_HI = 1
 ANCHOR_AUTO, ANCHOR_STREAM, ANCHOR_TC = 0, 1, 2
 
 # every symbol include/shasta_b200.h declares: name -> (restype, argtypes)

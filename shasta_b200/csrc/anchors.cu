@@ -118,9 +118,9 @@ struct AnchorFinishArgs {
   const float* db2[4];
 };
 
-constexpr int kFinishBG = 4;  // frame pairs per CTA
-
 // grid: x = 5 roles (anchor 0..3, 4 = real-box copy / back-projection), y = output slices, z = frame-pair groups
+// kFinishBG = frame pairs per CTA (their hidden vectors live in shared memory)
+template <int kFinishBG>
 __global__ void __launch_bounds__(256)
 anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, const float* __restrict__ det_boxes,
                      const float* __restrict__ prev_boxes, int B, int M, float* __restrict__ feat_cur,
@@ -170,27 +170,41 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
   __syncthreads();
 
   // ---- aug_shape.i.2 + abs -> anchor row of the augmented feature array
+  // a warp owns 4 output rows at a time (4 independent coalesced weight streams), lanes stride over the 5M inputs
   {
-    const int jper = (kF + gridDim.y - 1) / gridDim.y;
+    const int jper = (kF / 32 + gridDim.y - 1) / gridDim.y * 32;
     const int jbeg = blockIdx.y * jper, jend = min(kF, jbeg + jper);
     float* fdst = (i < 2) ? feat_prev : feat_cur;  // newborn/fp extend the T axis, dead/fn the D axis
     const int row = M + (i & 1);
-    for (int j = jbeg + warp; j < jend; j += 8) {
-      const float* wr = a.w2[i] + (size_t)j * N5;
-      float acc[kFinishBG];
+    for (int j0 = jbeg + warp * 4; j0 < jend; j0 += 32) {
+      const float* wr[4];
 #pragma unroll
-      for (int g = 0; g < kFinishBG; ++g) acc[g] = 0.f;
+      for (int r = 0; r < 4; ++r) wr[r] = a.w2[i] + (size_t)min(j0 + r, kF - 1) * N5;
+      float acc[4][kFinishBG];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int g = 0; g < kFinishBG; ++g) acc[r][g] = 0.f;
+#pragma unroll 2
       for (int n = lane; n < N5; n += 32) {
-        const float wv = __ldg(wr + n);
+        float wv[4];
 #pragma unroll
-        for (int g = 0; g < kFinishBG; ++g) acc[g] = fmaf(wv, hid[g * N5 + n], acc[g]);
+        for (int r = 0; r < 4; ++r) wv[r] = __ldg(wr[r] + n);
+#pragma unroll
+        for (int g = 0; g < kFinishBG; ++g) {
+          const float h = hid[g * N5 + n];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[r][g] = fmaf(wv[r], h, acc[r][g]);
+        }
       }
 #pragma unroll
-      for (int g = 0; g < kFinishBG; ++g) {
-        const float v = warp_sum(acc[g]);
-        if (lane == 0 && g < nb)
-          fdst[((size_t)(bg0 + g) * T + row) * kF + j] = fabsf(v + a.b2[i][j]);
-      }
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int g = 0; g < kFinishBG; ++g) {
+          const float v = warp_sum(acc[r][g]);
+          if (lane == 0 && g < nb && j0 + r < jend)
+            fdst[((size_t)(bg0 + g) * T + row) * kF + j0 + r] = fabsf(v + a.b2[i][j0 + r]);
+        }
     }
   }
 
@@ -276,18 +290,28 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
     a.db2[i] = p.aug_dets_b2[i];
   }
   const int H7 = (7 * M) / 32;
-  const size_t smem = sizeof(float) * ((size_t)kFinishBG * N5 + (size_t)kFinishBG * (H7 > 0 ? H7 : 1));
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    SHASTA_CUDA(cudaFuncSetAttribute(anchor_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  const int BG = (B > 4 && (size_t)8 * (N5 + H7 + 1) * sizeof(float) <= 200 * 1024) ? 8 : 4;
+  const size_t smem = sizeof(float) * ((size_t)BG * N5 + (size_t)BG * (H7 > 0 ? H7 : 1));
+  static size_t configured[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > configured[BG == 8]) {
+    if (BG == 8)
+      SHASTA_CUDA(cudaFuncSetAttribute(anchor_finish_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      SHASTA_CUDA(cudaFuncSetAttribute(anchor_finish_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[BG == 8] = smem;
   }
-  const int groups = (B + kFinishBG - 1) / kFinishBG;
-  const int slices = (groups >= 32) ? 1 : (groups >= 8 ? 4 : 8);
+  const int groups = (B + BG - 1) / BG;
+  const int slices = (groups >= 16) ? 2 : (groups >= 6 ? 5 : 10);  // 320 outputs = 10 passes of 32 rows
   dim3 fgrid(5, slices, groups);
-  anchor_finish_kernel<<<fgrid, 256, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev,
-                                                ws + L.off[SHASTA_WS_BOX_CUR], ws + L.off[SHASTA_WS_BOX_PREV],
-                                                ws + L.off[SHASTA_WS_ANCHOR_BOX]);
+  float* bc = ws + L.off[SHASTA_WS_BOX_CUR];
+  float* bp = ws + L.off[SHASTA_WS_BOX_PREV];
+  float* ab = ws + L.off[SHASTA_WS_ANCHOR_BOX];
+  if (BG == 8)
+    anchor_finish_kernel<8><<<fgrid, 256, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev, bc,
+                                                     bp, ab);
+  else
+    anchor_finish_kernel<4><<<fgrid, 256, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev, bc,
+                                                     bp, ab);
   SHASTA_CHECK_LAUNCH("anchor_finish_kernel");
   return 0;
 }

@@ -31,7 +31,7 @@ struct AnchorTcMaps {
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-anchor_hidden_tc_kernel(const __grid_constant__ AnchorTcMaps maps, int B, int M, int S, int ntiles_n,
+anchor_hidden_tc_kernel(const __grid_constant__ AnchorTcMaps maps, int B, int M, int S, int ntiles_n, int raw_hi,
                         float* __restrict__ part) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -135,7 +135,8 @@ anchor_hidden_tc_kernel(const __grid_constant__ AnchorTcMaps maps, int B, int M,
         wh4.y = __uint_as_float(__float_as_uint(w.y) & 0xffffe000u), wl4.y = w.y - wh4.y;
         wh4.z = __uint_as_float(__float_as_uint(w.z) & 0xffffe000u), wl4.z = w.z - wh4.z;
         wh4.w = __uint_as_float(__float_as_uint(w.w) & 0xffffe000u), wl4.w = w.w - wh4.w;
-        xh[idx] = ah, xl[idx] = al, wh[idx] = wh4, wl[idx] = wl4;
+        xl[idx] = al, wl[idx] = wl4;
+        if (!raw_hi) xh[idx] = ah, wh[idx] = wh4;  // raw_hi: rely on kind::tf32 ignoring the low 13 mantissa bits
       }
       fence_proxy_async_smem();
       mbar_arrive(split_bar(st));
@@ -246,7 +247,8 @@ int launch_anchor_hidden_tc(const shasta_params_t& p, const float* feat_cur, con
   }
   const int ntn = (int)((N5 + kTcBN - 1) / kTcBN), ntb = (B + kTcBM - 1) / kTcBM;
   dim3 grid(ntn * ntb, 4, S);
-  anchor_hidden_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(maps, B, M, S, ntn, part);
+  anchor_hidden_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(maps, B, M, S, ntn,
+                                                                 g_options[SHASTA_OPT_TC_RAW_HI], part);
   SHASTA_CHECK_LAUNCH("anchor_hidden_tc_kernel");
   return 0;
 }

@@ -75,6 +75,14 @@ struct PackLayout {
   size_t pair_end;    // end of the block the pairwise kernel stages in shared memory (from l2a)
   size_t aff_w[6];    // aff.{0..10}.weight^T : [in][out]
   size_t aff_b[6];
+  // UMMA B-operand images of the second pairwise layers (tensor-core variants), K-major canonical un-swizzled
+  // layout [k/4][n][4] (tf32) or [k/8][n][8] (bf16), N padded to a multiple of 16 with zero rows.
+  size_t tc32_begin;  // tf32 block: w2a hi, w2a lo (10x32x4 each), w2b hi, lo (18x32x4), w2c hi, lo (8x16x4)
+  size_t tc32_w2a_hi, tc32_w2a_lo, tc32_w2b_hi, tc32_w2b_lo, tc32_w2c_hi, tc32_w2c_lo;
+  size_t tc32_end;
+  size_t tc16_begin;  // bf16 block (counted in floats): w2a (5x32x8 bf16), w2b (9x32x8), w2c (4x16x8)
+  size_t tc16_w2a, tc16_w2b, tc16_w2c;
+  size_t tc16_end;
   size_t total;       // floats
 };
 
@@ -113,6 +121,19 @@ __host__ inline PackLayout pack_layout(int M) {
     P.aff_w[i] = take(win[i] * wout[i]);
     P.aff_b[i] = take(wout[i]);
   }
+  P.tc32_begin = o;
+  P.tc32_w2a_hi = take(10 * 32 * 4);
+  P.tc32_w2a_lo = take(10 * 32 * 4);
+  P.tc32_w2b_hi = take(18 * 32 * 4);
+  P.tc32_w2b_lo = take(18 * 32 * 4);
+  P.tc32_w2c_hi = take(8 * 16 * 4);
+  P.tc32_w2c_lo = take(8 * 16 * 4);
+  P.tc32_end = o;
+  P.tc16_begin = o;
+  P.tc16_w2a = take(5 * 32 * 8 / 2);
+  P.tc16_w2b = take(9 * 32 * 8 / 2);
+  P.tc16_w2c = take(4 * 16 * 8 / 2);
+  P.tc16_end = o;
   P.total = o;
   return P;
 }

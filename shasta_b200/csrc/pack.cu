@@ -1,5 +1,7 @@
 // Kernel-side weight cache: transposed / split / padded copies of the small layers (see PackLayout in common.cuh).
 // The PyTorch parameters stay the source of truth in (out,in) layout (state_dict contract).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace shasta {
@@ -11,6 +13,28 @@ __global__ void transpose_block_kernel(float* __restrict__ dst, int dst_ld, cons
   if (idx >= (long long)nj * nk) return;
   const int k = (int)(idx / nj), j = (int)(idx % nj);
   dst[(size_t)k * dst_ld + j] = src[(size_t)j * src_ld + k];
+}
+
+// UMMA B-operand image of a Linear weight (n_valid x K, row-major with leading dimension src_ld), padded to n_pad rows:
+// tf32 hi/lo split in the canonical K-major layout [k/4][n][4]; bf16 copy in [k/8][n][8].
+__global__ void umma_b_image_kernel(float* __restrict__ hi, float* __restrict__ lo, __nv_bfloat16* __restrict__ bf,
+                                    const float* __restrict__ src, int src_ld, int n_valid, int n_pad, int K) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pad * K) return;
+  const int n = idx / K, k = idx % K;
+  const float v = (n < n_valid) ? src[(size_t)n * src_ld + k] : 0.f;
+  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  hi[(k / 4) * (n_pad * 4) + n * 4 + (k % 4)] = h;
+  lo[(k / 4) * (n_pad * 4) + n * 4 + (k % 4)] = v - h;
+  bf[(k / 8) * (n_pad * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(v);
+}
+
+static int bimage(float* hi, float* lo, float* bf, const float* src, int src_ld, int n_valid, int n_pad, int K,
+                  cudaStream_t s) {
+  umma_b_image_kernel<<<(n_pad * K + 255) / 256, 256, 0, s>>>(hi, lo, reinterpret_cast<__nv_bfloat16*>(bf), src,
+                                                              src_ld, n_valid, n_pad, K);
+  SHASTA_CHECK_LAUNCH("umma_b_image_kernel");
+  return 0;
 }
 
 static int tblock(float* dst, int dst_ld, const float* src, int src_ld, int nj, int nk, cudaStream_t s) {
@@ -68,6 +92,13 @@ int launch_pack(const shasta_params_t& p, float* packed, cudaStream_t s) {
     TB(packed + P.aff_w[i], wout[i], p.aff_w[i], win[i], wout[i], win[i], s);
     TB(packed + P.aff_b[i], wout[i], p.aff_b[i], 1, wout[i], 1, s);
   }
+  // tensor-core operand images of fuse_shape.2 (20x40), res_coeff.2 (18x72), fuse_det.2 (8x32)
+  int rc = bimage(packed + P.tc32_w2a_hi, packed + P.tc32_w2a_lo, packed + P.tc16_w2a, p.fuse_shape_w[1], 40, 20, 32, 40, s);
+  if (rc) return rc;
+  rc = bimage(packed + P.tc32_w2b_hi, packed + P.tc32_w2b_lo, packed + P.tc16_w2b, p.res_coeff_w[1], 72, 18, 32, 72, s);
+  if (rc) return rc;
+  rc = bimage(packed + P.tc32_w2c_hi, packed + P.tc32_w2c_lo, packed + P.tc16_w2c, p.fuse_det_w[1], 32, 8, 16, 32, s);
+  if (rc) return rc;
   return 0;
 }
 

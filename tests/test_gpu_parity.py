@@ -112,8 +112,9 @@ def test_anchors_stage_tcgen05(name, force_tc_anchors):
     _anchors_stage(name)
 
 
+@pytest.mark.parametrize("raw_hi", [0, 1])
 @pytest.mark.parametrize("B", [12, 130])
-def test_anchor_paths_agree_at_m200(B):
+def test_anchor_paths_agree_at_m200(B, raw_hi):
     """Streaming CUDA-core kernel vs tcgen05 kernel on the headline shape (K = 64000, 4 x 1000 rows), one and two
     batch tiles."""
     M = 200
@@ -129,10 +130,12 @@ def test_anchor_paths_agree_at_m200(B):
     out = {}
     for mode in (_cabi.ANCHOR_STREAM, _cabi.ANCHOR_TC):
         lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, mode)
+        lib.shasta_set_option(_cabi.OPT_TC_RAW_HI, raw_hi)
         try:
             st.anchors(boxes, boxes)
         finally:
             lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, _cabi.ANCHOR_AUTO)
+            lib.shasta_set_option(_cabi.OPT_TC_RAW_HI, 0)
         torch.cuda.synchronize()
         out[mode] = torch.cat([fc[:, M:], fp[:, M:]], dim=1).clone()
     a, b = out[_cabi.ANCHOR_STREAM].cpu().numpy(), out[_cabi.ANCHOR_TC].cpu().numpy()
@@ -141,15 +144,17 @@ def test_anchor_paths_agree_at_m200(B):
     xc = fc[:, :M].reshape(B, -1).double()
     xp = fp[:, :M].reshape(B, -1).double()
     ref = []
-    for i, x in ((2, xp), (3, xp), (0, xc), (1, xc)):
-        l0, l2 = model.aug_shape[i][0], model.aug_shape[i][2]
-        h = torch.relu(x @ l0.weight.double().T + l0.bias.double())
-        ref.append(torch.abs(h @ l2.weight.double().T + l2.bias.double()))
+    with torch.no_grad():
+        for i, x in ((2, xp), (3, xp), (0, xc), (1, xc)):
+            l0, l2 = model.aug_shape[i][0], model.aug_shape[i][2]
+            h = torch.relu(x @ l0.weight.double().T + l0.bias.double())
+            ref.append(torch.abs(h @ l2.weight.double().T + l2.bias.double()))
     ref = torch.stack(ref, dim=1).cpu().numpy()
     scale = np.abs(ref).max()
     err_stream = np.abs(a - ref).max() / scale
     err_tc = np.abs(b - ref).max() / scale
-    print("anchor L1+L2 max err / scale vs float64: streaming fp32 %.3g, tcgen05 3xTF32 %.3g" % (err_stream, err_tc))
+    print("anchor L1+L2 max err / scale vs float64 (B=%d raw_hi=%d): streaming fp32 %.3g, tcgen05 3xTF32 %.3g"
+          % (B, raw_hi, err_stream, err_tc))
     assert err_stream < 1e-4 and err_tc < 1e-4, (err_stream, err_tc)
 
 
