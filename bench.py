@@ -36,7 +36,7 @@ UNIT = "frame-pairs/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frame pairs per step per GPU")
@@ -87,15 +87,20 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples that arrived inside [t_begin, t_end] (widened by one sampling period)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows
+                if (t_begin is None or ts >= t_begin - 0.12) and (t_end is None or ts <= t_end + 0.12)]
+        if not rows:
+            rows = [r for (_, r) in self.rows[-2:]]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -298,13 +303,16 @@ def main():
         torch.cuda.synchronize()
 
     with torch.no_grad():
+        # the clock sampler starts BEFORE the warm-up: nvidia-smi start-up can stall the GPU for milliseconds
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.5)
         for _ in range(max(a.warmup, 3)):
             step()
         launches_per_step = lib.shasta_last_launch_count()
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin = time.time()
         e0.record()
         for _ in range(a.steps):
             m1, m2 = step()
@@ -321,7 +329,13 @@ def main():
                 dist.all_gather_into_tensor(gathered, dec_pack)
         e1.record()
         barrier()
-        clocks = sampler.stop()
+        t_end = time.time()
+        if t_end - t_begin < 0.35:   # keep the GPU under the same load until a few clock samples exist
+            while time.time() - t_begin < 0.35:
+                step()
+            torch.cuda.synchronize()
+            t_end = time.time()
+        clocks = sampler.stop(t_begin, t_end)
         ms = e0.elapsed_time(e1)
         if dist is not None:
             tms = torch.tensor([ms], device=device)

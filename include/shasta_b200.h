@@ -79,6 +79,7 @@ typedef struct shasta_geom {
  *   BOX_*   (B,T,8)    augmented boxes [x,y,z,w,l,h,yaw,0]; BOX_CUR is back-projected (shasta.py:270-274)
  *   HIDDEN_PART (S,B,4,5M) split-K partial sums of aug_shape.i.0
  *   PROJ_PREV (B,T,144) ; PROJ_CUR (B,144,DP) k-major, DP = D rounded up to 64 ; first-layer projections
+ *   PROJ_CUR_T (B,T,144) the same current-frame projections object-major (operand of the tcgen05 pairwise tiles)
  *   AUX_*   (B,T,8)    [x,y,z,log w,log l,log h,cos yaw,sin yaw] of the augmented boxes
  *   COLNORM (B,D)      L2 norm over T of the squared-distance column (F.normalize, shasta.py:279)
  *   RESIDUAL / LOGITS (B,T,RS) with RS = D rounded up to 4
@@ -98,7 +99,8 @@ enum shasta_region {
   SHASTA_WS_RESIDUAL = 10,
   SHASTA_WS_LOGITS = 11,
   SHASTA_WS_ANCHOR_BOX = 12,
-  SHASTA_WS_NUM_REGIONS = 13
+  SHASTA_WS_PROJ_CUR_T = 13,
+  SHASTA_WS_NUM_REGIONS = 14
 };
 
 /* Runtime options (process-wide, not thread-safe; meant for tests and benchmarks).

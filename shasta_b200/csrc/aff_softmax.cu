@@ -5,14 +5,14 @@
 //   matched2 = softmax(matched[:, :, :-2], dim=1)   real detections over {previous objects, newborn, FP}
 // Reference: shasta.py:94-109,323-325.
 //
-// aff_row_kernel: a CTA owns 16 rows; activations stay in shared memory between the six layers (k-major,
-// [width][16]); transposed weights stream from L2 with coalesced loads; the row softmax is done by the same CTA
+// aff_row_kernel: a CTA owns 32 rows; activations stay in shared memory between the six layers (k-major,
+// [width][32]); transposed weights stream from L2 with coalesced loads; the row softmax is done by the same CTA
 // with warp-shuffle reductions. col_softmax_kernel does the column direction over the L2-resident logits.
 #include "common.cuh"
 
 namespace shasta {
 
-constexpr int kAffRows = 16;
+constexpr int kAffRows = 32;
 constexpr int kAffThreads = 256;
 
 // out[j][r] = act(bias[j] + sum_k in[k][r] * WT[k][j]),  N compile-time (<= 128)
@@ -20,15 +20,32 @@ template <int N, bool RELU>
 __device__ __forceinline__ void dense_fixed(const float* __restrict__ in, const float* __restrict__ WT,
                                             const float* __restrict__ bias, float* __restrict__ out, int K) {
   constexpr int G = kAffThreads / N;      // thread groups over rows
-  constexpr int RPT = kAffRows / G;       // rows per thread: 8, 4 or 2
+  constexpr int RPT = kAffRows / G;       // rows per thread: 16, 8 or 4
   const int j = threadIdx.x % N, g = threadIdx.x / N;
   const int r0 = g * RPT;
   float acc[RPT];
   const float bj = __ldg(bias + j);
 #pragma unroll
   for (int r = 0; r < RPT; ++r) acc[r] = bj;
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
+  int k = 0;
+  for (; k + 4 <= K; k += 4) {  // four independent weight loads in flight per thread
+    float w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[u] = __ldg(WT + (size_t)(k + u) * N + j);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4* ip = reinterpret_cast<const float4*>(in + (k + u) * kAffRows + r0);
+#pragma unroll
+      for (int q = 0; q < RPT / 4; ++q) {
+        const float4 v = ip[q];
+        acc[q * 4 + 0] = fmaf(v.x, w[u], acc[q * 4 + 0]);
+        acc[q * 4 + 1] = fmaf(v.y, w[u], acc[q * 4 + 1]);
+        acc[q * 4 + 2] = fmaf(v.z, w[u], acc[q * 4 + 2]);
+        acc[q * 4 + 3] = fmaf(v.w, w[u], acc[q * 4 + 3]);
+      }
+    }
+  }
+  for (; k < K; ++k) {
     const float w = __ldg(WT + (size_t)k * N + j);
     const float* ip = in + k * kAffRows + r0;
 #pragma unroll
@@ -43,14 +60,14 @@ aff_row_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, con
                float* __restrict__ logits, float* __restrict__ matched1) {
   extern __shared__ __align__(16) float sm[];
   const int T = M + 2, D = M + 2, RS = row_stride(M);
-  float* bufA = sm;                          // [D][16]  input rows, later the logits
-  float* bufB = sm + (size_t)D * kAffRows;   // [128][16]
-  float* bufC = bufB + 128 * kAffRows;       // [128][16]
+  float* bufA = sm;                          // [D][32]  input rows, later the logits
+  float* bufB = sm + (size_t)D * kAffRows;   // [128][32]
+  float* bufC = bufB + 128 * kAffRows;       // [128][32]
   const long long row0 = (long long)blockIdx.x * kAffRows;
   const long long nrows = (long long)B * T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // stage 16 residual rows, transposed to [d][r]
+  // stage 32 residual rows, transposed to [d][r]
   for (int r = warp; r < kAffRows; r += kAffThreads / 32) {
     const long long row = row0 + r;
     const float* src = residual + (size_t)row * RS;
@@ -69,7 +86,7 @@ aff_row_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, con
   dense_fixed<128, true>(bufC, packed + P.aff_w[4], packed + P.aff_b[4], bufB, 64);
   __syncthreads();
 
-  // last layer 128 -> D, all 16 rows per thread, logits to shared (bufA) and to global
+  // last layer 128 -> D, all 32 rows per thread, logits to shared (bufA) and to global
   {
     const float* WT = packed + P.aff_w[5];
     const float* bias = packed + P.aff_b[5];
@@ -78,17 +95,21 @@ aff_row_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, con
       const float bj = __ldg(bias + j);
 #pragma unroll
       for (int r = 0; r < kAffRows; ++r) acc[r] = bj;
-#pragma unroll 2
-      for (int k = 0; k < 128; ++k) {
-        const float w = __ldg(WT + (size_t)k * D + j);
-        const float4* ip = reinterpret_cast<const float4*>(bufB + k * kAffRows);
+      for (int k = 0; k < 128; k += 4) {
+        float w[4];
 #pragma unroll
-        for (int q = 0; q < kAffRows / 4; ++q) {
-          const float4 v = ip[q];
-          acc[q * 4 + 0] = fmaf(v.x, w, acc[q * 4 + 0]);
-          acc[q * 4 + 1] = fmaf(v.y, w, acc[q * 4 + 1]);
-          acc[q * 4 + 2] = fmaf(v.z, w, acc[q * 4 + 2]);
-          acc[q * 4 + 3] = fmaf(v.w, w, acc[q * 4 + 3]);
+        for (int u = 0; u < 4; ++u) w[u] = __ldg(WT + (size_t)(k + u) * D + j);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4* ip = reinterpret_cast<const float4*>(bufB + (k + u) * kAffRows);
+#pragma unroll
+          for (int q = 0; q < kAffRows / 4; ++q) {
+            const float4 v = ip[q];
+            acc[q * 4 + 0] = fmaf(v.x, w[u], acc[q * 4 + 0]);
+            acc[q * 4 + 1] = fmaf(v.y, w[u], acc[q * 4 + 1]);
+            acc[q * 4 + 2] = fmaf(v.z, w[u], acc[q * 4 + 2]);
+            acc[q * 4 + 3] = fmaf(v.w, w[u], acc[q * 4 + 3]);
+          }
         }
       }
 #pragma unroll

@@ -118,7 +118,8 @@ struct AnchorFinishArgs {
   const float* db2[4];
 };
 
-// grid: x = 5 roles (anchor 0..3, 4 = real-box copy / back-projection), y = output slices, z = frame-pair groups
+// grid: x = 9 roles (0-3 anchor shape i, 4 real-box copy / back-projection, 5-8 anchor box i), y = output slices,
+// z = frame-pair groups
 // kFinishBG = frame pairs per CTA (their hidden vectors live in shared memory)
 template <int kFinishBG>
 __global__ void __launch_bounds__(256)
@@ -155,9 +156,60 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
     return;
   }
 
+  if (role >= 5) {
+    // ---- aug_dets.i : Linear(7M -> 7M/32) + ReLU + Linear(-> 7), abs on dims 3:6        shasta.py:69-76,260-267
+    if (blockIdx.y != 0) return;
+    const int i = role - 5;
+    const float* src = (i < 2) ? det_boxes : prev_boxes;  // boxes BEFORE back-projection
+    const int K7 = 7 * M;
+    float* xb = sm;            // [2][K7] flat (M,7) boxes of two frame pairs
+    float* hd = sm + 2 * K7;   // [2][H7]
+    for (int bb = 0; bb < nb; bb += 2) {
+      const int nb2 = min(2, nb - bb);
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < nb2 * K7; idx += blockDim.x) {
+        const int g = idx / K7, k = idx % K7;
+        xb[idx] = src[((size_t)(bg0 + bb + g) * M + k / 7) * 11 + (k % 7)];
+      }
+      __syncthreads();
+      for (int h = warp; h < H7; h += 8) {
+        const float* wr = a.dw0[i] + (size_t)h * K7;
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+        for (int k = lane; k < K7; k += 32) {
+          const float wv = __ldg(wr + k);
+          acc0 = fmaf(wv, xb[k], acc0);
+          acc1 = fmaf(wv, xb[K7 + k], acc1);
+        }
+        acc0 = warp_sum(acc0);
+        acc1 = warp_sum(acc1);
+        if (lane == 0) {
+          const float bh = a.db0[i][h];
+          hd[h] = fmaxf(acc0 + bh, 0.f);
+          hd[H7 + h] = fmaxf(acc1 + bh, 0.f);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < nb2 * 8) {
+        const int g = threadIdx.x >> 3, c = threadIdx.x & 7;
+        const int b = bg0 + bb + g;
+        float v = 0.f;
+        if (c < 7) {
+          float acc = 0.f;
+          for (int h = 0; h < H7; ++h) acc = fmaf(a.dw2[i][c * H7 + h], hd[g * H7 + h], acc);
+          v = acc + a.db2[i][c];
+          if (c >= 3 && c < 6) v = fabsf(v);
+          anchor_box[((size_t)b * 4 + i) * 7 + c] = v;
+        }
+        float* bdst = (i < 2) ? box_prev : box_cur;
+        bdst[((size_t)b * T + M + (i & 1)) * 8 + c] = v;
+      }
+    }
+    return;
+  }
+
   const int i = role;
   float* hid = sm;                      // [kFinishBG][N5]
-  float* hd = sm + kFinishBG * N5;      // [kFinishBG][max(H7,1)]
 
   // ---- hidden = relu(sum over splits + bias)        aug_shape.i.0 + ReLU
   for (int idx = threadIdx.x; idx < nb * N5; idx += blockDim.x) {
@@ -208,36 +260,6 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
     }
   }
 
-  // ---- aug_dets.i (only the first output slice does it)
-  if (blockIdx.y == 0) {
-    const float* src = (i < 2) ? det_boxes : prev_boxes;
-    const int K7 = 7 * M;
-    for (int o = warp; o < nb * H7; o += 8) {
-      const int bg = o / H7, h = o % H7;
-      const float* wr = a.dw0[i] + (size_t)h * K7;
-      const float* bx = src + (size_t)(bg0 + bg) * M * 11;
-      float acc = 0.f;
-      for (int k = lane; k < K7; k += 32) acc = fmaf(__ldg(wr + k), bx[(k / 7) * 11 + (k % 7)], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) hd[bg * H7 + h] = fmaxf(acc + a.db0[i][h], 0.f);
-    }
-    __syncthreads();
-    if (threadIdx.x < nb * 8) {
-      const int bg = threadIdx.x >> 3, c = threadIdx.x & 7;
-      const int b = bg0 + bg;
-      float v = 0.f;
-      if (c < 7) {
-        v = a.db2[i][c];
-        float acc = 0.f;
-        for (int h = 0; h < H7; ++h) acc = fmaf(a.dw2[i][c * H7 + h], hd[bg * H7 + h], acc);
-        v = acc + v;
-        if (c >= 3 && c < 6) v = fabsf(v);
-        anchor_box[((size_t)b * 4 + i) * 7 + c] = v;
-      }
-      float* bdst = (i < 2) ? box_prev : box_cur;
-      bdst[((size_t)b * T + M + (i & 1)) * 8 + c] = v;
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -291,7 +313,9 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   }
   const int H7 = (7 * M) / 32;
   const int BG = (B > 4 && (size_t)8 * (N5 + H7 + 1) * sizeof(float) <= 200 * 1024) ? 8 : 4;
-  const size_t smem = sizeof(float) * ((size_t)BG * N5 + (size_t)BG * (H7 > 0 ? H7 : 1));
+  const size_t smem_shape = sizeof(float) * (size_t)BG * N5;
+  const size_t smem_dets = sizeof(float) * (2 * (size_t)(7 * M) + 2 * (size_t)(H7 > 0 ? H7 : 1));
+  const size_t smem = smem_shape > smem_dets ? smem_shape : smem_dets;
   static size_t configured[2] = {0, 0};
   if (smem > 48 * 1024 && smem > configured[BG == 8]) {
     if (BG == 8)
@@ -302,7 +326,7 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   }
   const int groups = (B + BG - 1) / BG;
   const int slices = (groups >= 16) ? 2 : (groups >= 6 ? 5 : 10);  // 320 outputs = 10 passes of 32 rows
-  dim3 fgrid(5, slices, groups);
+  dim3 fgrid(9, slices, groups);  // roles: 0-3 anchor shapes, 4 box copy, 5-8 anchor boxes
   float* bc = ws + L.off[SHASTA_WS_BOX_CUR];
   float* bp = ws + L.off[SHASTA_WS_BOX_PREV];
   float* ab = ws + L.off[SHASTA_WS_ANCHOR_BOX];

@@ -47,6 +47,7 @@ __host__ inline WsLayout ws_layout(int B, int M) {
   sz[SHASTA_WS_RESIDUAL] = (size_t)B * T * row_stride(M);
   sz[SHASTA_WS_LOGITS] = (size_t)B * T * row_stride(M);
   sz[SHASTA_WS_ANCHOR_BOX] = (size_t)B * 4 * 7;
+  sz[SHASTA_WS_PROJ_CUR_T] = (size_t)B * T * kProj;
   size_t o = 0;
   for (int i = 0; i < SHASTA_WS_NUM_REGIONS; ++i) {
     L.off[i] = o;
@@ -80,7 +81,7 @@ struct PackLayout {
   size_t tc32_begin;  // tf32 block: w2a hi, w2a lo (10x32x4 each), w2b hi, lo (18x32x4), w2c hi, lo (8x16x4)
   size_t tc32_w2a_hi, tc32_w2a_lo, tc32_w2b_hi, tc32_w2b_lo, tc32_w2c_hi, tc32_w2c_lo;
   size_t tc32_end;
-  size_t tc16_begin;  // bf16 block (counted in floats): w2a (5x32x8 bf16), w2b (9x32x8), w2c (4x16x8)
+  size_t tc16_begin;  // bf16 block (counted in floats): w2a (6x32x8 bf16), w2b (10x32x8), w2c (4x16x8)
   size_t tc16_w2a, tc16_w2b, tc16_w2c;
   size_t tc16_end;
   size_t total;       // floats
@@ -130,8 +131,8 @@ __host__ inline PackLayout pack_layout(int M) {
   P.tc32_w2c_lo = take(8 * 16 * 4);
   P.tc32_end = o;
   P.tc16_begin = o;
-  P.tc16_w2a = take(5 * 32 * 8 / 2);
-  P.tc16_w2b = take(9 * 32 * 8 / 2);
+  P.tc16_w2a = take(6 * 32 * 8 / 2);   // K = 40 padded to 48 (3 MMA steps of 16), pad chunks stay zero
+  P.tc16_w2b = take(10 * 32 * 8 / 2);  // K = 72 padded to 80
   P.tc16_w2c = take(4 * 16 * 8 / 2);
   P.tc16_end = o;
   P.total = o;

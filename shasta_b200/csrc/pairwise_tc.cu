@@ -1,14 +1,412 @@
-// Tensor-core (tcgen05 / TMEM) variants of the pairwise stage. Placeholder until the tcgen05 tile kernel lands:
-// the entry point exists so the C ABI is stable, and reports SHASTA_ERR_UNSUPPORTED instead of silently falling back.
+// Pairwise stage on the 5th-generation tensor cores (north-star "remaining pairwise layers
+// are tcgen05/TMEM tiles").
+//
+// One MMA tile = 128 (t,d) pairs = 128 TMEM lanes. A worker thread owns one pair: it forms
+// h1 = ReLU(PROJ_PREV[t] + PROJ_CUR[d]) in registers (the on-chip outer sum) and stores it straight into TENSOR
+// MEMORY with tcgen05.st as the A operand of the second-layer GEMMs — the pair activations never touch shared or
+// global memory. The second layers of the three pairwise MLPs are block-diagonal, so they run as three small UMMAs
+//   fuse_det.2   : [128 x 32] x [32 x 16]    fuse_shape.2 : [128 x 40] x [40 x 32]    res_coeff.2 : [128 x 72] x [72 x 32]
+// with the weights as pre-split, zero-padded B-operand images in shared memory (pack.cu). Accumulators come back
+// with tcgen05.ld; bias/ReLU, the tiny third/fourth layers, the hand-designed residuals and the weighted sum
+// (shasta.py:277-319) finish in the same thread.
+//   variant 1 (fp32 mode): kind::tf32, three MMAs per K step on hi/lo splits (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo)
+//   variant 2 (bf16 mode): kind::f16 with bf16 operands, one MMA per K step, fp32 accumulate.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace shasta {
 
+using namespace tc;
+
+constexpr int kPtTT = 8;            // t rows per CTA
+constexpr int kPtDT = 64;           // d columns per CTA = 4 MMA tiles of 8 x 16 pairs
+constexpr int kPtQStride = 148;     // floats per d row of the staged PROJ_CUR tile (148 % 32 = 20: conflict-free LDS.128)
+constexpr int kPtThreads = 160;     // 4 worker warps + 1 MMA warp
+constexpr int kPtTmemCols = 256;
+
+// TMEM column map (per CTA): A operands share [0,144), accumulators live in [144,224)
+constexpr int kColDetHi = 0, kColDetLo = 32;       // K = 32
+constexpr int kColShpHi = 64, kColShpLo = 104;     // K = 40
+constexpr int kColCofHi = 0, kColCofLo = 72;       // K = 72 (reuses the det/shape columns once their MMAs retired)
+constexpr int kColDShp = 144, kColDCof = 176, kColDDet = 208;
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]^T
+__device__ __forceinline__ void mma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ float relu_f(float x) { return fmaxf(x, 0.f); }
+
+// Builds K columns of the A operand for one pair: h[k] = relu(p[k] + q[k]), k in [koff, koff+K).
+// tf32: hi at col_hi + k, lo at col_lo + k (one 32-bit column per element);  bf16: packed pairs at col_hi + k/2.
+template <bool BF16, int K>
+__device__ __forceinline__ void build_a(const float* __restrict__ prow, const float* __restrict__ qrow, int koff,
+                                        uint32_t tmem_lane_base, int col_hi, int col_lo) {
+#pragma unroll
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    const float4 p0 = *reinterpret_cast<const float4*>(prow + koff + k0);
+    const float4 p1 = *reinterpret_cast<const float4*>(prow + koff + k0 + 4);
+    const float4 q0 = *reinterpret_cast<const float4*>(qrow + koff + k0);
+    const float4 q1 = *reinterpret_cast<const float4*>(qrow + koff + k0 + 4);
+    const float h[8] = {relu_f(p0.x + q0.x), relu_f(p0.y + q0.y), relu_f(p0.z + q0.z), relu_f(p0.w + q0.w),
+                        relu_f(p1.x + q1.x), relu_f(p1.y + q1.y), relu_f(p1.z + q1.z), relu_f(p1.w + q1.w)};
+    if (BF16) {
+      uint32_t v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(h[2 * j], h[2 * j + 1]);  // low half = even k
+        v[j] = *reinterpret_cast<const uint32_t*>(&b2);
+      }
+      tmem_st4(tmem_lane_base + (uint32_t)(col_hi + k0 / 2), v);
+    } else {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        hi[j] = __float_as_uint(h[j]) & 0xffffe000u;
+        lo[j] = __float_as_uint(h[j] - __uint_as_float(hi[j]));
+      }
+      tmem_st8(tmem_lane_base + (uint32_t)(col_hi + k0), hi);
+      tmem_st8(tmem_lane_base + (uint32_t)(col_lo + k0), lo);
+    }
+  }
+}
+
+struct PtSmem {  // float offsets inside dynamic shared memory (after the 1 KB aligned base)
+  static constexpr int ps = 0;                                  // [8][144]
+  static constexpr int qs = ps + kPtTT * kProj;                 // [64][148]
+  static constexpr int auxp = qs + kPtDT * kPtQStride;          // [8][8]
+  static constexpr int auxc = auxp + kPtTT * 8;                 // [64][8]
+  static constexpr int cn = auxc + kPtDT * 8;                   // [64]
+  static constexpr int w = cn + kPtDT;                          // small-layer block (l2a .. pair_end of PackLayout)
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(kPtThreads, 2)
+pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, const float* __restrict__ proj_prev,
+                   const float* __restrict__ proj_cur_t, const float* __restrict__ aux_prev,
+                   const float* __restrict__ aux_cur, const float* __restrict__ colnorm,
+                   float* __restrict__ residual) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int T = M + 2, D = M + 2;
+  const int RS = row_stride(M);
+  const int b = blockIdx.z, t0 = blockIdx.y * kPtTT, d0 = blockIdx.x * kPtDT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- shared memory carve-up: [B-operand images (128 B aligned)] [barriers] [float region]
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
+  const int bimg_floats = BF16 ? (int)(P.tc16_end - P.tc16_begin) : (int)(P.tc32_end - P.tc32_begin);
+  float* bimg = reinterpret_cast<float*>(gbase);
+  const uint32_t bars = sbase + bimg_floats * 4;                     // 6 mbarriers + tmem slot
+  float* fl = reinterpret_cast<float*>(gbase + bimg_floats * 4 + 64);
+  float* Ps = fl + PtSmem::ps;
+  float* Qs = fl + PtSmem::qs;
+  float* Ap = fl + PtSmem::auxp;
+  float* Ac = fl + PtSmem::auxc;
+  float* Cn = fl + PtSmem::cn;
+  float* Ws = fl + PtSmem::w;
+  const int wbase = (int)P.l2a, wcount = (int)(P.pair_end - P.l2a);
+  auto bar_a = [&](int x) { return bars + 8u * x; };        // x: 0 det, 1 shape, 2 coeff  (A operand ready)
+  auto bar_d = [&](int x) { return bars + 8u * (3 + x); };  // accumulator ready
+  const uint32_t tmem_slot = bars + 48;
+
+  if (tid == 0) {
+    for (int x = 0; x < 3; ++x) mbar_init(bar_a(x), 128), mbar_init(bar_d(x), 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, kPtTmemCols);
+
+  // ---- stage operands (all 160 threads) ----
+  {
+    const float4* src = reinterpret_cast<const float4*>(packed + (BF16 ? P.tc16_begin : P.tc32_begin));
+    for (int v = tid; v < bimg_floats / 4; v += kPtThreads) reinterpret_cast<float4*>(bimg)[v] = __ldg(src + v);
+    const int nt = min(kPtTT, T - t0);
+    const float4* psrc = reinterpret_cast<const float4*>(proj_prev + ((size_t)b * T + t0) * kProj);
+    for (int v = tid; v < kPtTT * kProj / 4; v += kPtThreads)
+      reinterpret_cast<float4*>(Ps)[v] = (v < nt * kProj / 4) ? __ldg(psrc + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // PROJ_CUR_T is (B,T,144) object-major: 64 rows of 144 floats, padded to a stride of 148 in shared memory
+    const int ndq = max(0, min(kPtDT, D - d0));
+    const float4* qsrc = reinterpret_cast<const float4*>(proj_cur_t + ((size_t)b * T + d0) * kProj);
+    for (int v = tid; v < kPtDT * (kProj / 4); v += kPtThreads) {
+      const int dr = v / (kProj / 4), k4 = v % (kProj / 4);
+      reinterpret_cast<float4*>(Qs + dr * kPtQStride)[k4] =
+          (dr < ndq) ? __ldg(qsrc + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float4* apsrc = reinterpret_cast<const float4*>(aux_prev + ((size_t)b * T + t0) * 8);
+    if (tid < kPtTT * 2)
+      reinterpret_cast<float4*>(Ap)[tid] = (tid < nt * 2) ? __ldg(apsrc + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nd = max(0, min(kPtDT, D - d0));
+    const float4* acsrc = reinterpret_cast<const float4*>(aux_cur + ((size_t)b * T + d0) * 8);
+    for (int v = tid; v < kPtDT * 2; v += kPtThreads)
+      reinterpret_cast<float4*>(Ac)[v] = (v < nd * 2) ? __ldg(acsrc + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < kPtDT) Cn[tid] = (tid < nd) ? colnorm[(size_t)b * T + d0 + tid] : 1.f;
+    for (int v = tid; v < wcount / 4; v += kPtThreads)
+      reinterpret_cast<float4*>(Ws)[v] = __ldg(reinterpret_cast<const float4*>(packed + wbase) + v);
+  }
+  fence_proxy_async_smem();  // B images were written by the generic proxy, UMMA reads them through the async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - sbase));
+
+  const int ntiles = kPtDT / 16;
+
+  if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // B images: [k chunk][n][16 bytes]; chunk stride (LBO) = N*16 bytes, 8-row group stride (SBO) = 128 bytes
+      const uint32_t bi = sbase;
+      uint32_t off_a_hi, off_a_lo, off_b_hi, off_b_lo, off_c_hi, off_c_lo;
+      if (BF16) {
+        off_a_hi = (uint32_t)(P.tc16_w2a - P.tc16_begin) * 4, off_b_hi = (uint32_t)(P.tc16_w2b - P.tc16_begin) * 4;
+        off_c_hi = (uint32_t)(P.tc16_w2c - P.tc16_begin) * 4;
+        off_a_lo = off_b_lo = off_c_lo = 0;
+      } else {
+        off_a_hi = (uint32_t)(P.tc32_w2a_hi - P.tc32_begin) * 4, off_a_lo = (uint32_t)(P.tc32_w2a_lo - P.tc32_begin) * 4;
+        off_b_hi = (uint32_t)(P.tc32_w2b_hi - P.tc32_begin) * 4, off_b_lo = (uint32_t)(P.tc32_w2b_lo - P.tc32_begin) * 4;
+        off_c_hi = (uint32_t)(P.tc32_w2c_hi - P.tc32_begin) * 4, off_c_lo = (uint32_t)(P.tc32_w2c_lo - P.tc32_begin) * 4;
+      }
+      constexpr uint32_t fmt = BF16 ? kFmtBF16 : kFmtTF32;
+      constexpr uint32_t idesc32 = umma_idesc(fmt, 128, 32), idesc16 = umma_idesc(fmt, 128, 16);
+      // one K step = 32 bytes of K per row = 2 chunks of the B image = 8 A columns (tf32: 8 x 32 bit, bf16: 16 x 16 bit)
+      auto run = [&](int ksteps, int n, uint32_t idesc, uint32_t d_col, int a_hi, int a_lo, uint32_t b_hi,
+                     uint32_t b_lo) {
+        const uint32_t lbo = (uint32_t)n * 16u;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t dbh = umma_desc_noswz(bi + b_hi + (uint32_t)k * 2u * lbo, lbo, 128);
+          if (BF16) {
+            mma_ts_f16(tmem + d_col, tmem + (uint32_t)(a_hi + 8 * k), dbh, idesc, k != 0);
+          } else {
+            const uint64_t dbl = umma_desc_noswz(bi + b_lo + (uint32_t)k * 2u * lbo, lbo, 128);
+            mma_ts_tf32(tmem + d_col, tmem + (uint32_t)(a_hi + 8 * k), dbh, idesc, k != 0);
+            mma_ts_tf32(tmem + d_col, tmem + (uint32_t)(a_lo + 8 * k), dbh, idesc, 1);
+            mma_ts_tf32(tmem + d_col, tmem + (uint32_t)(a_hi + 8 * k), dbl, idesc, 1);
+          }
+        }
+      };
+      for (int tile = 0; tile < ntiles; ++tile) {
+        const uint32_t ph = tile & 1;
+        mbar_wait(bar_a(0), ph);
+        tc_fence_after();
+        run(BF16 ? 2 : 4, 16, idesc16, kColDDet, kColDetHi, kColDetLo, off_c_hi, off_c_lo);   // fuse_det.2, K = 32
+        mma_commit(bar_d(0));
+        mbar_wait(bar_a(1), ph);
+        tc_fence_after();
+        run(BF16 ? 3 : 5, 32, idesc32, kColDShp, kColShpHi, kColShpLo, off_a_hi, off_a_lo);   // fuse_shape.2, K = 40
+        mma_commit(bar_d(1));
+        mbar_wait(bar_a(2), ph);
+        tc_fence_after();
+        run(BF16 ? 5 : 9, 32, idesc32, kColDCof, kColCofHi, kColCofLo, off_b_hi, off_b_lo);   // res_coeff.2, K = 72
+        mma_commit(bar_d(2));
+      }
+    }
+  } else {
+    // ===================== workers: one thread = one (t,d) pair = one TMEM lane =====================
+    const int r = tid;                 // 0..127
+    const int ti = r >> 4, di = r & 15;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's TMEM lane quarter
+    const float* prow = Ps + ti * kProj;
+    const float* B2a = Ws + (P.l2a_b - wbase);
+    const float* B2b = Ws + (P.l2b_b - wbase);
+    const float* B2c = Ws + (P.l2c_b - wbase);
+    const float* W3a = Ws + (P.l3a - wbase);
+    const float* B3a = Ws + (P.l3a_b - wbase);
+    const float* W4a = Ws + (P.l4a - wbase);
+    const float* B4a = Ws + (P.l4a_b - wbase);
+    const float* W3b = Ws + (P.l3b - wbase);
+    const float* B3b = Ws + (P.l3b_b - wbase);
+    const float* W3c = Ws + (P.l3c - wbase);
+    const float* B3c = Ws + (P.l3c_b - wbase);
+    const float4 ap0 = *reinterpret_cast<const float4*>(Ap + ti * 8);
+    const float4 ap1 = *reinterpret_cast<const float4*>(Ap + ti * 8 + 4);
+    const int t = t0 + ti;
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const uint32_t ph = tile & 1;
+      const int dl = tile * 16 + di;
+      const float* qrow = Qs + dl * kPtQStride;
+
+      // (1) A operands of fuse_det.2 and fuse_shape.2 (disjoint TMEM columns)
+      build_a<BF16, 32>(prow, qrow, 112, lane_base, BF16 ? kColDetHi : kColDetHi, kColDetLo);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_a(0));
+      // bf16 packs two k per column: 40 bf16 = 20 columns; K is padded to 48 (3 steps of 16) with zero columns
+      if (BF16) {
+        build_a<true, 40>(prow, qrow, 0, lane_base, kColShpHi, kColShpLo);
+        const uint32_t z[4] = {0u, 0u, 0u, 0u};
+        tmem_st4(lane_base + (uint32_t)(kColShpHi + 20), z);
+      } else {
+        build_a<false, 40>(prow, qrow, 0, lane_base, kColShpHi, kColShpLo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_a(1));
+
+      // (2) fuse_det epilogue: 8 -> 1
+      float fused, shape;
+      {
+        mbar_wait(bar_d(0), ph);
+        tc_fence_after();
+        uint32_t v[8];
+        tmem_ld8(lane_base + kColDDet, v);
+        tmem_ld_wait();
+        float s = B3c[0];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s = fmaf(relu_f(__uint_as_float(v[k]) + B2c[k]), W3c[k], s);
+        fused = s;
+      }
+      // (3) fuse_shape epilogue: 20 -> 10 -> 1
+      {
+        mbar_wait(bar_d(1), ph);
+        tc_fence_after();
+        uint32_t v[16], v2[8];
+        tmem_ld16(lane_base + kColDShp, v);
+        tmem_ld8(lane_base + kColDShp + 16, v2);
+        tmem_ld_wait();
+        float a3[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) a3[j] = B3a[j];
+#pragma unroll
+        for (int k = 0; k < 20; ++k) {
+          const float h = relu_f(__uint_as_float(k < 16 ? v[k] : v2[k - 16]) + B2a[k]);
+#pragma unroll
+          for (int j4 = 0; j4 < 3; ++j4) {
+            const float4 w = *reinterpret_cast<const float4*>(W3a + k * 12 + j4 * 4);
+            a3[j4 * 4 + 0] = fmaf(h, w.x, a3[j4 * 4 + 0]);
+            a3[j4 * 4 + 1] = fmaf(h, w.y, a3[j4 * 4 + 1]);
+            a3[j4 * 4 + 2] = fmaf(h, w.z, a3[j4 * 4 + 2]);
+            a3[j4 * 4 + 3] = fmaf(h, w.w, a3[j4 * 4 + 3]);
+          }
+        }
+        float s = B4a[0];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) s = fmaf(relu_f(a3[k]), W4a[k], s);
+        shape = s;
+      }
+      // (4) A operand of res_coeff.2 — overwrites the det/shape columns, whose MMAs have retired (bar_d 0,1 passed)
+      tc_fence_before();
+      if (BF16) {
+        build_a<true, 72>(prow, qrow, 40, lane_base, kColCofHi, kColCofLo);
+        const uint32_t z[4] = {0u, 0u, 0u, 0u};
+        tmem_st4(lane_base + (uint32_t)(kColCofHi + 36), z);   // K padded 72 -> 80
+      } else {
+        build_a<false, 72>(prow, qrow, 40, lane_base, kColCofHi, kColCofLo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_a(2));
+
+      // (5) hand-designed residuals while the res_coeff MMAs run          shasta.py:277-283
+      const float4 ac0 = *reinterpret_cast<const float4*>(Ac + dl * 8);
+      const float4 ac1 = *reinterpret_cast<const float4*>(Ac + dl * 8 + 4);
+      const float dx = ap0.x - ac0.x, dy = ap0.y - ac0.y, dz = ap0.z - ac0.z;
+      float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      dist = __fdiv_rn(dist, fmaxf(Cn[dl], 1e-12f));
+      const float dim = __fadd_rn(__fadd_rn(fabsf(ap0.w - ac0.w), fabsf(ap1.x - ac1.x)), fabsf(ap1.y - ac1.y));
+      const float dc = ap1.z - ac1.z, ds = ap1.w - ac1.w;
+      const float rot = sqrtf(__fadd_rn(__fmul_rn(dc, dc), __fmul_rn(ds, ds)));
+      const float res_dist = __fadd_rn(__fadd_rn(dist, dim), rot);
+
+      // (6) res_coeff epilogue: 18 -> 3, weighted sum, store
+      {
+        mbar_wait(bar_d(2), ph);
+        tc_fence_after();
+        uint32_t v[16], v2[8];
+        tmem_ld16(lane_base + kColDCof, v);
+        tmem_ld8(lane_base + kColDCof + 16, v2);
+        tmem_ld_wait();
+        const float4 b3 = *reinterpret_cast<const float4*>(B3b);
+        float alpha = b3.x, beta = b3.y, omega = b3.z;
+#pragma unroll
+        for (int k = 0; k < 18; ++k) {
+          const float h = relu_f(__uint_as_float(k < 16 ? v[k] : v2[k - 16]) + B2b[k]);
+          const float4 w = *reinterpret_cast<const float4*>(W3b + k * 4);
+          alpha = fmaf(h, w.x, alpha);
+          beta = fmaf(h, w.y, beta);
+          omega = fmaf(h, w.z, omega);
+        }
+        const float out = __fadd_rn(__fadd_rn(__fmul_rn(alpha, fused), __fmul_rn(beta, res_dist)),
+                                    __fmul_rn(omega, shape));
+        const int d = d0 + dl;
+        if (t < T && d < D) residual[((size_t)b * T + t) * RS + d] = out;
+      }
+      tc_fence_before();  // order this tile's TMEM reads before the next tile's stores / MMAs
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, kPtTmemCols);
+  }
+}
+
 int launch_pairwise_tc(const float* packed, int B, int M, float* ws, const WsLayout& L, int variant,
                        cudaStream_t s) {
-  (void)packed, (void)B, (void)M, (void)ws, (void)L, (void)s;
-  set_error("pairwise variant %d (tcgen05) is not built in this revision", variant);
-  return SHASTA_ERR_UNSUPPORTED;
+  if (variant != 1 && variant != 2) {
+    set_error("pairwise variant %d unknown (0 = CUDA cores, 1 = tcgen05 3xTF32, 2 = tcgen05 bf16)", variant);
+    return SHASTA_ERR_ARG;
+  }
+  const PackLayout P = pack_layout(M);
+  const int T = M + 2;
+  const bool bf16 = variant == 2;
+  const size_t bimg = (bf16 ? (P.tc16_end - P.tc16_begin) : (P.tc32_end - P.tc32_begin)) * sizeof(float);
+  const size_t smem = 128 + bimg + 64 + sizeof(float) * (PtSmem::w + (P.pair_end - P.l2a));
+  static bool configured[2] = {false, false};
+  if (!configured[bf16]) {
+    if (bf16)
+      SHASTA_CUDA(cudaFuncSetAttribute(pairwise_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      SHASTA_CUDA(cudaFuncSetAttribute(pairwise_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[bf16] = true;
+  }
+  dim3 grid((T + kPtDT - 1) / kPtDT, (T + kPtTT - 1) / kPtTT, B);
+  const float* pp = ws + L.off[SHASTA_WS_PROJ_PREV];
+  const float* pc = ws + L.off[SHASTA_WS_PROJ_CUR_T];
+  const float* ap = ws + L.off[SHASTA_WS_AUX_PREV];
+  const float* ac = ws + L.off[SHASTA_WS_AUX_CUR];
+  const float* cn = ws + L.off[SHASTA_WS_COLNORM];
+  float* res = ws + L.off[SHASTA_WS_RESIDUAL];
+  if (bf16)
+    pairwise_tc_kernel<true><<<grid, kPtThreads, smem, s>>>(packed, P, B, M, pp, pc, ap, ac, cn, res);
+  else
+    pairwise_tc_kernel<false><<<grid, kPtThreads, smem, s>>>(packed, P, B, M, pp, pc, ap, ac, cn, res);
+  SHASTA_CHECK_LAUNCH("pairwise_tc_kernel");
+  return 0;
 }
 
 }  // namespace shasta

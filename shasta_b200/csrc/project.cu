@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(kProjThreads)
 project_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, int nproj_blocks,
                const float* __restrict__ feat_cur, const float* __restrict__ feat_prev,
                const float* __restrict__ box_cur, const float* __restrict__ box_prev, float* __restrict__ proj_prev,
-               float* __restrict__ proj_cur, float* __restrict__ aux_prev, float* __restrict__ aux_cur,
+               float* __restrict__ proj_cur, float* __restrict__ proj_cur_t, float* __restrict__ aux_prev,
+               float* __restrict__ aux_cur,
                float* __restrict__ colnorm, float* __restrict__ det_boxes_inout) {
   const int T = M + 2;
   const int DP = proj_cur_stride(M);
@@ -161,8 +162,9 @@ project_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, int
       if (det_thread) dst[j2] = out2[o];
     } else {
       float* dst = proj_cur + (size_t)b * kProj * DP + obj;
-      if (active) dst[(size_t)j0 * DP] = out0[o], dst[(size_t)j1 * DP] = out1[o];
-      if (det_thread) dst[(size_t)j2 * DP] = out2[o];
+      float* dstt = proj_cur_t + ((size_t)b * T + obj) * kProj;
+      if (active) dst[(size_t)j0 * DP] = out0[o], dst[(size_t)j1 * DP] = out1[o], dstt[j0] = out0[o], dstt[j1] = out1[o];
+      if (det_thread) dst[(size_t)j2 * DP] = out2[o], dstt[j2] = out2[o];
     }
   }
 }
@@ -175,7 +177,8 @@ int launch_project(const float* packed, int B, int M, float* ws, const WsLayout&
   project_kernel<<<nproj + B, kProjThreads, 0, s>>>(
       packed, pack_layout(M), B, M, nproj, ws + L.off[SHASTA_WS_FEAT_CUR], ws + L.off[SHASTA_WS_FEAT_PREV],
       ws + L.off[SHASTA_WS_BOX_CUR], ws + L.off[SHASTA_WS_BOX_PREV], ws + L.off[SHASTA_WS_PROJ_PREV],
-      ws + L.off[SHASTA_WS_PROJ_CUR], ws + L.off[SHASTA_WS_AUX_PREV], ws + L.off[SHASTA_WS_AUX_CUR],
+      ws + L.off[SHASTA_WS_PROJ_CUR], ws + L.off[SHASTA_WS_PROJ_CUR_T], ws + L.off[SHASTA_WS_AUX_PREV],
+      ws + L.off[SHASTA_WS_AUX_CUR],
       ws + L.off[SHASTA_WS_COLNORM], det_boxes_inout);
   SHASTA_CHECK_LAUNCH("project_kernel");
   return 0;

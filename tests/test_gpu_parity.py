@@ -242,12 +242,18 @@ def test_project_and_pairwise_stage(name):
     cn = np.sqrt((dist ** 2).sum(axis=1))
     got_cn = st.region(_cabi.WS_COLNORM, (B, T)).cpu().numpy()
     assert np.allclose(got_cn, cn, rtol=1e-5), np.abs(got_cn - cn).max()
-    # pairwise -> residual
-    st.pairwise(0)
-    res = st.region(_cabi.WS_RESIDUAL, (B, T, st.RS)).cpu().numpy()[:, :, :T]
+    # object-major copy of the current-frame projections (operand of the tcgen05 tiles)
+    got_pct = st.region(_cabi.WS_PROJ_CUR_T, (B, T, 144)).cpu().numpy()
+    assert np.array_equal(got_pct, got_pc)
+    # pairwise -> residual: CUDA-core fp32, tcgen05 3xTF32 (fp32-equivalent), tcgen05 bf16 (separate tolerance)
     want = g["residual"]
-    err = np.abs(res - want).max() / np.abs(want).max()
-    assert err < 1e-5, "residual max err / scale = %g" % err
+    for variant, tol in ((0, 1e-5), (1, 2e-5), (2, 2e-2)):
+        st.region(_cabi.WS_RESIDUAL, (B, T, st.RS)).zero_()
+        st.pairwise(variant)
+        res = st.region(_cabi.WS_RESIDUAL, (B, T, st.RS)).cpu().numpy()[:, :, :T]
+        err = np.abs(res - want).max() / np.abs(want).max()
+        print("pairwise variant %d: residual max err / scale = %.3g" % (variant, err))
+        assert err < tol, "variant %d residual max err / scale = %g" % (variant, err)
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -274,7 +280,26 @@ def test_forward_matches_reference_golden_tcgen05_anchors(name, force_tc_anchors
     test_forward_matches_reference_golden(name, 0)
 
 
-@pytest.mark.parametrize("flags", [0, 1])
+@pytest.mark.parametrize("name", golden_names())
+def test_forward_bf16_pairwise_tolerance(name):
+    """bf16 mode of the pairwise tiles (flags 0x20): tolerance stated separately from fp32 (north_star) —
+    affinities within 2e-2 relative; association agreement is reported, not required to be identical."""
+    c, pc_start, data, weights, g = load_golden(name)
+    model = G.make_model(c["M"], pc_start, weights)
+    model.kernel_flags = 0x20
+    with torch.no_grad():
+        m1, m2 = model.affinity(G.t(data["bev"]), G.t(data["prev_bev"]), G.t(data["det_boxes"]),
+                                G.t(data["prev_det_boxes"]))
+    m1, m2 = m1.cpu().numpy(), m2.cpu().numpy()
+    e1, e2 = G.rel_err(m1, g["matched1"]), G.rel_err(m2, g["matched2"])
+    agree = float(np.mean(m1.argmax(2) == g["matched1"].argmax(2)))
+    print("bf16 pairwise: rel err m1 %.3g m2 %.3g, row-argmax agreement %.4f" % (e1, e2, agree))
+    if c["peaky"] == 0:
+        assert e1 < 2e-2 and e2 < 2e-2, (e1, e2)
+    assert np.isfinite(m1).all() and np.isfinite(m2).all()
+
+
+@pytest.mark.parametrize("flags", [0, 1, 0x10])
 @pytest.mark.parametrize("name", golden_names())
 def test_forward_matches_reference_golden(name, flags):
     c, pc_start, data, weights, g = load_golden(name)
@@ -356,13 +381,24 @@ def test_all_zero_boxes_and_out_of_range_boxes():
 # ------------------------------------------------------------------------------------------------
 # headline size: M = 200 (BASELINE.json configs[0]/[1]) against the oracle, plus size-independent properties
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("H,W,B", [(180, 180, 3), (512, 512, 1)])
-def test_headline_size_against_oracle(H, W, B):
+@pytest.mark.parametrize("H,W,B,flags,anchor", [(180, 180, 3, 0, 0), (512, 512, 1, 0, 0), (180, 180, 2, 0x10, 2)])
+def test_headline_size_against_oracle(H, W, B, flags, anchor):
+    """anchor = 2 forces the tcgen05 anchors GEMM, flags 0x10 the tcgen05 3xTF32 pairwise tiles: the fp32-equivalent
+    tensor-core path must reproduce the oracle's association exactly as well."""
     M = 200
+    _cabi.lib().shasta_set_option(_cabi.OPT_ANCHOR_PATH, anchor)
+    try:
+        _headline(M, H, W, B, flags)
+    finally:
+        _cabi.lib().shasta_set_option(_cabi.OPT_ANCHOR_PATH, 0)
+
+
+def _headline(M, H, W, B, flags):
     pc_start = (-W * 0.3, -H * 0.3)
     data = synthetic.make_frame_pairs(B, M, H, W, 2024 + H, pc_start=pc_start)
     weights = synthetic.make_weights(M, seed=21, peaky=300.0)
     model = G.make_model(M, pc_start, weights)
+    model.kernel_flags = flags
     det = G.t(data["det_boxes"])
     with torch.no_grad():
         m1, m2 = model.affinity(G.t(data["bev"]), G.t(data["prev_bev"]), det, G.t(data["prev_det_boxes"]))
