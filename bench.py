@@ -273,7 +273,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
 
-    from shasta_b200 import _cabi
+    from shasta_b200 import _cabi, sharding
     lib = _cabi.lib()
     lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, a.anchor_path)
     lib.shasta_set_option(_cabi.OPT_TC_RAW_HI, a.raw_hi)
@@ -287,10 +287,8 @@ def main():
     n_det = torch.from_numpy(d["n_det"].astype(np.int32)).to(device)
     dec_i = [torch.empty((B, M), dtype=torch.int32, device=device) for _ in range(4)]
     dec_f = [torch.empty((B, M), dtype=torch.float32, device=device) for _ in range(2)]
-    gathered = None
     if world > 1:
         dec_pack = torch.empty((6, B, M), dtype=torch.float32, device=device)
-        gathered = torch.empty((world, 6, B, M), dtype=torch.float32, device=device)
 
     def step():
         det.copy_(det0)  # fresh boxes every step (the forward back-projects det_boxes in place)
@@ -326,7 +324,7 @@ def main():
                     dec_pack[i].copy_(tns)
                 dec_pack[4].copy_(dec_f[0])
                 dec_pack[5].copy_(dec_f[1])
-                dist.all_gather_into_tensor(gathered, dec_pack)
+                sharding.gather_rank_blocks(dec_pack)  # (world, 6, B, M) on every rank
         e1.record()
         barrier()
         t_end = time.time()
