@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--hw", type=int, default=512, help="BEV map height = width")
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0, help="kernel variant flags (see shasta_b200.h)")
     ap.add_argument("--anchor-path", type=int, default=0, help="0 auto, 1 streaming CUDA-core, 2 tcgen05")
-    ap.add_argument("--raw-hi", type=int, default=0)
+    ap.add_argument("--raw-hi", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -285,10 +285,9 @@ def main():
     B, M = a.batch, a.max_obj
     n_prev = torch.from_numpy(d["n_prev"].astype(np.int32)).to(device)
     n_det = torch.from_numpy(d["n_det"].astype(np.int32)).to(device)
-    dec_i = [torch.empty((B, M), dtype=torch.int32, device=device) for _ in range(4)]
-    dec_f = [torch.empty((B, M), dtype=torch.float32, device=device) for _ in range(2)]
-    if world > 1:
-        dec_pack = torch.empty((6, B, M), dtype=torch.float32, device=device)
+    # multi-GPU: every step's compact decode output (4 int32 + 2 float32 planes of (B,M)) lands in one block that is
+    # all-gathered ONCE at the end of the timed region - the only collective of the path
+    dec_pack = torch.empty((a.steps, 6, B, M), dtype=torch.int32, device=device) if world > 1 else None
 
     def step():
         det.copy_(det0)  # fresh boxes every step (the forward back-projects det_boxes in place)
@@ -312,19 +311,17 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_begin = time.time()
         e0.record()
-        for _ in range(a.steps):
+        for it in range(a.steps):
             m1, m2 = step()
-            if world > 1:  # NCCL only gathers the per-rank results (compact decode output)
+            if world > 1:
+                o = [dec_pack[it, i].data_ptr() for i in range(6)]  # prev_state, prev_argmax, fn_score, det_state, ...
                 rc = lib.shasta_decode_f32(m1.data_ptr(), m2.data_ptr(), n_prev.data_ptr(), n_det.data_ptr(), B, M,
-                                           dec_i[0].data_ptr(), dec_i[1].data_ptr(), dec_f[0].data_ptr(),
-                                           dec_i[2].data_ptr(), dec_i[3].data_ptr(), dec_f[1].data_ptr(),
+                                           o[0], o[1], o[2], o[3], o[4], o[5],
                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
                 _cabi.check(rc, "decode")
-                for i, tns in enumerate(dec_i):
-                    dec_pack[i].copy_(tns)
-                dec_pack[4].copy_(dec_f[0])
-                dec_pack[5].copy_(dec_f[1])
-                sharding.gather_rank_blocks(dec_pack)  # (world, 6, B, M) on every rank
+        if world > 1:  # NCCL only gathers the per-rank results
+            gathered = sharding.gather_rank_blocks(dec_pack)  # (world, steps, 6, B, M) on every rank
+            assert gathered.shape[0] == world
         e1.record()
         barrier()
         t_end = time.time()
@@ -341,7 +338,7 @@ def main():
             ms = float(tms.item())
         value = world * B * a.steps / (ms / 1e3)
         if world > 1:
-            launches_per_step += 1
+            launches_per_step += 1  # decode_kernel
 
         # ---- per-kernel durations, live, same loop with event records between the kernels -------------------
         model.kernel_flags = a.flags | 0x100

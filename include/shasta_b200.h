@@ -105,9 +105,11 @@ enum shasta_region {
 
 /* Runtime options (process-wide, not thread-safe; meant for tests and benchmarks).
  *   SHASTA_OPT_ANCHOR_PATH: 0 = auto (streaming CUDA-core kernel up to 8 frame pairs, tcgen05 3xTF32 GEMM above),
- *                           1 = always the streaming kernel, 2 = always the tcgen05 kernel.
- *   SHASTA_OPT_TC_RAW_HI:   0 = the tcgen05 kernels write tf32-exact high parts back to shared memory (safe),
- *                           1 = feed the raw fp32 tile as the high part (relies on kind::tf32 truncating). */
+ *                           1 = always the streaming kernel, 2 = always the tcgen05 kernel (TMEM-resident weight
+ *                           low parts, bounded accumulation chains), 3 = the first-generation tcgen05 kernel.
+ *   SHASTA_OPT_TC_RAW_HI:   1 (default) = the tcgen05 anchors kernels feed the raw fp32 tile as the tf32 "high" part:
+ *                           kind::tf32 ignores the low 13 mantissa bits (measured on B200: identical accuracy),
+ *                           0 = write tf32-exact high parts back to shared memory first. */
 enum shasta_option { SHASTA_OPT_ANCHOR_PATH = 0, SHASTA_OPT_TC_RAW_HI = 1, SHASTA_OPT_COUNT = 4 };
 SHASTA_API int shasta_set_option(int option, int value);
 SHASTA_API int shasta_get_option(int option);

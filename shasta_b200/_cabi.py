@@ -56,7 +56,7 @@ WS_FEAT_CUR, WS_FEAT_PREV, WS_BOX_CUR, WS_BOX_PREV, WS_HIDDEN_PART, WS_PROJ_PREV
 
 OPT_ANCHOR_PATH = 0
 OPT_TC_RAW_HI = 1
-ANCHOR_AUTO, ANCHOR_STREAM, ANCHOR_TC = 0, 1, 2
+ANCHOR_AUTO, ANCHOR_STREAM, ANCHOR_TC, ANCHOR_TC_GEN1 = 0, 1, 2, 3
 
 # every symbol include/shasta_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _sz, _u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_uint32

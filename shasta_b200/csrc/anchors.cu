@@ -263,6 +263,9 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
 }
 
 // ------------------------------------------------------------------------------------------------
+int anchor_tc2_splits(int M, int B);  // anchors_tc2.cu
+int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, const float* feat_prev, int B, int S,
+                             float* part, cudaStream_t s);
 int anchor_tc_splits(int M, int B);  // anchors_tc.cu
 int launch_anchor_hidden_tc(const shasta_params_t& p, const float* feat_cur, const float* feat_prev, int B, int S,
                             float* part, cudaStream_t s);
@@ -276,11 +279,14 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   float* part = ws + L.off[SHASTA_WS_HIDDEN_PART];
 
   // small batches are pure weight streaming (HBM-bound on CUDA cores); from 9 frame pairs on the 3xTF32
-  // tensor-core GEMM wins.  option 0: 0 = auto, 1 = always streaming kernel, 2 = always tensor-core kernel
+  // tensor-core GEMM wins.  option 0: 0 = auto, 1 = streaming kernel, 2 = tcgen05 kernel, 3 = first-gen tcgen05
   const int mode = g_options[SHASTA_OPT_ANCHOR_PATH];
-  const bool use_tc = (mode == 2) || (mode == 0 && B > 8);
   int S;
-  if (use_tc) {
+  if (mode == 2 || (mode == 0 && B > 8)) {        // tcgen05, weights on the M side, TMEM-resident low parts
+    S = anchor_tc2_splits(M, B);
+    int rc = launch_anchor_hidden_tc2(p, feat_cur, feat_prev, B, S, part, s);
+    if (rc) return rc;
+  } else if (mode == 3) {                         // first-generation tcgen05 kernel (kept for comparison)
     S = anchor_tc_splits(M, B);
     int rc = launch_anchor_hidden_tc(p, feat_cur, feat_prev, B, S, part, s);
     if (rc) return rc;

@@ -1,0 +1,333 @@
+// aug_shape.i.0 on tcgen05, second generation ("weights on the M side").
+//
+//   HIDDEN_PART[s][b][i][n] = sum_{k in split s} W0_i[n][k] * X_src(i)[b][k]              (shasta.py:54, 241-244)
+//
+// What changed against anchors_tc.cu (kept as option 3 for comparison):
+//   * the weight tile is the UMMA A operand (M = 128 weight rows = 128 TMEM lanes), the batch is the N dimension
+//     (64 or 128 frame pairs). A stage then holds 16 KB of weights + 2 x BN x 128 B of activations, so 6 (BN = 64) or
+//     4 (BN = 128) stages fit in shared memory and ~96 KB of weight bytes are in flight per SM - the kernel is a weight
+//     streamer and needs that much to cover HBM latency;
+//   * the low part of the weight tile never goes back to shared memory: the splitter warps write it to TENSOR MEMORY
+//     (tcgen05.st) and the third MMA of each K step reads its A operand from TMEM (TS mode);
+//   * accumulation chains are bounded: every kFlush K blocks (512 elements) the accumulator is drained into fp32
+//     registers (round-to-nearest adds) while the MMAs continue into a second TMEM buffer. Long chains inside the
+//     tensor core lose ~2 decimal digits at K = 64 000 (measured 5e-5 vs 2e-7 for fp32 FMA);
+//   * the epilogue writes along the weight-row dimension, i.e. coalesced.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace shasta {
+
+using namespace tc;
+
+constexpr int kT2BM = 128;       // weight rows per tile (UMMA M, TMEM lanes)
+constexpr int kT2BK = 32;        // floats of K per stage = one 128-byte swizzle atom
+constexpr int kT2Threads = 256;
+constexpr int kT2Flush = 16;     // K blocks per accumulation chain
+constexpr int kT2WTile = kT2BM * kT2BK * 4;  // 16 KB
+
+template <int BN>
+struct T2Cfg {
+  static constexpr int kXTile = BN * kT2BK * 4;                    // 8 / 16 KB
+  static constexpr int kStageBytes = kT2WTile + 2 * kXTile;        // Whi | Xhi | Xlo
+  static constexpr int kStages = (BN == 64) ? 6 : 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kColD = 0;                                  // two accumulator buffers of BN columns
+  static constexpr int kColWl = 2 * BN;                            // kStages x 32 columns of weight low parts
+  static_assert(2 * BN + kStages * 32 <= 512, "TMEM budget");
+};
+
+struct AnchorT2Maps {
+  CUtensorMap w[4];  // aug_shape.i.0.weight (5M, 320M), box 32 x 128
+  CUtensorMap x[2];  // FEAT_CUR / FEAT_PREV as (B, 320M) with row stride (M+2)*320, box 32 x BN
+};
+
+__device__ __forceinline__ void t2_tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void t2_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void t2_mma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kT2Threads, 1)
+anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M, int S, int ntiles_n, int raw_hi,
+                         float* __restrict__ part) {
+  using C = T2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N5 = 5 * M;
+  const int kblocks = (kF * M) / kT2BK;
+  const int nt = blockIdx.x % ntiles_n, bt = blockIdx.x / ntiles_n;
+  const int i = blockIdx.y, s = blockIdx.z;
+  const int kb_beg = (int)((long long)kblocks * s / S), kb_end = (int)((long long)kblocks * (s + 1) / S);
+  const int nkb = kb_end - kb_beg;
+  const int n0 = nt * kT2BM, b0 = bt * BN;
+  const int nchunks = (nkb + kT2Flush - 1) / kT2Flush;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int st) { return bars + 8u * st; };
+  auto split_bar = [&](int st) { return bars + 8u * (C::kStages + st); };
+  auto empty_bar = [&](int st) { return bars + 8u * (2 * C::kStages + st); };
+  auto dfull_bar = [&](int buf) { return bars + 8u * (3 * C::kStages + buf); };
+  auto dempty_bar = [&](int buf) { return bars + 8u * (3 * C::kStages + 2 + buf); };
+  const uint32_t tmem_slot = bars + 8u * (3 * C::kStages + 4);
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.w[i]);
+    tma_prefetch_desc(&maps.x[i >> 1]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int st = 0; st < C::kStages; ++st) {
+      mbar_init(full_bar(st), 1);
+      mbar_init(split_bar(st), 128);
+      mbar_init(empty_bar(st), 1);
+    }
+    for (int buf = 0; buf < 2; ++buf) mbar_init(dfull_bar(buf), 1), mbar_init(dempty_bar(buf), 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(empty_bar(st), ph ^ 1);
+        const uint32_t sb = base + st * C::kStageBytes;
+        mbar_expect_tx(full_bar(st), kT2WTile + C::kXTile);
+        const int k0 = (kb_beg + kb) * kT2BK;
+        tma_load_2d(sb, &maps.w[i], full_bar(st), k0, n0, kEvictFirst);                  // weights: streamed once
+        tma_load_2d(sb + kT2WTile, &maps.x[i >> 1], full_bar(st), k0, b0, kEvictLast);   // activations: reused
+        if (++st == C::kStages) st = 0, ph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(kFmtTF32, kT2BM, BN);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int chunk = kb / kT2Flush, buf = chunk & 1;
+        const bool first = (kb % kT2Flush) == 0;
+        if (first && chunk >= 2) {  // the flush of chunk-2 must have drained this accumulator buffer
+          mbar_wait(dempty_bar(buf), ((chunk >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(split_bar(st), ph);
+        tc_fence_after();
+        const uint32_t sb = base + st * C::kStageBytes;
+        const uint64_t dwh = umma_desc_sw128(sb);
+        const uint64_t dxh = umma_desc_sw128(sb + kT2WTile), dxl = umma_desc_sw128(sb + kT2WTile + C::kXTile);
+        const uint32_t d = tmem + (uint32_t)(C::kColD + buf * BN);
+        const uint32_t wl = tmem + (uint32_t)(C::kColWl + st * 32);
+#pragma unroll
+        for (int k = 0; k < kT2BK / 8; ++k) {
+          const uint64_t adv = (uint64_t)((k * 32) >> 4);
+          mma_tf32(d, dwh + adv, dxh + adv, idesc, !(first && k == 0));
+          mma_tf32(d, dwh + adv, dxl + adv, idesc, 1);
+          t2_mma_ts_tf32(d, wl + (uint32_t)(k * 8), dxh + adv, idesc, 1);
+        }
+        mma_commit(empty_bar(st));
+        if ((kb % kT2Flush) == kT2Flush - 1 || kb == nkb - 1) mma_commit(dfull_bar(buf));
+        if (++st == C::kStages) st = 0, ph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== splitter + accumulator flush + epilogue =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // weight row inside the tile == TMEM lane
+    const int t = threadIdx.x - 128;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+
+    auto flush = [&](int chunk) {
+      const int buf = chunk & 1;
+      mbar_wait(dfull_bar(buf), (chunk >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(lane_base + (uint32_t)(C::kColD + buf * BN + c0), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      mbar_arrive(dempty_bar(buf));
+    };
+
+    int st = 0;
+    uint32_t ph = 0;
+    int next_flush = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      // chunk c is complete once the MMAs of K block (c+1)*kFlush-1 retired; the pipeline guarantees that by the
+      // time the splitter sees K block (c+1)*kFlush-1+kStages, so this wait does not stall
+      if (next_flush < nchunks - 1 && kb >= (next_flush + 1) * kT2Flush - 1 + C::kStages) flush(next_flush++);
+
+      mbar_wait(full_bar(st), ph);
+      uint8_t* sg = gen_base + st * C::kStageBytes;
+      // --- weight tile: row r, 8 chunks of 16 bytes, 128B-swizzled (chunk c lives at c ^ (r & 7))
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        uint32_t lo[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4* p = reinterpret_cast<float4*>(sg + r * 128 + (((c + h) ^ (r & 7)) << 4));
+          const float4 w = *p;
+          float4 wh;
+          wh.x = __uint_as_float(__float_as_uint(w.x) & 0xffffe000u);
+          wh.y = __uint_as_float(__float_as_uint(w.y) & 0xffffe000u);
+          wh.z = __uint_as_float(__float_as_uint(w.z) & 0xffffe000u);
+          wh.w = __uint_as_float(__float_as_uint(w.w) & 0xffffe000u);
+          lo[h * 4 + 0] = __float_as_uint(w.x - wh.x);
+          lo[h * 4 + 1] = __float_as_uint(w.y - wh.y);
+          lo[h * 4 + 2] = __float_as_uint(w.z - wh.z);
+          lo[h * 4 + 3] = __float_as_uint(w.w - wh.w);
+          if (!raw_hi) *p = wh;
+        }
+        t2_tmem_st8(lane_base + (uint32_t)(C::kColWl + st * 32 + c * 4), lo);
+      }
+      // --- activation tile: elementwise, layout-agnostic
+      float4* xh = reinterpret_cast<float4*>(sg + kT2WTile);
+      float4* xl = reinterpret_cast<float4*>(sg + kT2WTile + C::kXTile);
+#pragma unroll
+      for (int j = 0; j < C::kXTile / 16 / 128; ++j) {
+        const int idx = j * 128 + t;
+        const float4 a = xh[idx];
+        float4 ah, al;
+        ah.x = __uint_as_float(__float_as_uint(a.x) & 0xffffe000u), al.x = a.x - ah.x;
+        ah.y = __uint_as_float(__float_as_uint(a.y) & 0xffffe000u), al.y = a.y - ah.y;
+        ah.z = __uint_as_float(__float_as_uint(a.z) & 0xffffe000u), al.z = a.z - ah.z;
+        ah.w = __uint_as_float(__float_as_uint(a.w) & 0xffffe000u), al.w = a.w - ah.w;
+        xl[idx] = al;
+        if (!raw_hi) xh[idx] = ah;
+      }
+      t2_tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(split_bar(st));
+      if (++st == C::kStages) st = 0, ph ^= 1;
+    }
+    while (next_flush < nchunks) flush(next_flush++);
+
+    // ---- epilogue: registers -> split-K partial sums, coalesced along the weight-row dimension
+    const int n = n0 + r;
+    if (n < N5) {
+#pragma unroll
+      for (int j = 0; j < BN; ++j) {
+        const int b = b0 + j;
+        if (b < B) part[(((size_t)s * B + b) * 4 + i) * N5 + n] = acc[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map2(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  static EncodeTiledFn2 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn2>(p);
+  }
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return SHASTA_ERR_UNSUPPORTED;
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kT2BK, box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SHASTA_ERR_ARG;
+  }
+  return 0;
+}
+
+static int t2_bn(int B) { return B <= 64 ? 64 : 128; }
+
+int anchor_tc2_splits(int M, int B) {
+  const int bn = t2_bn(B);
+  const int tiles = 4 * ((5 * M + kT2BM - 1) / kT2BM) * ((B + bn - 1) / bn);
+  const int kblocks = 10 * M;
+  const int smax = hidden_splits(M) < kblocks ? hidden_splits(M) : kblocks;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int S = 1; S <= smax && S <= 64; ++S) {
+    const int waves = (tiles * S + 147) / 148;
+    const double cost = waves * ((double)(kblocks + S - 1) / S + 16.0);
+    if (cost < best_cost) best_cost = cost, best = S;
+  }
+  return best;
+}
+
+int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, const float* feat_prev, int B, int S,
+                             float* part, cudaStream_t s) {
+  const int M = p.max_obj;
+  const int bn = t2_bn(B);
+  const uint64_t K = (uint64_t)kF * M, N5 = 5ull * M, ld = (uint64_t)(M + 2) * kF;
+  AnchorT2Maps maps;
+  for (int i = 0; i < 4; ++i) {
+    int rc = make_map2(&maps.w[i], p.aug_shape_w0[i], N5, K, K, 128);
+    if (rc) return rc;
+  }
+  int rc = make_map2(&maps.x[0], feat_cur, (uint64_t)B, K, ld, (uint32_t)bn);
+  if (rc) return rc;
+  rc = make_map2(&maps.x[1], feat_prev, (uint64_t)B, K, ld, (uint32_t)bn);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    SHASTA_CUDA(cudaFuncSetAttribute(anchor_hidden_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     T2Cfg<64>::kSmemBytes));
+    SHASTA_CUDA(cudaFuncSetAttribute(anchor_hidden_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     T2Cfg<128>::kSmemBytes));
+    configured = true;
+  }
+  const int ntn = (int)((N5 + kT2BM - 1) / kT2BM), ntb = (B + bn - 1) / bn;
+  dim3 grid(ntn * ntb, 4, S);
+  const int raw_hi = g_options[SHASTA_OPT_TC_RAW_HI];
+  if (bn == 64)
+    anchor_hidden_tc2_kernel<64><<<grid, kT2Threads, T2Cfg<64>::kSmemBytes, s>>>(maps, B, M, S, ntn, raw_hi, part);
+  else
+    anchor_hidden_tc2_kernel<128><<<grid, kT2Threads, T2Cfg<128>::kSmemBytes, s>>>(maps, B, M, S, ntn, raw_hi, part);
+  SHASTA_CHECK_LAUNCH("anchor_hidden_tc2_kernel");
+  return 0;
+}
+
+}  // namespace shasta

@@ -92,10 +92,10 @@ def test_gather_from_boxes(name, variant):
 # ------------------------------------------------------------------------------------------------
 # a3+a4: anchors
 # ------------------------------------------------------------------------------------------------
-@pytest.fixture
-def force_tc_anchors():
+@pytest.fixture(params=[_cabi.ANCHOR_TC, _cabi.ANCHOR_TC_GEN1], ids=["tc2", "tc1"])
+def force_tc_anchors(request):
     lib = _cabi.lib()
-    lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, _cabi.ANCHOR_TC)
+    lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, request.param)
     yield
     lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, _cabi.ANCHOR_AUTO)
 
@@ -128,18 +128,19 @@ def test_anchor_paths_agree_at_m200(B, raw_hi):
     fp[:, :M] = torch.randn((B, M, 320), device=G.DEV, generator=gen).relu_()
     boxes = torch.randn((B, M, 11), device=G.DEV, generator=gen)
     out = {}
-    for mode in (_cabi.ANCHOR_STREAM, _cabi.ANCHOR_TC):
+    for mode in (_cabi.ANCHOR_STREAM, _cabi.ANCHOR_TC, _cabi.ANCHOR_TC_GEN1):
         lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, mode)
         lib.shasta_set_option(_cabi.OPT_TC_RAW_HI, raw_hi)
         try:
             st.anchors(boxes, boxes)
         finally:
             lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, _cabi.ANCHOR_AUTO)
-            lib.shasta_set_option(_cabi.OPT_TC_RAW_HI, 0)
+            lib.shasta_set_option(_cabi.OPT_TC_RAW_HI, 1)
         torch.cuda.synchronize()
         out[mode] = torch.cat([fc[:, M:], fp[:, M:]], dim=1).clone()
     a, b = out[_cabi.ANCHOR_STREAM].cpu().numpy(), out[_cabi.ANCHOR_TC].cpu().numpy()
-    assert np.isfinite(b).all()
+    b1 = out[_cabi.ANCHOR_TC_GEN1].cpu().numpy()
+    assert np.isfinite(b).all() and np.isfinite(b1).all()
     # float64 reference of all four anchors: rows [dead, fn] of FEAT_CUR then [newborn, fp] of FEAT_PREV
     xc = fc[:, :M].reshape(B, -1).double()
     xp = fp[:, :M].reshape(B, -1).double()
@@ -153,9 +154,10 @@ def test_anchor_paths_agree_at_m200(B, raw_hi):
     scale = np.abs(ref).max()
     err_stream = np.abs(a - ref).max() / scale
     err_tc = np.abs(b - ref).max() / scale
-    print("anchor L1+L2 max err / scale vs float64 (B=%d raw_hi=%d): streaming fp32 %.3g, tcgen05 3xTF32 %.3g"
-          % (B, raw_hi, err_stream, err_tc))
-    assert err_stream < 1e-4 and err_tc < 1e-4, (err_stream, err_tc)
+    err_tc1 = np.abs(b1 - ref).max() / scale
+    print("anchor L1+L2 max err / scale vs float64 (B=%d raw_hi=%d): streaming fp32 %.3g, tcgen05 (bounded chains) "
+          "%.3g, tcgen05 gen1 %.3g" % (B, raw_hi, err_stream, err_tc, err_tc1))
+    assert err_stream < 1e-5 and err_tc < 1e-5 and err_tc1 < 1e-4, (err_stream, err_tc, err_tc1)
 
 
 def _anchors_stage(name):
