@@ -67,53 +67,74 @@ def config_dict(a, extra=None):
 # clocks sampling during the timed region (B200_PROFILING.md recipe)
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason samples DURING the timed region (B200_PROFILING.md recipe), taken in-process through
+    NVML every 20 ms. (An `nvidia-smi -lms` child was measurably perturbing short timed regions: its queries stall
+    kernel launches for milliseconds.) Falls back to one nvidia-smi query if NVML is unavailable."""
+    HW_SLOWDOWN, SW_THERMAL, HW_THERMAL, SW_POWER_CAP = 0x8, 0x20, 0x40, 0x4
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.rows = []
-        self.proc = None
+        self.handle = None
+        self.nv = None
+        self._stop = threading.Event()
+        self.thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
+            import pynvml as nv
+            nv.nvmlInit()
+            try:
+                uuid = torch.cuda.get_device_properties(self.gpu).uuid
+                self.handle = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:  # noqa: BLE001
+                self.handle = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nv = nv
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
         except Exception:  # noqa: BLE001
-            self.proc = None
+            self.nv = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:  # noqa: BLE001
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.time(), mhz, reasons))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.02)
 
     def stop(self, t_begin=None, t_end=None):
-        """Summary of the samples that arrived inside [t_begin, t_end] (widened by one sampling period)."""
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        rows = [r for (ts, r) in self.rows
-                if (t_begin is None or ts >= t_begin - 0.12) and (t_end is None or ts <= t_end + 0.12)]
-        if not rows:
-            rows = [r for (_, r) in self.rows[-2:]]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
+        """Summary of the samples taken inside [t_begin, t_end]."""
+        if self.nv is None:
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10)
+                f = [float(x) for x in out.stdout.strip().split(",")]
+                return {"sm_mhz": f[0], "sm_max_mhz": f[1], "reasons": ["nvml unavailable: one nvidia-smi sample after the run"],
+                        "samples": 1}
+            except Exception:  # noqa: BLE001
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source available"], "samples": 0}
+        self._stop.set()
+        self.thread.join(1.0)
+        rows = [r for r in self.rows if (t_begin is None or r[0] >= t_begin) and (t_end is None or r[0] <= t_end)]
+        if not rows:
+            rows = self.rows[-2:]
+        reasons = set()
+        for _, _, bits in rows:
+            for name, bit in (("hw_slowdown", self.HW_SLOWDOWN), ("hw_thermal_slowdown", self.HW_THERMAL),
+                              ("sw_thermal_slowdown", self.SW_THERMAL), ("sw_power_cap", self.SW_POWER_CAP)):
+                if bits & bit:
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                "samples": len(sm), "source": "nvml"}
 
 
 # --------------------------------------------------------------------------------------------------

@@ -6,56 +6,97 @@
 // Reference: shasta.py:94-109,323-325.
 //
 // aff_row_kernel: a CTA owns 32 rows; activations stay in shared memory between the six layers (k-major,
-// [width][32]); transposed weights stream from L2 with coalesced loads; the row softmax is done by the same CTA
-// with warp-shuffle reductions. col_softmax_kernel does the column direction over the L2-resident logits.
+// [width][32]); transposed weights stream from L2 through a double-buffered shared-memory chunk into 4 x RPT register
+// tiles; the row softmax is done by the same CTA with warp-shuffle reductions. col_softmax_kernel does the column direction over the L2-resident logits.
 #include "common.cuh"
 
 namespace shasta {
 
 constexpr int kAffRows = 32;
 constexpr int kAffThreads = 256;
+constexpr int kAffKC = 32;     // K rows of the weight chunk staged in shared memory
+constexpr int kAffNT = 128;    // output columns per pass
 
-// out[j][r] = act(bias[j] + sum_k in[k][r] * WT[k][j]),  N compile-time (<= 128)
-template <int N, bool RELU>
-__device__ __forceinline__ void dense_fixed(const float* __restrict__ in, const float* __restrict__ WT,
-                                            const float* __restrict__ bias, float* __restrict__ out, int K) {
-  constexpr int G = kAffThreads / N;      // thread groups over rows
-  constexpr int RPT = kAffRows / G;       // rows per thread: 16, 8 or 4
-  const int j = threadIdx.x % N, g = threadIdx.x / N;
-  const int r0 = g * RPT;
-  float acc[RPT];
-  const float bj = __ldg(bias + j);
+// One dense layer on a 32-row activation tile held in shared memory ([width][32], k-major):
+//   out[j][r] = act(bias[j] + sum_k in[k][r] * WT[k][j]),   WT = transposed weights [K][ldw] in global memory.
+// Outputs are produced in passes of NT columns; the weights of a pass stream through a double-buffered shared
+// memory chunk (coalesced 16-byte loads issued one chunk ahead), every thread keeps a CPT x RPT register tile.
+template <int NT, bool RELU>
+__device__ __forceinline__ void dense_tile(const float* __restrict__ in, const float* __restrict__ WT, int ldw,
+                                           const float* __restrict__ bias, float* __restrict__ out, int K, int N,
+                                           float* __restrict__ wbuf) {
+  constexpr int TXN = NT / 4;                 // threads across the columns of a pass (4 columns each)
+  constexpr int TY = kAffThreads / TXN;       // thread groups across rows
+  constexpr int RPT = kAffRows / TY;          // rows per thread: 4 (NT=128), 2 (64), 1 (32)
+  constexpr int VPT = kAffKC * NT / 4 / kAffThreads;  // float4 per thread per weight chunk: 4, 2, 1
+  const int tx = threadIdx.x % TXN, ty = threadIdx.x / TXN;
+  const int r0 = ty * RPT;
+  for (int n0 = 0; n0 < N; n0 += NT) {
+    float acc[4][RPT];
 #pragma unroll
-  for (int r = 0; r < RPT; ++r) acc[r] = bj;
-  int k = 0;
-  for (; k + 4 <= K; k += 4) {  // four independent weight loads in flight per thread
-    float w[4];
+    for (int c = 0; c < 4; ++c) {
+      const int j = n0 + tx * 4 + c;
+      const float bj = (j < N) ? __ldg(bias + j) : 0.f;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) w[u] = __ldg(WT + (size_t)(k + u) * N + j);
+      for (int r = 0; r < RPT; ++r) acc[c][r] = bj;
+    }
+    float4 pre[VPT];
+    auto prefetch = [&](int k0) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float4* ip = reinterpret_cast<const float4*>(in + (k + u) * kAffRows + r0);
+      for (int v = 0; v < VPT; ++v) {
+        const int idx = v * kAffThreads + threadIdx.x;   // float4 index inside the [kAffKC][NT] chunk
+        const int kk = idx / (NT / 4), c4 = idx % (NT / 4);
+        const int k = k0 + kk, j = n0 + c4 * 4;
+        pre[v] = (k < K && j < ldw) ? __ldg(reinterpret_cast<const float4*>(WT + (size_t)k * ldw + j))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    prefetch(0);
+    int cur = 0;
+    for (int k0 = 0; k0 < K; k0 += kAffKC) {
+      float* wb = wbuf + cur * (kAffKC * NT);
 #pragma unroll
-      for (int q = 0; q < RPT / 4; ++q) {
-        const float4 v = ip[q];
-        acc[q * 4 + 0] = fmaf(v.x, w[u], acc[q * 4 + 0]);
-        acc[q * 4 + 1] = fmaf(v.y, w[u], acc[q * 4 + 1]);
-        acc[q * 4 + 2] = fmaf(v.z, w[u], acc[q * 4 + 2]);
-        acc[q * 4 + 3] = fmaf(v.w, w[u], acc[q * 4 + 3]);
+      for (int v = 0; v < VPT; ++v) reinterpret_cast<float4*>(wb)[v * kAffThreads + threadIdx.x] = pre[v];
+      __syncthreads();
+      if (k0 + kAffKC < K) prefetch(k0 + kAffKC);
+      const int kn = min(kAffKC, K - k0);
+#pragma unroll 4
+      for (int kk = 0; kk < kn; ++kk) {
+        const float4 w = *reinterpret_cast<const float4*>(wb + kk * NT + tx * 4);
+        const float* ip = in + (k0 + kk) * kAffRows + r0;
+        float a[RPT];
+        if (RPT == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(ip);
+          a[0] = v.x, a[1 % RPT] = v.y, a[2 % RPT] = v.z, a[3 % RPT] = v.w;
+        } else if (RPT == 2) {
+          const float2 v = *reinterpret_cast<const float2*>(ip);
+          a[0] = v.x, a[1 % RPT] = v.y;
+        } else {
+          a[0] = ip[0];
+        }
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          acc[0][r] = fmaf(a[r], w.x, acc[0][r]);
+          acc[1][r] = fmaf(a[r], w.y, acc[1][r]);
+          acc[2][r] = fmaf(a[r], w.z, acc[2][r]);
+          acc[3][r] = fmaf(a[r], w.w, acc[3][r]);
+        }
+      }
+      cur ^= 1;  // the next chunk goes to the other buffer; the barrier above orders its readers
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = n0 + tx * 4 + c;
+      if (j < N) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) out[j * kAffRows + r0 + r] = RELU ? fmaxf(acc[c][r], 0.f) : acc[c][r];
       }
     }
+    __syncthreads();  // wbuf is reused by the next pass / layer, out is read by the next layer
   }
-  for (; k < K; ++k) {
-    const float w = __ldg(WT + (size_t)k * N + j);
-    const float* ip = in + k * kAffRows + r0;
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) acc[r] = fmaf(ip[r], w, acc[r]);
-  }
-#pragma unroll
-  for (int r = 0; r < RPT; ++r) out[j * kAffRows + r0 + r] = RELU ? fmaxf(acc[r], 0.f) : acc[r];
 }
 
-__global__ void __launch_bounds__(kAffThreads)
+__global__ void __launch_bounds__(kAffThreads, 2)
 aff_row_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, const float* __restrict__ residual,
                float* __restrict__ logits, float* __restrict__ matched1) {
   extern __shared__ __align__(16) float sm[];
@@ -63,6 +104,7 @@ aff_row_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, con
   float* bufA = sm;                          // [D][32]  input rows, later the logits
   float* bufB = sm + (size_t)D * kAffRows;   // [128][32]
   float* bufC = bufB + 128 * kAffRows;       // [128][32]
+  float* wbuf = bufC + 128 * kAffRows;       // [2][32][128] weight chunks
   const long long row0 = (long long)blockIdx.x * kAffRows;
   const long long nrows = (long long)B * T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,60 +117,26 @@ aff_row_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, con
   }
   __syncthreads();
 
-  dense_fixed<128, true>(bufA, packed + P.aff_w[0], packed + P.aff_b[0], bufB, D);
-  __syncthreads();
-  dense_fixed<64, true>(bufB, packed + P.aff_w[1], packed + P.aff_b[1], bufC, 128);
-  __syncthreads();
-  dense_fixed<32, true>(bufC, packed + P.aff_w[2], packed + P.aff_b[2], bufB, 64);
-  __syncthreads();
-  dense_fixed<64, true>(bufB, packed + P.aff_w[3], packed + P.aff_b[3], bufC, 32);
-  __syncthreads();
-  dense_fixed<128, true>(bufC, packed + P.aff_w[4], packed + P.aff_b[4], bufB, 64);
-  __syncthreads();
+  dense_tile<128, true>(bufA, packed + P.aff_w[0], 128, packed + P.aff_b[0], bufB, D, 128, wbuf);
+  dense_tile<64, true>(bufB, packed + P.aff_w[1], 64, packed + P.aff_b[1], bufC, 128, 64, wbuf);
+  dense_tile<32, true>(bufC, packed + P.aff_w[2], 32, packed + P.aff_b[2], bufB, 64, 32, wbuf);
+  dense_tile<64, true>(bufB, packed + P.aff_w[3], 64, packed + P.aff_b[3], bufC, 32, 64, wbuf);
+  dense_tile<128, true>(bufC, packed + P.aff_w[4], 128, packed + P.aff_b[4], bufB, 64, 128, wbuf);
+  dense_tile<128, false>(bufB, packed + P.aff_w[5], RS, packed + P.aff_b[5], bufA, 128, D, wbuf);  // logits
 
-  // last layer 128 -> D, all 32 rows per thread, logits to shared (bufA) and to global
-  {
-    const float* WT = packed + P.aff_w[5];
-    const float* bias = packed + P.aff_b[5];
-    for (int j = threadIdx.x; j < D; j += kAffThreads) {
-      float acc[kAffRows];
-      const float bj = __ldg(bias + j);
-#pragma unroll
-      for (int r = 0; r < kAffRows; ++r) acc[r] = bj;
-      for (int k = 0; k < 128; k += 4) {
-        float w[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = __ldg(WT + (size_t)(k + u) * D + j);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4* ip = reinterpret_cast<const float4*>(bufB + (k + u) * kAffRows);
-#pragma unroll
-          for (int q = 0; q < kAffRows / 4; ++q) {
-            const float4 v = ip[q];
-            acc[q * 4 + 0] = fmaf(v.x, w[u], acc[q * 4 + 0]);
-            acc[q * 4 + 1] = fmaf(v.y, w[u], acc[q * 4 + 1]);
-            acc[q * 4 + 2] = fmaf(v.z, w[u], acc[q * 4 + 2]);
-            acc[q * 4 + 3] = fmaf(v.w, w[u], acc[q * 4 + 3]);
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < kAffRows; ++r) {
-        bufA[j * kAffRows + r] = acc[r];
-        if (row0 + r < nrows) logits[(size_t)(row0 + r) * RS + j] = acc[r];
-      }
-    }
-  }
-  __syncthreads();
-
-  // row softmax over D for rows t < M  -> matched1 (B,M,M+2)
+  // logits to global (coalesced along d) and row softmax over D for rows t < M  -> matched1 (B,M,M+2)
   for (int r = warp; r < kAffRows; r += kAffThreads / 32) {
     const long long row = row0 + r;
     if (row >= nrows) continue;
     const int b = (int)(row / T), t = (int)(row % T);
-    if (t >= M) continue;
+    float* lrow = logits + (size_t)row * RS;
     float mx = -INFINITY;
-    for (int d = lane; d < D; d += 32) mx = fmaxf(mx, bufA[d * kAffRows + r]);
+    for (int d = lane; d < D; d += 32) {
+      const float v = bufA[d * kAffRows + r];
+      lrow[d] = v;
+      mx = fmaxf(mx, v);
+    }
+    if (t >= M) continue;
     mx = warp_max(mx);
     float sum = 0.f;
     for (int d = lane; d < D; d += 32) sum += expf(bufA[d * kAffRows + r] - mx);
@@ -174,7 +182,7 @@ int launch_aff_softmax(const float* packed, int B, int M, float* ws, const WsLay
                        float* matched2, cudaStream_t s, cudaEvent_t mid) {
   const PackLayout P = pack_layout(M);
   const int T = M + 2;
-  const size_t smem = sizeof(float) * ((size_t)T + 256) * kAffRows;
+  const size_t smem = sizeof(float) * (((size_t)T + 256) * kAffRows + 2 * kAffKC * kAffNT);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     SHASTA_CUDA(cudaFuncSetAttribute(aff_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -74,7 +74,7 @@ struct PackLayout {
   size_t l3b, l3b_b;  // [20][4], [4]     res_coeff.4 (18 inputs padded to 20, 3 outputs padded to 4)
   size_t l3c, l3c_b;  // [8], [4]         fuse_det.4
   size_t pair_end;    // end of the block the pairwise kernel stages in shared memory (from l2a)
-  size_t aff_w[6];    // aff.{0..10}.weight^T : [in][out]
+  size_t aff_w[6];    // aff.{0..10}.weight^T : [in][out rounded up to a multiple of 4]
   size_t aff_b[6];
   // UMMA B-operand images of the second pairwise layers (tensor-core variants), K-major canonical un-swizzled
   // layout [k/4][n][4] (tf32) or [k/8][n][8] (bf16), N padded to a multiple of 16 with zero rows.
@@ -119,8 +119,9 @@ __host__ inline PackLayout pack_layout(int M) {
   const size_t win[6] = {D, 128, 64, 32, 64, 128};
   const size_t wout[6] = {128, 64, 32, 64, 128, D};
   for (int i = 0; i < 6; ++i) {
-    P.aff_w[i] = take(win[i] * wout[i]);
-    P.aff_b[i] = take(wout[i]);
+    // row stride of the transposed weights = outputs rounded up to 4 floats (16-byte aligned rows, zero padded)
+    P.aff_w[i] = take(win[i] * ((wout[i] + 3) / 4 * 4));
+    P.aff_b[i] = take((wout[i] + 3) / 4 * 4);
   }
   P.tc32_begin = o;
   P.tc32_w2a_hi = take(10 * 32 * 4);

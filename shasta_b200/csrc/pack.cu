@@ -89,7 +89,7 @@ int launch_pack(const shasta_params_t& p, float* packed, cudaStream_t s) {
   const int win[6] = {D, 128, 64, 32, 64, 128};
   const int wout[6] = {128, 64, 32, 64, 128, D};
   for (int i = 0; i < 6; ++i) {
-    TB(packed + P.aff_w[i], wout[i], p.aff_w[i], win[i], wout[i], win[i], s);
+    TB(packed + P.aff_w[i], (wout[i] + 3) / 4 * 4, p.aff_w[i], win[i], wout[i], win[i], s);
     TB(packed + P.aff_b[i], wout[i], p.aff_b[i], 1, wout[i], 1, s);
   }
   // tensor-core operand images of fuse_shape.2 (20x40), res_coeff.2 (18x72), fuse_det.2 (8x32)

@@ -23,7 +23,7 @@ using namespace tc;
 constexpr int kPtTT = 8;            // t rows per CTA
 constexpr int kPtDT = 64;           // d columns per CTA = 4 MMA tiles of 8 x 16 pairs
 constexpr int kPtQStride = 148;     // floats per d row of the staged PROJ_CUR tile (148 % 32 = 20: conflict-free LDS.128)
-constexpr int kPtThreads = 160;     // 4 worker warps + 1 MMA warp
+constexpr int kPtThreads = 288;     // 8 worker warps (two threads per pair) + 1 MMA warp
 constexpr int kPtTmemCols = 256;
 
 // TMEM column map (per CTA): A operands share [0,144), accumulators live in [144,224)
@@ -110,7 +110,8 @@ struct PtSmem {  // float offsets inside dynamic shared memory (after the 1 KB a
   static constexpr int auxp = qs + kPtDT * kPtQStride;          // [8][8]
   static constexpr int auxc = auxp + kPtTT * 8;                 // [64][8]
   static constexpr int cn = auxc + kPtDT * 8;                   // [64]
-  static constexpr int w = cn + kPtDT;                          // small-layer block (l2a .. pair_end of PackLayout)
+  static constexpr int shp = cn + kPtDT;                        // [2][128] fuse_shape results (group B -> group A)
+  static constexpr int w = shp + 256;                           // small-layer block (l2a .. pair_end of PackLayout)
 };
 
 template <bool BF16>
@@ -130,26 +131,30 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
   uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
   const int bimg_floats = BF16 ? (int)(P.tc16_end - P.tc16_begin) : (int)(P.tc32_end - P.tc32_begin);
   float* bimg = reinterpret_cast<float*>(gbase);
-  const uint32_t bars = sbase + bimg_floats * 4;                     // 6 mbarriers + tmem slot
-  float* fl = reinterpret_cast<float*>(gbase + bimg_floats * 4 + 64);
+  const uint32_t bars = sbase + bimg_floats * 4;                     // 7 mbarriers + tmem slot
+  float* fl = reinterpret_cast<float*>(gbase + bimg_floats * 4 + 128);
   float* Ps = fl + PtSmem::ps;
   float* Qs = fl + PtSmem::qs;
   float* Ap = fl + PtSmem::auxp;
   float* Ac = fl + PtSmem::auxc;
   float* Cn = fl + PtSmem::cn;
+  float* Sh = fl + PtSmem::shp;   // [2][128] fuse_shape outputs handed from group B to group A
   float* Ws = fl + PtSmem::w;
   const int wbase = (int)P.l2a, wcount = (int)(P.pair_end - P.l2a);
   auto bar_a = [&](int x) { return bars + 8u * x; };        // x: 0 det, 1 shape, 2 coeff  (A operand ready)
   auto bar_d = [&](int x) { return bars + 8u * (3 + x); };  // accumulator ready
-  const uint32_t tmem_slot = bars + 48;
+  const uint32_t bar_s = bars + 48;                         // fuse_shape scalar ready
+  const uint32_t tmem_slot = bars + 56;
 
   if (tid == 0) {
-    for (int x = 0; x < 3; ++x) mbar_init(bar_a(x), 128), mbar_init(bar_d(x), 1);
+    mbar_init(bar_a(0), 128), mbar_init(bar_a(1), 128), mbar_init(bar_a(2), 256);
+    for (int x = 0; x < 3; ++x) mbar_init(bar_d(x), 1);
+    mbar_init(bar_s, 128);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, kPtTmemCols);
+  if (warp == 8) tmem_alloc(tmem_slot, kPtTmemCols);
 
-  // ---- stage operands (all 160 threads) ----
+  // ---- stage operands (all threads) ----
   {
     const float4* src = reinterpret_cast<const float4*>(packed + (BF16 ? P.tc16_begin : P.tc32_begin));
     for (int v = tid; v < bimg_floats / 4; v += kPtThreads) reinterpret_cast<float4*>(bimg)[v] = __ldg(src + v);
@@ -168,11 +173,10 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
     const float4* apsrc = reinterpret_cast<const float4*>(aux_prev + ((size_t)b * T + t0) * 8);
     if (tid < kPtTT * 2)
       reinterpret_cast<float4*>(Ap)[tid] = (tid < nt * 2) ? __ldg(apsrc + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const int nd = max(0, min(kPtDT, D - d0));
     const float4* acsrc = reinterpret_cast<const float4*>(aux_cur + ((size_t)b * T + d0) * 8);
     for (int v = tid; v < kPtDT * 2; v += kPtThreads)
-      reinterpret_cast<float4*>(Ac)[v] = (v < nd * 2) ? __ldg(acsrc + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid < kPtDT) Cn[tid] = (tid < nd) ? colnorm[(size_t)b * T + d0 + tid] : 1.f;
+      reinterpret_cast<float4*>(Ac)[v] = (v < ndq * 2) ? __ldg(acsrc + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < kPtDT) Cn[tid] = (tid < ndq) ? colnorm[(size_t)b * T + d0 + tid] : 1.f;
     for (int v = tid; v < wcount / 4; v += kPtThreads)
       reinterpret_cast<float4*>(Ws)[v] = __ldg(reinterpret_cast<const float4*>(packed + wbase) + v);
   }
@@ -184,7 +188,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
 
   const int ntiles = kPtDT / 16;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // B images: [k chunk][n][16 bytes]; chunk stride (LBO) = N*16 bytes, 8-row group stride (SBO) = 128 bytes
@@ -234,10 +238,13 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
       }
     }
   } else {
-    // ===================== workers: one thread = one (t,d) pair = one TMEM lane =====================
-    const int r = tid;                 // 0..127
+    // ===================== workers: TWO threads per (t,d) pair, both on the pair's TMEM lane ==================
+    // group A (warps 0-3): fuse_det operand, first 40 K of res_coeff; epilogues of fuse_det and res_coeff, final sum
+    // group B (warps 4-7): fuse_shape operand, last 32 K of res_coeff; epilogue of fuse_shape (the heaviest)
+    const bool grp_b = warp >= 4;
+    const int r = tid & 127;           // pair row inside the tile == TMEM lane
     const int ti = r >> 4, di = r & 15;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's TMEM lane quarter
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float* prow = Ps + ti * kProj;
     const float* B2a = Ws + (P.l2a_b - wbase);
     const float* B2b = Ws + (P.l2b_b - wbase);
@@ -259,44 +266,98 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
       const int dl = tile * 16 + di;
       const float* qrow = Qs + dl * kPtQStride;
 
-      // (1) A operands of fuse_det.2 and fuse_shape.2 (disjoint TMEM columns)
-      build_a<BF16, 32>(prow, qrow, 112, lane_base, BF16 ? kColDetHi : kColDetHi, kColDetLo);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(bar_a(0));
-      // bf16 packs two k per column: 40 bf16 = 20 columns; K is padded to 48 (3 steps of 16) with zero columns
-      if (BF16) {
-        build_a<true, 40>(prow, qrow, 0, lane_base, kColShpHi, kColShpLo);
-        const uint32_t z[4] = {0u, 0u, 0u, 0u};
-        tmem_st4(lane_base + (uint32_t)(kColShpHi + 20), z);
-      } else {
-        build_a<false, 40>(prow, qrow, 0, lane_base, kColShpHi, kColShpLo);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(bar_a(1));
+      if (!grp_b) {
+        // ---------------- group A ----------------
+        build_a<BF16, 32>(prow, qrow, 112, lane_base, kColDetHi, kColDetLo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_a(0));
 
-      // (2) fuse_det epilogue: 8 -> 1
-      float fused, shape;
-      {
+        // both first MMAs must have retired before their TMEM columns are recycled for res_coeff
         mbar_wait(bar_d(0), ph);
+        mbar_wait(bar_d(1), ph);
         tc_fence_after();
-        uint32_t v[8];
-        tmem_ld8(lane_base + kColDDet, v);
+        uint32_t vd[8];
+        tmem_ld8(lane_base + kColDDet, vd);
         tmem_ld_wait();
-        float s = B3c[0];
+        tc_fence_before();
+        build_a<BF16, 40>(prow, qrow, 40, lane_base, kColCofHi, kColCofLo);          // res_coeff K 0..39
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_a(2));
+
+        // fuse_det epilogue 8 -> 1 and the hand-designed residuals, while the res_coeff MMAs run
+        float fused = B3c[0];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s = fmaf(relu_f(__uint_as_float(v[k]) + B2c[k]), W3c[k], s);
-        fused = s;
-      }
-      // (3) fuse_shape epilogue: 20 -> 10 -> 1
-      {
+        for (int k = 0; k < 8; ++k) fused = fmaf(relu_f(__uint_as_float(vd[k]) + B2c[k]), W3c[k], fused);
+        const float4 ac0 = *reinterpret_cast<const float4*>(Ac + dl * 8);
+        const float4 ac1 = *reinterpret_cast<const float4*>(Ac + dl * 8 + 4);
+        const float dx = ap0.x - ac0.x, dy = ap0.y - ac0.y, dz = ap0.z - ac0.z;
+        float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        dist = __fdiv_rn(dist, fmaxf(Cn[dl], 1e-12f));
+        const float dim = __fadd_rn(__fadd_rn(fabsf(ap0.w - ac0.w), fabsf(ap1.x - ac1.x)), fabsf(ap1.y - ac1.y));
+        const float dc = ap1.z - ac1.z, ds = ap1.w - ac1.w;
+        const float rot = sqrtf(__fadd_rn(__fmul_rn(dc, dc), __fmul_rn(ds, ds)));
+        const float res_dist = __fadd_rn(__fadd_rn(dist, dim), rot);
+
+        // res_coeff epilogue 18 -> 3
+        mbar_wait(bar_d(2), ph);
+        tc_fence_after();
+        uint32_t v[16], v2[8];
+        tmem_ld16(lane_base + kColDCof, v);
+        tmem_ld8(lane_base + kColDCof + 16, v2);
+        tmem_ld_wait();
+        tc_fence_before();
+        const float4 b3 = *reinterpret_cast<const float4*>(B3b);
+        float alpha = b3.x, beta = b3.y, omega = b3.z;
+#pragma unroll
+        for (int k = 0; k < 18; ++k) {
+          const float h = relu_f(__uint_as_float(k < 16 ? v[k] : v2[k - 16]) + B2b[k]);
+          const float4 w = *reinterpret_cast<const float4*>(W3b + k * 4);
+          alpha = fmaf(h, w.x, alpha);
+          beta = fmaf(h, w.y, beta);
+          omega = fmaf(h, w.z, omega);
+        }
+        mbar_wait(bar_s, ph);
+        const float shape = Sh[(tile & 1) * 128 + r];
+        const float out = __fadd_rn(__fadd_rn(__fmul_rn(alpha, fused), __fmul_rn(beta, res_dist)),
+                                    __fmul_rn(omega, shape));
+        const int d = d0 + dl;
+        if (t < T && d < D) residual[((size_t)b * T + t) * RS + d] = out;
+      } else {
+        // ---------------- group B ----------------
+        if (BF16) {
+          build_a<true, 40>(prow, qrow, 0, lane_base, kColShpHi, kColShpLo);
+          const uint32_t z[4] = {0u, 0u, 0u, 0u};
+          tmem_st4(lane_base + (uint32_t)(kColShpHi + 20), z);   // K padded 40 -> 48
+        } else {
+          build_a<false, 40>(prow, qrow, 0, lane_base, kColShpHi, kColShpLo);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_a(1));
+
+        mbar_wait(bar_d(0), ph);
         mbar_wait(bar_d(1), ph);
         tc_fence_after();
         uint32_t v[16], v2[8];
         tmem_ld16(lane_base + kColDShp, v);
         tmem_ld8(lane_base + kColDShp + 16, v2);
         tmem_ld_wait();
+        tc_fence_before();
+        if (BF16) {
+          // bf16 columns: res_coeff K 40..71 = packed columns 20..35, then zero padding 36..39 (K 72 -> 80)
+          build_a<true, 32>(prow, qrow, 80, lane_base, kColCofHi + 20, kColCofLo);
+          const uint32_t z[4] = {0u, 0u, 0u, 0u};
+          tmem_st4(lane_base + (uint32_t)(kColCofHi + 36), z);
+        } else {
+          build_a<false, 32>(prow, qrow, 80, lane_base, kColCofHi + 40, kColCofLo + 40);  // res_coeff K 40..71
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_a(2));
+
+        // fuse_shape epilogue: 20 -> 10 -> 1, while the res_coeff MMAs run
         float a3[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) a3[j] = B3a[j];
@@ -312,64 +373,20 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
             a3[j4 * 4 + 3] = fmaf(h, w.w, a3[j4 * 4 + 3]);
           }
         }
-        float s = B4a[0];
+        float sres = B4a[0];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) s = fmaf(relu_f(a3[k]), W4a[k], s);
-        shape = s;
-      }
-      // (4) A operand of res_coeff.2 — overwrites the det/shape columns, whose MMAs have retired (bar_d 0,1 passed)
-      tc_fence_before();
-      if (BF16) {
-        build_a<true, 72>(prow, qrow, 40, lane_base, kColCofHi, kColCofLo);
-        const uint32_t z[4] = {0u, 0u, 0u, 0u};
-        tmem_st4(lane_base + (uint32_t)(kColCofHi + 36), z);   // K padded 72 -> 80
-      } else {
-        build_a<false, 72>(prow, qrow, 40, lane_base, kColCofHi, kColCofLo);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(bar_a(2));
-
-      // (5) hand-designed residuals while the res_coeff MMAs run          shasta.py:277-283
-      const float4 ac0 = *reinterpret_cast<const float4*>(Ac + dl * 8);
-      const float4 ac1 = *reinterpret_cast<const float4*>(Ac + dl * 8 + 4);
-      const float dx = ap0.x - ac0.x, dy = ap0.y - ac0.y, dz = ap0.z - ac0.z;
-      float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      dist = __fdiv_rn(dist, fmaxf(Cn[dl], 1e-12f));
-      const float dim = __fadd_rn(__fadd_rn(fabsf(ap0.w - ac0.w), fabsf(ap1.x - ac1.x)), fabsf(ap1.y - ac1.y));
-      const float dc = ap1.z - ac1.z, ds = ap1.w - ac1.w;
-      const float rot = sqrtf(__fadd_rn(__fmul_rn(dc, dc), __fmul_rn(ds, ds)));
-      const float res_dist = __fadd_rn(__fadd_rn(dist, dim), rot);
-
-      // (6) res_coeff epilogue: 18 -> 3, weighted sum, store
-      {
+        for (int k = 0; k < 10; ++k) sres = fmaf(relu_f(a3[k]), W4a[k], sres);
+        Sh[(tile & 1) * 128 + r] = sres;
+        mbar_arrive(bar_s);   // mbarrier arrive has release semantics: the shared-memory write above is visible
+        // the res_coeff MMAs read this group's TMEM columns: they must retire before the next tile rewrites them
         mbar_wait(bar_d(2), ph);
         tc_fence_after();
-        uint32_t v[16], v2[8];
-        tmem_ld16(lane_base + kColDCof, v);
-        tmem_ld8(lane_base + kColDCof + 16, v2);
-        tmem_ld_wait();
-        const float4 b3 = *reinterpret_cast<const float4*>(B3b);
-        float alpha = b3.x, beta = b3.y, omega = b3.z;
-#pragma unroll
-        for (int k = 0; k < 18; ++k) {
-          const float h = relu_f(__uint_as_float(k < 16 ? v[k] : v2[k - 16]) + B2b[k]);
-          const float4 w = *reinterpret_cast<const float4*>(W3b + k * 4);
-          alpha = fmaf(h, w.x, alpha);
-          beta = fmaf(h, w.y, beta);
-          omega = fmaf(h, w.z, omega);
-        }
-        const float out = __fadd_rn(__fadd_rn(__fmul_rn(alpha, fused), __fmul_rn(beta, res_dist)),
-                                    __fmul_rn(omega, shape));
-        const int d = d0 + dl;
-        if (t < T && d < D) residual[((size_t)b * T + t) * RS + d] = out;
       }
-      tc_fence_before();  // order this tile's TMEM reads before the next tile's stores / MMAs
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem, kPtTmemCols);
   }
@@ -385,7 +402,7 @@ int launch_pairwise_tc(const float* packed, int B, int M, float* ws, const WsLay
   const int T = M + 2;
   const bool bf16 = variant == 2;
   const size_t bimg = (bf16 ? (P.tc16_end - P.tc16_begin) : (P.tc32_end - P.tc32_begin)) * sizeof(float);
-  const size_t smem = 128 + bimg + 64 + sizeof(float) * (PtSmem::w + (P.pair_end - P.l2a));
+  const size_t smem = 128 + bimg + 128 + sizeof(float) * (PtSmem::w + (P.pair_end - P.l2a));
   static bool configured[2] = {false, false};
   if (!configured[bf16]) {
     if (bf16)
