@@ -163,8 +163,9 @@ SHASTA_API int shasta_project_f32(const float* packed, int batch, int max_obj, f
                        float* det_boxes_inout, shasta_stream_t stream);
 
 /* Per-pair work (shasta.py:277-319): on-chip outer sum + ReLU, layers 2.. of the three pairwise MLPs,
- * hand-designed residuals, weighted sum -> RESIDUAL (B,T,RS). variant 0 = fp32 CUDA-core tiles,
- * 1 = tcgen05 3xTF32 tensor-core tiles (fp32-equivalent), 2 = tcgen05 bf16 tiles. */
+ * hand-designed residuals, weighted sum -> RESIDUAL (B,T,RS). variant 0 = default (= 1),
+ * 1 = tcgen05 3xTF32 tensor-core tiles (fp32-equivalent), 2 = tcgen05 bf16 tiles (bf16 tolerance),
+ * 3 = fp32 CUDA-core tiles. */
 SHASTA_API int shasta_pairwise_f32(const float* packed, int batch, int max_obj, float* workspace, int variant,
                         shasta_stream_t stream);
 

@@ -271,7 +271,8 @@ int launch_pairwise_tc(const float* packed, int B, int M, float* ws, const WsLay
 
 int launch_pairwise(const float* packed, int B, int M, float* ws, const WsLayout& L, int variant,
                     cudaStream_t s) {
-  if (variant != 0) return launch_pairwise_tc(packed, B, M, ws, L, variant, s);
+  // 0 = default (tcgen05 3xTF32, fp32-equivalent), 1 = tcgen05 3xTF32, 2 = tcgen05 bf16, 3 = CUDA-core fp32
+  if (variant != 3) return launch_pairwise_tc(packed, B, M, ws, L, variant == 0 ? 1 : variant, s);
   const PackLayout P = pack_layout(M);
   const int T = M + 2;
   const size_t smem = sizeof(float) * (PwSmem::w + (P.pair_end - P.l2a));

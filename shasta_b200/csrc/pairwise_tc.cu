@@ -20,8 +20,8 @@ namespace shasta {
 
 using namespace tc;
 
-constexpr int kPtTT = 8;            // t rows per CTA
-constexpr int kPtDT = 64;           // d columns per CTA = 4 MMA tiles of 8 x 16 pairs
+constexpr int kPtTT = 16;           // t rows per CTA (two 8-row tile rows)
+constexpr int kPtDT = 64;           // d columns per CTA = 4 MMA tile columns; a CTA walks up to 2 x 4 tiles of 8 x 16 pairs
 constexpr int kPtQStride = 148;     // floats per d row of the staged PROJ_CUR tile (148 % 32 = 20: conflict-free LDS.128)
 constexpr int kPtThreads = 288;     // 8 worker warps (two threads per pair) + 1 MMA warp
 constexpr int kPtTmemCols = 256;
@@ -105,9 +105,9 @@ __device__ __forceinline__ void build_a(const float* __restrict__ prow, const fl
 }
 
 struct PtSmem {  // float offsets inside dynamic shared memory (after the 1 KB aligned base)
-  static constexpr int ps = 0;                                  // [8][144]
+  static constexpr int ps = 0;                                  // [16][144]
   static constexpr int qs = ps + kPtTT * kProj;                 // [64][148]
-  static constexpr int auxp = qs + kPtDT * kPtQStride;          // [8][8]
+  static constexpr int auxp = qs + kPtDT * kPtQStride;          // [16][8]
   static constexpr int auxc = auxp + kPtTT * 8;                 // [64][8]
   static constexpr int cn = auxc + kPtDT * 8;                   // [64]
   static constexpr int shp = cn + kPtDT;                        // [2][128] fuse_shape results (group B -> group A)
@@ -186,7 +186,10 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - sbase));
 
-  const int ntiles = kPtDT / 16;
+  // only the tiles that contain real pairs (D = 202 -> 13 tile columns, not 16; T = 202 -> 26 tile rows)
+  const int ntd = min(kPtDT / 16, (D - d0 + 15) / 16);
+  const int ntt = min(kPtTT / 8, (T - t0 + 7) / 8);
+  const int ntiles = ntd * ntt;
 
   if (warp == 8) {
     // ===================== MMA issuer =====================
@@ -245,7 +248,6 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
     const int r = tid & 127;           // pair row inside the tile == TMEM lane
     const int ti = r >> 4, di = r & 15;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const float* prow = Ps + ti * kProj;
     const float* B2a = Ws + (P.l2a_b - wbase);
     const float* B2b = Ws + (P.l2b_b - wbase);
     const float* B2c = Ws + (P.l2c_b - wbase);
@@ -257,14 +259,16 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
     const float* B3b = Ws + (P.l3b_b - wbase);
     const float* W3c = Ws + (P.l3c - wbase);
     const float* B3c = Ws + (P.l3c_b - wbase);
-    const float4 ap0 = *reinterpret_cast<const float4*>(Ap + ti * 8);
-    const float4 ap1 = *reinterpret_cast<const float4*>(Ap + ti * 8 + 4);
-    const int t = t0 + ti;
 
     for (int tile = 0; tile < ntiles; ++tile) {
       const uint32_t ph = tile & 1;
-      const int dl = tile * 16 + di;
+      const int tl = (tile / ntd) * 8 + ti;     // row of the staged PROJ_PREV block
+      const int dl = (tile % ntd) * 16 + di;    // row of the staged PROJ_CUR block
+      const int t = t0 + tl;
+      const float* prow = Ps + tl * kProj;
       const float* qrow = Qs + dl * kPtQStride;
+      const float4 ap0 = *reinterpret_cast<const float4*>(Ap + tl * 8);
+      const float4 ap1 = *reinterpret_cast<const float4*>(Ap + tl * 8 + 4);
 
       if (!grp_b) {
         // ---------------- group A ----------------
@@ -395,7 +399,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
 int launch_pairwise_tc(const float* packed, int B, int M, float* ws, const WsLayout& L, int variant,
                        cudaStream_t s) {
   if (variant != 1 && variant != 2) {
-    set_error("pairwise variant %d unknown (0 = CUDA cores, 1 = tcgen05 3xTF32, 2 = tcgen05 bf16)", variant);
+    set_error("pairwise variant %d unknown (0 = default, 1 = tcgen05 3xTF32, 2 = tcgen05 bf16, 3 = CUDA cores)", variant);
     return SHASTA_ERR_ARG;
   }
   const PackLayout P = pack_layout(M);

@@ -19,7 +19,7 @@ from . import registry as builder
 from .registry import TRACK
 
 FLAG_TMA_GATHER = 1
-PAIRWISE_FFMA, PAIRWISE_TF32X3, PAIRWISE_BF16 = 0, 1, 2
+PAIRWISE_DEFAULT, PAIRWISE_TF32X3, PAIRWISE_BF16, PAIRWISE_FFMA = 0, 1, 2, 3   # kernel_flags bits 4-7
 
 
 class _Workspace:
