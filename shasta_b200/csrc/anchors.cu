@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256)
 anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, const float* __restrict__ det_boxes,
                      const float* __restrict__ prev_boxes, int B, int M, float* __restrict__ feat_cur,
                      float* __restrict__ feat_prev, float* __restrict__ box_cur, float* __restrict__ box_prev,
-                     float* __restrict__ anchor_box) {
+                     float* __restrict__ anchor_box, int nbx) {
   extern __shared__ __align__(16) float sm[];
   const int T = M + 2, N5 = 5 * M, H7 = (7 * M) / 32;
   const int role = blockIdx.x;
@@ -162,31 +162,37 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
     const int i = role - 5;
     const float* src = (i < 2) ? det_boxes : prev_boxes;  // boxes BEFORE back-projection
     const int K7 = 7 * M;
-    float* xb = sm;            // [2][K7] flat (M,7) boxes of two frame pairs
-    float* hd = sm + 2 * K7;   // [2][H7]
-    for (int bb = 0; bb < nb; bb += 2) {
-      const int nb2 = min(2, nb - bb);
+    // as many frame pairs at once as fit in the shared memory this launch was given (nbx passed by the host)
+    float* xb = sm;                // [nbx][K7] flat (M,7) boxes
+    float* hd = sm + nbx * K7;     // [nbx][H7]
+    for (int bb = 0; bb < nb; bb += nbx) {
+      const int nb2 = min(nbx, nb - bb);
       __syncthreads();
       for (int idx = threadIdx.x; idx < nb2 * K7; idx += blockDim.x) {
         const int g = idx / K7, k = idx % K7;
         xb[idx] = src[((size_t)(bg0 + bb + g) * M + k / 7) * 11 + (k % 7)];
       }
+      for (int idx = nb2 * K7 + threadIdx.x; idx < nbx * K7; idx += blockDim.x) xb[idx] = 0.f;
       __syncthreads();
       for (int h = warp; h < H7; h += 8) {
         const float* wr = a.dw0[i] + (size_t)h * K7;
-        float acc0 = 0.f, acc1 = 0.f;
+        float acc[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) acc[g] = 0.f;
 #pragma unroll 4
         for (int k = lane; k < K7; k += 32) {
           const float wv = __ldg(wr + k);
-          acc0 = fmaf(wv, xb[k], acc0);
-          acc1 = fmaf(wv, xb[K7 + k], acc1);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (g < nbx) acc[g] = fmaf(wv, xb[g * K7 + k], acc[g]);
         }
-        acc0 = warp_sum(acc0);
-        acc1 = warp_sum(acc1);
-        if (lane == 0) {
-          const float bh = a.db0[i][h];
-          hd[h] = fmaxf(acc0 + bh, 0.f);
-          hd[H7 + h] = fmaxf(acc1 + bh, 0.f);
+        const float bh = a.db0[i][h];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (g < nbx) {
+            const float v = warp_sum(acc[g]);
+            if (lane == 0) hd[g * H7 + h] = fmaxf(v + bh, 0.f);
+          }
         }
       }
       __syncthreads();
@@ -320,7 +326,10 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   const int H7 = (7 * M) / 32;
   const int BG = (B > 4 && (size_t)8 * (N5 + H7 + 1) * sizeof(float) <= 200 * 1024) ? 8 : 4;
   const size_t smem_shape = sizeof(float) * (size_t)BG * N5;
-  const size_t smem_dets = sizeof(float) * (2 * (size_t)(7 * M) + 2 * (size_t)(H7 > 0 ? H7 : 1));
+  // anchor-box role: frame pairs staged at once (all BG of them unless that needs more than 160 KB)
+  int nbx = (int)((160u * 1024u) / (sizeof(float) * (size_t)(7 * M + (H7 > 0 ? H7 : 1))));
+  nbx = nbx > BG ? BG : (nbx < 1 ? 1 : nbx);
+  const size_t smem_dets = sizeof(float) * (size_t)nbx * (size_t)(7 * M + (H7 > 0 ? H7 : 1));
   const size_t smem = smem_shape > smem_dets ? smem_shape : smem_dets;
   static size_t configured[2] = {0, 0};
   if (smem > 48 * 1024 && smem > configured[BG == 8]) {
@@ -338,10 +347,10 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   float* ab = ws + L.off[SHASTA_WS_ANCHOR_BOX];
   if (BG == 8)
     anchor_finish_kernel<8><<<fgrid, 256, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev, bc,
-                                                     bp, ab);
+                                                     bp, ab, nbx);
   else
     anchor_finish_kernel<4><<<fgrid, 256, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev, bc,
-                                                     bp, ab);
+                                                     bp, ab, nbx);
   SHASTA_CHECK_LAUNCH("anchor_finish_kernel");
   return 0;
 }
