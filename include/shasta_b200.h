@@ -65,6 +65,27 @@ typedef struct shasta_params {
   const float* aff_b[6];
 } shasta_params_t;
 
+/* Gradient buffers, same fields and (out,in) layout as shasta_params_t (they are the .grad tensors). The backward
+ * pass ACCUMULATES into them (+=); a NULL pointer means "parameter frozen, skip". */
+typedef struct shasta_grads {
+  float* aug_shape_w0[4];
+  float* aug_shape_b0[4];
+  float* aug_shape_w2[4];
+  float* aug_shape_b2[4];
+  float* aug_dets_w0[4];
+  float* aug_dets_b0[4];
+  float* aug_dets_w2[4];
+  float* aug_dets_b2[4];
+  float* fuse_shape_w[4];
+  float* fuse_shape_b[4];
+  float* fuse_det_w[3];
+  float* fuse_det_b[3];
+  float* res_coeff_w[3];
+  float* res_coeff_b[3];
+  float* aff_w[6];
+  float* aff_b[6];
+} shasta_grads_t;
+
 /* BEV geometry of BEVFeatureExtractor (bird_eye_view.py:11-22). */
 typedef struct shasta_geom {
   float pc_start_x, pc_start_y;
@@ -182,6 +203,19 @@ SHASTA_API int shasta_forward_f32(const shasta_params_t* host_params, const floa
                        const float* prev_bev, float* det_boxes, const float* prev_det_boxes, int batch,
                        const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes,
                        float* matched1, float* matched2, uint32_t flags, shasta_stream_t stream);
+
+/* Backward of the head for the training configuration (tools/nusc_shasta/train.py:201-214, BASELINE.json config 5).
+ * Call after shasta_forward_f32 on the SAME workspace (its regions hold the saved activations) with the forward's
+ * outputs matched1/matched2 and the upstream gradients gm1 (B,M,M+2), gm2 (B,M+2,M) of the loss. Computes
+ *   dlogits  = dual-softmax backward                                    (shasta.py:324-325)
+ *   aff.*    gradients and d residual                                   (shasta.py:323)
+ * and accumulates into the non-NULL entries of `host_grads`. Stages further upstream (pairwise MLPs, projections,
+ * anchors) are added to this entry point as they land; entries they would fill are left untouched until then.
+ * The workspace regions LOGITS / RESIDUAL are overwritten with dlogits / d residual. */
+SHASTA_API int shasta_backward_f32(const shasta_params_t* host_params, const shasta_grads_t* host_grads,
+                                   const float* packed, int batch, float* workspace, size_t workspace_bytes,
+                                   const float* matched1, const float* matched2, const float* gm1, const float* gm2,
+                                   shasta_stream_t stream);
 
 /* Per-kernel timing for the roofline report (no reference counterpart). After shasta_profile_begin(n), every
  * shasta_forward_f32 call with flag bit 8 (0x100) records CUDA events between its kernels (up to n calls);

@@ -40,6 +40,11 @@ class ShastaParams(ctypes.Structure):
     ]
 
 
+class ShastaGrads(ctypes.Structure):
+    """Mirror of shasta_grads_t (same fields as ShastaParams without the two leading ints)."""
+    _fields_ = [f for f in ShastaParams._fields_ if f[0] not in ("max_obj", "num_feats")]
+
+
 class ShastaGeom(ctypes.Structure):
     """Mirror of shasta_geom_t."""
     _fields_ = [
@@ -81,6 +86,8 @@ SYMBOLS = {
     "shasta_aff_softmax_f32": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "shasta_forward_f32": (_i, [ctypes.POINTER(ShastaParams), _vp, _vp, _vp, _vp, _vp, _i,
                                 ctypes.POINTER(ShastaGeom), _vp, _sz, _vp, _vp, _u32, _vp]),
+    "shasta_backward_f32": (_i, [ctypes.POINTER(ShastaParams), ctypes.POINTER(ShastaGrads), _vp, _i, _vp, _sz, _vp, _vp,
+                                 _vp, _vp, _vp]),
     "shasta_profile_begin": (_i, [_i]),
     "shasta_profile_end": (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "shasta_decode_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libshasta_b200.so")
 SOURCES = ["api.cu", "pack.cu", "gather.cu", "anchors.cu", "anchors_tc.cu", "anchors_tc2.cu", "project.cu", "pairwise.cu", "pairwise_tc.cu",
-           "aff_softmax.cu", "decode.cu"]
+           "aff_softmax.cu", "backward.cu", "decode.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -21,7 +21,7 @@ def _stale(obj, src):
     if not os.path.exists(obj):
         return True
     t = os.path.getmtime(obj)
-    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(HERE, "..", "include", "shasta_b200.h"), __file__]
+    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "dense_tile.cuh"), os.path.join(HERE, "..", "include", "shasta_b200.h"), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

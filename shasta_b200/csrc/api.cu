@@ -299,6 +299,37 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
   return 0;
 }
 
+int shasta_backward_f32(const shasta_params_t* host_params, const shasta_grads_t* host_grads, const float* packed,
+                        int batch, float* workspace, size_t workspace_bytes, const float* matched1,
+                        const float* matched2, const float* gm1, const float* gm2, shasta_stream_t stream) {
+  int rc = check_params(host_params);
+  if (rc) return rc;
+  const int M = host_params->max_obj;
+  rc = check_dims(batch, M);
+  if (rc) return rc;
+  NOT_NULL(host_grads);
+  NOT_NULL(packed);
+  NOT_NULL(workspace);
+  NOT_NULL(matched1);
+  NOT_NULL(matched2);
+  NOT_NULL(gm1);
+  NOT_NULL(gm2);
+  ALIGNED16(packed);
+  ALIGNED16(workspace);
+  if (workspace_bytes < shasta_workspace_bytes(batch, M)) {
+    set_error("workspace too small");
+    return SHASTA_ERR_SIZE;
+  }
+  for (int i = 0; i < 6; ++i)
+    if ((host_grads->aff_w[i] == nullptr) != (host_grads->aff_b[i] == nullptr)) {
+      set_error("aff.%d: weight and bias gradients must both be given or both be NULL", 2 * i);
+      return SHASTA_ERR_ARG;
+    }
+  if (batch == 0) return 0;
+  return launch_backward(*host_params, *host_grads, packed, batch, workspace, ws_layout(batch, M), matched1, matched2,
+                         gm1, gm2, (cudaStream_t)stream);
+}
+
 int shasta_profile_begin(int max_steps) {
   if (max_steps < 1 || max_steps > 4096) {
     set_error("profile: max_steps out of range");

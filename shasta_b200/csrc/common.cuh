@@ -76,6 +76,7 @@ struct PackLayout {
   size_t pair_end;    // end of the block the pairwise kernel stages in shared memory (from l2a)
   size_t aff_w[6];    // aff.{0..10}.weight^T : [in][out rounded up to a multiple of 4]
   size_t aff_b[6];
+  size_t aff_wn[6];   // aff.{0..10}.weight as (out, in rounded up to a multiple of 4): operand of the backward pass
   // UMMA B-operand images of the second pairwise layers (tensor-core variants), K-major canonical un-swizzled
   // layout [k/4][n][4] (tf32) or [k/8][n][8] (bf16), N padded to a multiple of 16 with zero rows.
   size_t tc32_begin;  // tf32 block: w2a hi, w2a lo (10x32x4 each), w2b hi, lo (18x32x4), w2c hi, lo (8x16x4)
@@ -123,6 +124,7 @@ __host__ inline PackLayout pack_layout(int M) {
     P.aff_w[i] = take(win[i] * ((wout[i] + 3) / 4 * 4));
     P.aff_b[i] = take((wout[i] + 3) / 4 * 4);
   }
+  for (int i = 0; i < 6; ++i) P.aff_wn[i] = take(wout[i] * ((win[i] + 3) / 4 * 4));
   P.tc32_begin = o;
   P.tc32_w2a_hi = take(10 * 32 * 4);
   P.tc32_w2a_lo = take(10 * 32 * 4);
@@ -194,6 +196,9 @@ int launch_pairwise(const float* packed, int B, int M, float* ws, const WsLayout
                     cudaStream_t s);
 int launch_aff_softmax(const float* packed, int B, int M, float* ws, const WsLayout& L, float* matched1,
                        float* matched2, cudaStream_t s, cudaEvent_t mid);
+int launch_backward(const shasta_params_t& p, const shasta_grads_t& g, const float* packed, int B, float* ws,
+                    const WsLayout& L, const float* m1, const float* m2, const float* gm1, const float* gm2,
+                    cudaStream_t s);
 int launch_decode(const float* m1, const float* m2, const int32_t* n_prev, const int32_t* n_det, int B, int M,
                   int32_t* prev_state, int32_t* prev_argmax, float* fn_score, int32_t* det_state,
                   int32_t* det_argmax, float* det_score, cudaStream_t s);

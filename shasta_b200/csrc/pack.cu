@@ -37,6 +37,15 @@ static int bimage(float* hi, float* lo, float* bf, const float* src, int src_ld,
   return 0;
 }
 
+// dst[j * dst_ld + k] = src[j * src_ld + k]   (row copy into a padded leading dimension)
+__global__ void copy_rows_kernel(float* __restrict__ dst, int dst_ld, const float* __restrict__ src, int src_ld,
+                                 int rows, int cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * cols) return;
+  const int j = (int)(idx / cols), k = (int)(idx % cols);
+  dst[(size_t)j * dst_ld + k] = src[(size_t)j * src_ld + k];
+}
+
 static int tblock(float* dst, int dst_ld, const float* src, int src_ld, int nj, int nk, cudaStream_t s) {
   const long long n = (long long)nj * nk;
   if (n == 0) return 0;
@@ -91,6 +100,10 @@ int launch_pack(const shasta_params_t& p, float* packed, cudaStream_t s) {
   for (int i = 0; i < 6; ++i) {
     TB(packed + P.aff_w[i], (wout[i] + 3) / 4 * 4, p.aff_w[i], win[i], wout[i], win[i], s);
     TB(packed + P.aff_b[i], wout[i], p.aff_b[i], 1, wout[i], 1, s);
+    const long long n = (long long)wout[i] * win[i];
+    copy_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(packed + P.aff_wn[i], (win[i] + 3) / 4 * 4, p.aff_w[i],
+                                                                 win[i], wout[i], win[i]);
+    SHASTA_CHECK_LAUNCH("copy_rows_kernel");
   }
   // tensor-core operand images of fuse_shape.2 (20x40), res_coeff.2 (18x72), fuse_det.2 (8x32)
   int rc = bimage(packed + P.tc32_w2a_hi, packed + P.tc32_w2a_lo, packed + P.tc16_w2a, p.fuse_shape_w[1], 40, 20, 32, 40, s);

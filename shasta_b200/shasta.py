@@ -231,9 +231,6 @@ class Shasta(nn.Module):
         if tuple(det_boxes.shape) != (B, M, 11) or tuple(prev_det_boxes.shape) != (B, M, 11):
             raise ValueError("boxes must be (B=%d, max_obj=%d, 11); got %s / %s" %
                              (B, M, tuple(det_boxes.shape), tuple(prev_det_boxes.shape)))
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            from .training import affinity_with_grad  # built on the same kernels (forward) + backward kernels
-            return affinity_with_grad(self, bev, prev_bev, det_boxes, prev_det_boxes)
         if B == 0:
             return (torch.empty((0, M, M + 2), dtype=torch.float32, device=device),
                     torch.empty((0, M + 2, M), dtype=torch.float32, device=device))
@@ -245,9 +242,27 @@ class Shasta(nn.Module):
         prev_c = prev_det_boxes.to(device, non_blocking=True).contiguous()
         det_c = det_boxes.to(device, non_blocking=True).contiguous()
 
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.aff.parameters()):
+            # training configuration: same forward kernels on a private workspace + CUDA backward (training.py)
+            from .training import affinity_with_grad
+            m1, m2 = affinity_with_grad(self, bev, prev_bev, det_c, prev_c)
+        else:
+            m1, m2, _ = self._launch_forward(bev, prev_bev, det_c, prev_c, self._workspace(B, device))
+        if det_c is not det_boxes:
+            if det_boxes.is_cuda:
+                det_boxes[:, :, :2] = det_c[:, :, :2]
+            else:  # pinned host input: asynchronous write-back of the back-projected boxes (shasta.py:270)
+                det_boxes.copy_(det_c, non_blocking=True)
+        return m1, m2
+
+    def _launch_forward(self, bev, prev_bev, det_c, prev_c, ws):
+        """Enqueues the five forward kernels on the current stream. Inputs are validated, contiguous, boxes on the
+        device; ``ws`` is the workspace the activations are left in (the backward pass reads them)."""
+        device = det_c.device
+        B, H, W, _ = bev.shape
+        M = self.max_obj
         lib = _cabi.lib()
         self._ensure_packed(device)
-        ws = self._workspace(B, device)
         m1 = torch.empty((B, M, M + 2), dtype=torch.float32, device=device)
         m2 = torch.empty((B, M + 2, M), dtype=torch.float32, device=device)
         geom = self.bev_extractor.geom(H, W)
@@ -258,15 +273,10 @@ class Shasta(nn.Module):
                 m1.data_ptr(), m2.data_ptr(), int(self.kernel_flags),
                 ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
         _cabi.check(rc, "shasta_forward_f32")
-        if det_c is not det_boxes:
-            if det_boxes.is_cuda:
-                det_boxes[:, :, :2] = det_c[:, :, :2]
-            else:  # pinned host input: asynchronous write-back of the back-projected boxes (shasta.py:270)
-                det_boxes.copy_(det_c, non_blocking=True)
         anchors = ws.region(_cabi.WS_ANCHOR_BOX, B * 4 * 7).view(B, 4, 7)
         self.newborn, self.fp = anchors[:, 0:1, :], anchors[:, 1:2, :]
         self.dead_trk, self.fn = anchors[:, 2:3, :], anchors[:, 3:4, :]
-        return m1, m2
+        return m1, m2, ws
 
     def forward(self, example, train_mode=True, **kwargs):
         """shasta.py:213-327. ``example`` needs ``det_boxes`` and ``prev_det_boxes`` (B,M,11) and either the

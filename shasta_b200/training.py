@@ -1,0 +1,63 @@
+"""Training configuration (BASELINE.json config 5): forward on a private workspace + hand-written CUDA backward.
+
+The reference trains the head with plain autograd (tools/nusc_shasta/train.py:195-215: forward, the two masked
+cross-entropy terms on matched1/matched2, ``loss.backward()``, Adam). Here the forward is the same set of kernels as
+inference; ``torch.autograd`` only sees one node whose backward calls ``shasta_backward_f32``:
+dual-softmax backward, the aff row-MLP backward (weight/bias gradients + d residual).
+
+Gradient coverage of this revision: ``aff.*``. The pairwise MLPs, the per-object projections and the anchor generators
+are not differentiated yet (their parameters receive no gradient, like the frozen trunk); DESIGN.md §7 tracks it.
+"""
+import ctypes
+
+import torch
+
+from . import _cabi
+
+AFF_LAYERS = (0, 2, 4, 6, 8, 10)
+
+
+def differentiable_parameters(model):
+    """Parameters that receive gradients from the CUDA backward, in the order the autograd node expects them."""
+    out = []
+    for li in AFF_LAYERS:
+        out += [model.aff[li].weight, model.aff[li].bias]
+    return out
+
+
+class _AffinityFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, bev, prev_bev, det_c, prev_c, *params):
+        from .shasta import _Workspace
+        B = bev.shape[0]
+        ws = _Workspace(B, model.max_obj, det_c.device)   # private: the backward reads the saved activations
+        m1, m2, _ = model._launch_forward(bev, prev_bev, det_c, prev_c, ws)
+        ctx.model, ctx.ws, ctx.batch = model, ws, B
+        ctx.save_for_backward(m1, m2)
+        return m1, m2
+
+    @staticmethod
+    def backward(ctx, gm1, gm2):
+        model, ws, B = ctx.model, ctx.ws, ctx.batch
+        m1, m2 = ctx.saved_tensors
+        gm1 = torch.zeros_like(m1) if gm1 is None else gm1.contiguous().float()
+        gm2 = torch.zeros_like(m2) if gm2 is None else gm2.contiguous().float()
+        lib = _cabi.lib()
+        params = differentiable_parameters(model)
+        grads = [torch.zeros_like(p) for p in params]
+        g = _cabi.ShastaGrads()
+        for n in range(6):
+            g.aff_w[n] = grads[2 * n].data_ptr()
+            g.aff_b[n] = grads[2 * n + 1].data_ptr()
+        device = m1.device
+        with torch.cuda.device(device):
+            rc = lib.shasta_backward_f32(
+                ctypes.byref(model._cparams), ctypes.byref(g), model._packed.data_ptr(), B, ws.buf.data_ptr(), ws.nbytes,
+                m1.data_ptr(), m2.data_ptr(), gm1.data_ptr(), gm2.data_ptr(),
+                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+        _cabi.check(rc, "shasta_backward_f32")
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def affinity_with_grad(model, bev, prev_bev, det_c, prev_c):
+    return _AffinityFunction.apply(model, bev, prev_bev, det_c, prev_c, *differentiable_parameters(model))
