@@ -32,9 +32,15 @@ struct T2Cfg {
   static constexpr int kStageBytes = kT2WTile + 2 * kXTile;        // Whi | Xhi | Xlo
   static constexpr int kStages = (BN == 64) ? 6 : 4;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
-  static constexpr int kColD = 0;                                  // two accumulator buffers of BN columns
-  static constexpr int kColWl = 2 * BN;                            // kStages x 32 columns of weight low parts
-  static_assert(2 * BN + kStages * 32 <= 512, "TMEM budget");
+  // BN = 64: the Xhi and Xlo tiles are adjacent in shared memory and are fed as ONE 128-row B operand, so that
+  // Whi*Xhi^T and Whi*Xlo^T come out of a single N = 128 MMA (columns [0,64) and [64,128) of the accumulator); the
+  // TMEM-A MMA adds Wlo*Xhi^T into columns [0,64). Two MMAs per K step instead of three: the single issuing thread,
+  // not the tensor pipe, was the limiter (ncu: 37 % tensor-active at 32-cycle MMAs).
+  static constexpr bool kFuseX = (BN == 64);
+  static constexpr int kDW = kFuseX ? 2 * BN : BN;                 // accumulator buffer width in TMEM columns
+  static constexpr int kColD = 0;                                  // two accumulator buffers of kDW columns
+  static constexpr int kColWl = 2 * kDW;                           // kStages x 32 columns of weight low parts
+  static_assert(2 * kDW + kStages * 32 <= 512, "TMEM budget");
 };
 
 struct AnchorT2Maps {
@@ -122,6 +128,7 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(kFmtTF32, kT2BM, BN);
+      constexpr uint32_t idesc2 = umma_idesc(kFmtTF32, kT2BM, 2 * BN > 256 ? 256 : 2 * BN);
       int st = 0;
       uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
@@ -136,13 +143,17 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M
         const uint32_t sb = base + st * C::kStageBytes;
         const uint64_t dwh = umma_desc_sw128(sb);
         const uint64_t dxh = umma_desc_sw128(sb + kT2WTile), dxl = umma_desc_sw128(sb + kT2WTile + C::kXTile);
-        const uint32_t d = tmem + (uint32_t)(C::kColD + buf * BN);
+        const uint32_t d = tmem + (uint32_t)(C::kColD + buf * C::kDW);
         const uint32_t wl = tmem + (uint32_t)(C::kColWl + st * 32);
 #pragma unroll
         for (int k = 0; k < kT2BK / 8; ++k) {
           const uint64_t adv = (uint64_t)((k * 32) >> 4);
-          mma_tf32(d, dwh + adv, dxh + adv, idesc, !(first && k == 0));
-          mma_tf32(d, dwh + adv, dxl + adv, idesc, 1);
+          if (C::kFuseX) {
+            mma_tf32(d, dwh + adv, dxh + adv, idesc2, !(first && k == 0));   // [Xhi; Xlo] as one 128-row operand
+          } else {
+            mma_tf32(d, dwh + adv, dxh + adv, idesc, !(first && k == 0));
+            mma_tf32(d, dwh + adv, dxl + adv, idesc, 1);
+          }
           t2_mma_ts_tf32(d, wl + (uint32_t)(k * 8), dxh + adv, idesc, 1);
         }
         mma_commit(empty_bar(st));
@@ -167,10 +178,18 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(lane_base + (uint32_t)(C::kColD + buf * BN + c0), v);
-        tmem_ld_wait();
+        tmem_ld16(lane_base + (uint32_t)(C::kColD + buf * C::kDW + c0), v);
+        if (C::kFuseX) {
+          uint32_t v2[16];
+          tmem_ld16(lane_base + (uint32_t)(C::kColD + buf * C::kDW + BN + c0), v2);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+        }
       }
       tc_fence_before();
       mbar_arrive(dempty_bar(buf));
