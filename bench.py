@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0, help="kernel variant flags (see shasta_b200.h)")
     ap.add_argument("--anchor-path", type=int, default=0, help="0 auto, 1 streaming CUDA-core, 2 tcgen05")
     ap.add_argument("--raw-hi", type=int, default=1)
+    ap.add_argument("--dbg", type=int, default=0, help="kernel experiment bits (results invalid when non-zero)")
+    ap.add_argument("--splits", type=int, default=0, help="force the split-K count of the anchors GEMM (experiment)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -298,6 +300,8 @@ def main():
     lib = _cabi.lib()
     lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, a.anchor_path)
     lib.shasta_set_option(_cabi.OPT_TC_RAW_HI, a.raw_hi)
+    lib.shasta_set_option(2, a.dbg)
+    lib.shasta_set_option(3, a.splits)
     pc_start, d, bev, prev_bev = make_inputs(a, device, seed=1000 + rank)
     model = build_model(a, pc_start, device)
     det0 = torch.from_numpy(d["det_boxes"]).to(device)

@@ -121,7 +121,9 @@ enum shasta_region {
   SHASTA_WS_LOGITS = 11,
   SHASTA_WS_ANCHOR_BOX = 12,
   SHASTA_WS_PROJ_CUR_T = 13,
-  SHASTA_WS_NUM_REGIONS = 14
+  SHASTA_WS_DPROJ_PREV = 14, /* (B,T,144) gradients of the first-layer projections (backward pass only) */
+  SHASTA_WS_DPROJ_CUR = 15,
+  SHASTA_WS_NUM_REGIONS = 16
 };
 
 /* Runtime options (process-wide, not thread-safe; meant for tests and benchmarks).
@@ -209,8 +211,11 @@ SHASTA_API int shasta_forward_f32(const shasta_params_t* host_params, const floa
  * outputs matched1/matched2 and the upstream gradients gm1 (B,M,M+2), gm2 (B,M+2,M) of the loss. Computes
  *   dlogits  = dual-softmax backward                                    (shasta.py:324-325)
  *   aff.*    gradients and d residual                                   (shasta.py:323)
- * and accumulates into the non-NULL entries of `host_grads`. Stages further upstream (pairwise MLPs, projections,
- * anchors) are added to this entry point as they land; entries they would fill are left untouched until then.
+ *   fuse_shape.*, res_coeff.*, fuse_det.* gradients (all layers, incl. the decomposed first ones) and the
+ *            gradients of the per-object projections                    (shasta.py:286-319)
+ * and accumulates into the non-NULL entries of `host_grads` (the aff group and the pairwise group must each be given
+ * completely or not at all). aug_shape.* / aug_dets.* (anchor generators) are not differentiated yet: those entries are
+ * ignored.
  * The workspace regions LOGITS / RESIDUAL are overwritten with dlogits / d residual. */
 SHASTA_API int shasta_backward_f32(const shasta_params_t* host_params, const shasta_grads_t* host_grads,
                                    const float* packed, int batch, float* workspace, size_t workspace_bytes,

@@ -67,7 +67,7 @@ __device__ __forceinline__ void t2_mma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a,
 template <int BN>
 __global__ void __launch_bounds__(kT2Threads, 1)
 anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M, int S, int ntiles_n, int raw_hi,
-                         float* __restrict__ part) {
+                         float* __restrict__ part, int dbg) {
   using C = T2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -147,6 +147,7 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M
         const uint32_t wl = tmem + (uint32_t)(C::kColWl + st * 32);
 #pragma unroll
         for (int k = 0; k < kT2BK / 8; ++k) {
+          if (dbg & 1) break;  // timing experiment: no MMAs (results are garbage)
           const uint64_t adv = (uint64_t)((k * 32) >> 4);
           if (C::kFuseX) {
             mma_tf32(d, dwh + adv, dxh + adv, idesc2, !(first && k == 0));   // [Xhi; Xlo] as one 128-row operand
@@ -205,6 +206,12 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M
 
       mbar_wait(full_bar(st), ph);
       uint8_t* sg = gen_base + st * C::kStageBytes;
+      if (dbg & 2) {  // timing experiment: no split work
+        tc_fence_before();
+        mbar_arrive(split_bar(st));
+        if (++st == C::kStages) st = 0, ph ^= 1;
+        continue;
+      }
       // --- weight tile: row r, 8 chunks of 16 bytes, 128B-swizzled (chunk c lives at c ^ (r & 7))
 #pragma unroll
       for (int c = 0; c < 8; c += 2) {
@@ -313,6 +320,7 @@ int anchor_tc2_splits(int M, int B) {
     const double cost = waves * ((double)(kblocks + S - 1) / S + 16.0);
     if (cost < best_cost) best_cost = cost, best = S;
   }
+  if (g_options[3] > 0 && g_options[3] <= smax) best = g_options[3];  // experiment knob: forced split count
   return best;
 }
 
@@ -341,10 +349,11 @@ int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, co
   const int ntn = (int)((N5 + kT2BM - 1) / kT2BM), ntb = (B + bn - 1) / bn;
   dim3 grid(ntn * ntb, 4, S);
   const int raw_hi = g_options[SHASTA_OPT_TC_RAW_HI];
+  const int dbg = g_options[2];
   if (bn == 64)
-    anchor_hidden_tc2_kernel<64><<<grid, kT2Threads, T2Cfg<64>::kSmemBytes, s>>>(maps, B, M, S, ntn, raw_hi, part);
+    anchor_hidden_tc2_kernel<64><<<grid, kT2Threads, T2Cfg<64>::kSmemBytes, s>>>(maps, B, M, S, ntn, raw_hi, part, dbg);
   else
-    anchor_hidden_tc2_kernel<128><<<grid, kT2Threads, T2Cfg<128>::kSmemBytes, s>>>(maps, B, M, S, ntn, raw_hi, part);
+    anchor_hidden_tc2_kernel<128><<<grid, kT2Threads, T2Cfg<128>::kSmemBytes, s>>>(maps, B, M, S, ntn, raw_hi, part, dbg);
   SHASTA_CHECK_LAUNCH("anchor_hidden_tc2_kernel");
   return 0;
 }

@@ -325,6 +325,19 @@ int shasta_backward_f32(const shasta_params_t* host_params, const shasta_grads_t
       set_error("aff.%d: weight and bias gradients must both be given or both be NULL", 2 * i);
       return SHASTA_ERR_ARG;
     }
+  {
+    const float* const* grp[] = {host_grads->fuse_shape_w, host_grads->fuse_shape_b, host_grads->fuse_det_w,
+                                 host_grads->fuse_det_b,   host_grads->res_coeff_w,  host_grads->res_coeff_b};
+    const int cnt[] = {4, 4, 3, 3, 3, 3};
+    int given = 0, total = 0;
+    for (int q = 0; q < 6; ++q)
+      for (int i = 0; i < cnt[q]; ++i) total++, given += (grp[q][i] != nullptr);
+    if (given != 0 && given != total) {
+      set_error("fuse_shape / fuse_det / res_coeff gradients must be given completely or not at all (%d of %d)", given,
+                total);
+      return SHASTA_ERR_ARG;
+    }
+  }
   if (batch == 0) return 0;
   return launch_backward(*host_params, *host_grads, packed, batch, workspace, ws_layout(batch, M), matched1, matched2,
                          gm1, gm2, (cudaStream_t)stream);

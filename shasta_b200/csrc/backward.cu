@@ -211,6 +211,10 @@ int launch_backward(const shasta_params_t& p, const shasta_grads_t& g, const flo
   aff_bwd_kernel<<<(unsigned)((nrows + kAffRows - 1) / kAffRows), kAffThreads, smem, s>>>(packed, P, B, M, residual,
                                                                                         logits, ag, residual);
   SHASTA_CHECK_LAUNCH("aff_bwd_kernel");
+  if (g.fuse_shape_w[0] != nullptr) {
+    int rc = launch_backward_pair(g, packed, B, M, ws, L, s);
+    if (rc) return rc;
+  }
   return 0;
 }
 

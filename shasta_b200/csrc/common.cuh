@@ -48,6 +48,8 @@ __host__ inline WsLayout ws_layout(int B, int M) {
   sz[SHASTA_WS_LOGITS] = (size_t)B * T * row_stride(M);
   sz[SHASTA_WS_ANCHOR_BOX] = (size_t)B * 4 * 7;
   sz[SHASTA_WS_PROJ_CUR_T] = (size_t)B * T * kProj;
+  sz[SHASTA_WS_DPROJ_PREV] = (size_t)B * T * kProj;
+  sz[SHASTA_WS_DPROJ_CUR] = (size_t)B * T * kProj;
   size_t o = 0;
   for (int i = 0; i < SHASTA_WS_NUM_REGIONS; ++i) {
     L.off[i] = o;
@@ -199,6 +201,8 @@ int launch_aff_softmax(const float* packed, int B, int M, float* ws, const WsLay
 int launch_backward(const shasta_params_t& p, const shasta_grads_t& g, const float* packed, int B, float* ws,
                     const WsLayout& L, const float* m1, const float* m2, const float* gm1, const float* gm2,
                     cudaStream_t s);
+int launch_backward_pair(const shasta_grads_t& g, const float* packed, int B, int M, float* ws, const WsLayout& L,
+                         cudaStream_t s);
 int launch_decode(const float* m1, const float* m2, const int32_t* n_prev, const int32_t* n_det, int B, int M,
                   int32_t* prev_state, int32_t* prev_argmax, float* fn_score, int32_t* det_state,
                   int32_t* det_argmax, float* det_score, cudaStream_t s);

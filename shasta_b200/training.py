@@ -3,10 +3,12 @@
 The reference trains the head with plain autograd (tools/nusc_shasta/train.py:195-215: forward, the two masked
 cross-entropy terms on matched1/matched2, ``loss.backward()``, Adam). Here the forward is the same set of kernels as
 inference; ``torch.autograd`` only sees one node whose backward calls ``shasta_backward_f32``:
-dual-softmax backward, the aff row-MLP backward (weight/bias gradients + d residual).
+dual-softmax backward, the aff row-MLP backward, the pairwise-MLP backward and the first-layer weight gradients.
 
-Gradient coverage of this revision: ``aff.*``. The pairwise MLPs, the per-object projections and the anchor generators
-are not differentiated yet (their parameters receive no gradient, like the frozen trunk); DESIGN.md §7 tracks it.
+Gradient coverage of this revision: ``aff.*``, ``fuse_shape.*``, ``res_coeff.*``, ``fuse_det.*`` (the pairwise MLPs
+incl. their decomposed first layers) — BASELINE.json config 5's "forward + backward of the pairwise MLP and the
+softmax". The anchor generators (``aug_shape.*``, ``aug_dets.*``) and ``shared_conv`` are not differentiated yet (their
+parameters receive no gradient, like the frozen trunk); DESIGN.md §7 tracks it.
 """
 import ctypes
 
@@ -15,14 +17,22 @@ import torch
 from . import _cabi
 
 AFF_LAYERS = (0, 2, 4, 6, 8, 10)
+GROUPS = (("aff", AFF_LAYERS), ("fuse_shape", (0, 2, 4, 6)), ("fuse_det", (0, 2, 4)), ("res_coeff", (0, 2, 4)))
 
 
 def differentiable_parameters(model):
-    """Parameters that receive gradients from the CUDA backward, in the order the autograd node expects them."""
+    """Parameters that receive gradients from the CUDA backward, in the order the autograd node expects them:
+    aff.*, fuse_shape.*, fuse_det.*, res_coeff.* (weight, bias per layer)."""
     out = []
-    for li in AFF_LAYERS:
-        out += [model.aff[li].weight, model.aff[li].bias]
+    for name, layers in GROUPS:
+        seq = getattr(model, name)
+        for li in layers:
+            out += [seq[li].weight, seq[li].bias]
     return out
+
+
+def differentiable_parameter_names():
+    return ["%s.%d.%s" % (name, li, k) for name, layers in GROUPS for li in layers for k in ("weight", "bias")]
 
 
 class _AffinityFunction(torch.autograd.Function):
@@ -46,9 +56,12 @@ class _AffinityFunction(torch.autograd.Function):
         params = differentiable_parameters(model)
         grads = [torch.zeros_like(p) for p in params]
         g = _cabi.ShastaGrads()
-        for n in range(6):
-            g.aff_w[n] = grads[2 * n].data_ptr()
-            g.aff_b[n] = grads[2 * n + 1].data_ptr()
+        it = iter(grads)
+        for name, layers in GROUPS:
+            gw, gb = getattr(g, name + "_w"), getattr(g, name + "_b")
+            for n in range(len(layers)):
+                gw[n] = next(it).data_ptr()
+                gb[n] = next(it).data_ptr()
         device = m1.device
         with torch.cuda.device(device):
             rc = lib.shasta_backward_f32(
