@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--raw-hi", type=int, default=1)
     ap.add_argument("--dbg", type=int, default=0, help="kernel experiment bits (results invalid when non-zero)")
     ap.add_argument("--splits", type=int, default=0, help="force the split-K count of the anchors GEMM (experiment)")
+    ap.add_argument("--train", action="store_true",
+                    help="BASELINE.json config 5: training step (forward + loss + CUDA backward + gradient all-reduce "
+                         "+ Adam on the differentiated parameters) instead of inference")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -277,10 +280,104 @@ def cpu_reference_timed(a, steps, warm):
 
 
 # --------------------------------------------------------------------------------------------------
+def run_train(a):
+    """Config 5: data-parallel training step of the head. One step = forward (same kernels as inference) + the
+    reference's loss (train.py:201-211) + CUDA backward + all-reduce of the gradients over the ranks + Adam."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    from shasta_b200 import _cabi, loss as L, training
+    lib = _cabi.lib()
+    pc_start, d, bev, prev_bev = make_inputs(a, device, seed=2000 + rank)
+    model = build_model(a, pc_start, device)
+    model.train()
+    params = training.differentiable_parameters(model)
+    for p_ in model.parameters():
+        p_.requires_grad_(False)
+    for p_ in params:
+        p_.requires_grad_(True)
+    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-2)
+    B, M = a.batch, a.max_obj
+    det0 = torch.from_numpy(d["det_boxes"]).to(device)
+    prev = torch.from_numpy(d["prev_det_boxes"]).to(device)
+    det = det0.clone()
+    rng = np.random.default_rng(7 + rank)
+    gt = np.zeros((B, M + 2, M + 2), np.float32)
+    for b_ in range(B):
+        for t in range(int(d["n_prev"][b_])):
+            gt[b_, t, rng.integers(0, M + 2)] = 1.0
+    gt = torch.from_numpy(gt).to(device)
+    flat = torch.zeros(sum(p_.numel() for p_ in params), device=device)
+
+    def step():
+        det.copy_(det0)
+        opt.zero_grad(set_to_none=True)
+        m1, m2 = model.affinity(bev, prev_bev, det, prev)
+        loss = L.affinity_loss(m1, m2, gt)
+        loss.backward()
+        if dist is not None:   # DDP-style gradient averaging: one flat all-reduce (0.6 MB)
+            torch.cat([p_.grad.reshape(-1) for p_ in params], out=flat)
+            dist.all_reduce(flat)
+            flat.div_(world)
+            o = 0
+            for p_ in params:
+                p_.grad.copy_(flat[o:o + p_.numel()].view_as(p_))
+                o += p_.numel()
+        opt.step()
+        return loss
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_w, n_warm = time.time(), 0
+    while n_warm < max(a.warmup, 3) or time.time() - t_w < 0.6:
+        step()
+        n_warm += 1
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
+    e0.record()
+    for _ in range(a.steps):
+        loss = step()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end)
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        tms = torch.tensor([ms], device=device)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    if rank == 0:
+        line = {"metric": "affinity-head training frame-pairs/sec (200x200 pairs)", "value": world * B * a.steps / (ms / 1e3),
+                "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": n_warm, "ms_per_step": ms / a.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "impl": "b200", "mode": "train", "loss": float(loss),
+                "config": config_dict(a, {"differentiated_parameters": training.differentiable_parameter_names(),
+                                          "note": "BASELINE.json config 5; anchors (aug_shape/aug_dets) frozen"}),
+                "clocks": clocks, "gpu_launches": (lib.shasta_last_launch_count() + 6) * a.steps}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)
+        return
+    if a.train:
+        run_train(a)
         return
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

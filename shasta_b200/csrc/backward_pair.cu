@@ -8,7 +8,8 @@
 //                       - the gradients of every layer >= 2 of the three MLPs (weights and biases),
 //                       - dPROJ_PREV[t] = sum_d dz1, dPROJ_CUR[d] = sum_t dz1   (dz1 = d h1 * [h1 > 0]).
 //                     Layer-2 weight gradients are tile GEMMs over the 128 pairs of a tile (operands stashed in shared
-//                     memory); the small layers use warp-shuffle reductions.
+//                     memory, h1 recomputed); the small layers and biases are dot products of two stash rows, one owner
+//                     thread per output - no atomics and no shuffles on that path.
 // first_layer_bwd_kernel : dW1 = dPROJ^T [feature ; box] for fuse_shape.0 / res_coeff.0 / fuse_det.0 and their biases.
 // Gradients w.r.t. the features and boxes themselves (anchor generators, shared_conv) are not produced yet.
 #include "common.cuh"
@@ -17,7 +18,6 @@ namespace shasta {
 
 constexpr int kPbThreads = 128;   // one thread per pair of an 8 (t) x 16 (d) tile
 constexpr int kPbQStride = 148;
-constexpr int kPbDzRows = 48;     // 0..19 fuse_shape, 20..39 res_coeff (18 used), 40..47 fuse_det
 
 struct PairGrads {
   float *w2a, *b2a, *w3a, *b3a, *w4a, *b4a;   // fuse_shape.2 (20,40) .4 (10,20) .6 (1,10)
@@ -33,12 +33,49 @@ struct Gs {
   static constexpr int total = 336;
 };
 
-__device__ __forceinline__ void wred(float v, float* dst) {
-  v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) atomicAdd(dst, v);
+// row layout of the per-tile stash in shared memory ([row][128 pairs]):
+//   0..47   dz2 (0..19 fuse_shape, 20..37 res_coeff, 38..39 zero, 40..47 fuse_det)   layer-2 pre-activation gradients
+//   48..57  dz3a      58..77 a2a = relu(z2a)      78..87 a3a = relu(z3a)      88 dshape
+//   89..106 a2b       107..109 d(alpha,beta,omega)   110..117 a2c      118 dfused      119 ones
+struct St {
+  static constexpr int dz2 = 0, dz3a = 48, a2a = 58, a3a = 78, ds = 88, a2b = 89, dco = 107, a2c = 110, df = 118,
+                       ones = 119, rows = 120;
+};
+
+// which two stash rows make small-gradient output v (Gs layout): grad[v] = sum_pairs row_a * row_b
+__device__ __forceinline__ void small_rows(int v, int& ra, int& rb) {
+  rb = St::ones;
+  if (v == Gs::b4a) ra = St::ds;
+  else if (v < Gs::b3a) ra = St::ds, rb = St::a3a + (v - Gs::w4a);
+  else if (v < Gs::w3a) ra = St::dz3a + (v - Gs::b3a);
+  else if (v < Gs::b2a) ra = St::dz3a + (v - Gs::w3a) / 20, rb = St::a2a + (v - Gs::w3a) % 20;
+  else if (v < Gs::b3b) ra = St::dz2 + (v - Gs::b2a);
+  else if (v < Gs::w3b) ra = St::dco + (v - Gs::b3b);
+  else if (v < Gs::b2b) ra = St::dco + (v - Gs::w3b) / 18, rb = St::a2b + (v - Gs::w3b) % 18;
+  else if (v < Gs::b3c) ra = St::dz2 + 20 + (v - Gs::b2b);
+  else if (v == Gs::b3c) ra = St::df;
+  else if (v < Gs::b2c) ra = St::df, rb = St::a2c + (v - Gs::w3c);
+  else if (v < Gs::b2c + 8) ra = St::dz2 + 40 + (v - Gs::b2c);
+  else ra = St::ones, rb = -1;  // padding slot
 }
 
-__global__ void __launch_bounds__(kPbThreads, 1)
+// Sums over the lanes of a warp, 32 quantities at once: lane l returns sum_lanes x[l]. 31 shuffles instead of 160.
+__device__ __forceinline__ float transpose_reduce32(float (&x)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? x[i] : x[i + s];
+      const float keep = up ? x[i + s] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return x[0];
+}
+
+__global__ void __launch_bounds__(kPbThreads, 2)
 pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, const float* __restrict__ proj_prev,
                 const float* __restrict__ proj_cur_t, const float* __restrict__ aux_prev,
                 const float* __restrict__ aux_cur, const float* __restrict__ colnorm,
@@ -56,11 +93,9 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
   float* Cn = Ac + 128;                    // [16]
   float* Ws = Cn + 16;                     // pair weight block (l2a .. pair_end)
   const int wbase = (int)P.l2a, wcount = (int)(P.pair_end - P.l2a);
-  float* H1s = Ws + ((wcount + 3) / 4 * 4);     // [144][128]
-  float* DZs = H1s + kProj * 128;               // [48][128]
-  float* dPs = DZs + kPbDzRows * 128;           // [8][144]
+  float* Ss = Ws + ((wcount + 3) / 4 * 4);      // [St::rows][128] stash
+  float* dPs = Ss + St::rows * 128;             // [8][144]
   float* dQs = dPs + 8 * kProj;                 // [16][144]
-  float* gsm = dQs + 16 * kProj;                // [Gs::total]
 
   const float* W2a = Ws + (P.l2a - wbase);
   const float* B2a = Ws + (P.l2a_b - wbase);
@@ -91,8 +126,7 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
     for (int v = p; v < wcount / 4; v += kPbThreads)
       reinterpret_cast<float4*>(Ws)[v] = __ldg(reinterpret_cast<const float4*>(packed + wbase) + v);
     for (int v = p; v < 16 * kProj; v += kPbThreads) dQs[v] = 0.f;
-    for (int v = p; v < Gs::total; v += kPbThreads) gsm[v] = 0.f;
-    for (int v = p; v < kPbDzRows * 128; v += kPbThreads) DZs[v] = 0.f;   // padding rows stay zero
+    for (int v = p; v < St::rows * 128; v += kPbThreads) Ss[v] = (v >= St::ones * 128) ? 1.f : 0.f;  // pad rows stay 0
   }
   // pass-B ownership: up to two 4x4 output tiles of the layer-2 weight gradients per thread
   // tiles 0..49 fuse_shape (5 j-groups x 10 k-groups), 50..139 res_coeff (5 x 18), 140..155 fuse_det (2 x 8)
@@ -112,8 +146,14 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
   for (int u = 0; u < 2; ++u)
 #pragma unroll
     for (int e = 0; e < 16; ++e) wacc[u][e] = 0.f;
+  // small-gradient ownership: outputs p, p+128, p+256 of the Gs layout
+  int sra[3], srb[3];
+  float sacc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int u = 0; u < 3; ++u) small_rows(min(p + u * kPbThreads, Gs::total - 1), sra[u], srb[u]);
   __syncthreads();
 
+  const float* qrow = Qs + di * kPbQStride;
   const int ntt = (T + 7) / 8;
   for (int tt = 0; tt < ntt; ++tt) {
     const int t0 = tt * 8;
@@ -132,18 +172,16 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
     const int t = t0 + ti, d = d0 + di;
     const bool valid = (t < T) && (d < D);
     const float gr = valid ? dres[((size_t)b * T + t) * RS + d] : 0.f;
+    const float* prow = Ps + ti * kProj;
 
-    // ================= pass A: one thread = one pair =================
-    // h1 (stashed for the layer-2 weight gradients)
-    for (int k = 0; k < kProj; ++k) H1s[k * 128 + p] = fmaxf(Ps[ti * kProj + k] + Qs[di * kPbQStride + k], 0.f);
-
+    // ================= pass A: one thread = one pair; h1[k] = relu(prow[k] + qrow[k]) is recomputed on the fly ======
     // ---- fuse_shape forward: 40 -> 20 -> 10 -> 1
     float z2a[20];
 #pragma unroll
     for (int j = 0; j < 20; ++j) z2a[j] = B2a[j];
 #pragma unroll 2
     for (int k = 0; k < 40; ++k) {
-      const float h = H1s[k * 128 + p];
+      const float h = fmaxf(prow[k] + qrow[k], 0.f);
 #pragma unroll
       for (int j4 = 0; j4 < 5; ++j4) {
         const float4 w = *reinterpret_cast<const float4*>(W2a + k * 20 + j4 * 4);
@@ -172,7 +210,7 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
     for (int j = 0; j < 18; ++j) z2b[j] = B2b[j];
 #pragma unroll 2
     for (int k = 0; k < 72; ++k) {
-      const float h = H1s[(40 + k) * 128 + p];
+      const float h = fmaxf(prow[40 + k] + qrow[40 + k], 0.f);
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) {
         const float4 w = *reinterpret_cast<const float4*>(W2b + k * 20 + j4 * 4);
@@ -200,7 +238,7 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
     for (int j = 0; j < 8; ++j) z2c[j] = B2c[j];
 #pragma unroll 2
     for (int k = 0; k < 32; ++k) {
-      const float h = H1s[(112 + k) * 128 + p];
+      const float h = fmaxf(prow[112 + k] + qrow[112 + k], 0.f);
       const float4 w0 = *reinterpret_cast<const float4*>(W2c + k * 8);
       const float4 w1 = *reinterpret_cast<const float4*>(W2c + k * 8 + 4);
       z2c[0] = fmaf(h, w0.x, z2c[0]), z2c[1] = fmaf(h, w0.y, z2c[1]);
@@ -227,141 +265,181 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
       res_dist = dist + dim + sqrtf(dc * dc + ds * ds);
     }
 
-    // ================= backward =================
+    // ================= backward: per-pair quantities go to the stash, reductions over pairs happen in pass B =========
     const float dshape = gr * omega, dfused = gr * alpha;
-    const float dco[3] = {gr * fused, gr * res_dist, gr * shape};
-
-    // fuse_shape.6 / .4
-    wred(dshape, gsm + Gs::b4a);
+    Ss[St::ds * 128 + p] = dshape;
+    Ss[St::df * 128 + p] = dfused;
+    Ss[(St::dco + 0) * 128 + p] = gr * fused;
+    Ss[(St::dco + 1) * 128 + p] = gr * res_dist;
+    Ss[(St::dco + 2) * 128 + p] = gr * shape;
     float dz3a[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-      wred(dshape * fmaxf(z3a[i], 0.f), gsm + Gs::w4a + i);
+      Ss[(St::a3a + i) * 128 + p] = fmaxf(z3a[i], 0.f);
       dz3a[i] = (z3a[i] > 0.f) ? dshape * W4a[i] : 0.f;
-      wred(dz3a[i], gsm + Gs::b3a + i);
+      Ss[(St::dz3a + i) * 128 + p] = dz3a[i];
     }
     float dz2a[20];
 #pragma unroll
     for (int j = 0; j < 20; ++j) {
-      const float a = fmaxf(z2a[j], 0.f);
       float da = 0.f;
 #pragma unroll
-      for (int i = 0; i < 10; ++i) {
-        wred(dz3a[i] * a, gsm + Gs::w3a + i * 20 + j);     // fuse_shape.4.weight is (10,20)
-        da = fmaf(dz3a[i], W3a[j * 12 + i], da);
-      }
+      for (int i = 0; i < 10; ++i) da = fmaf(dz3a[i], W3a[j * 12 + i], da);
       dz2a[j] = (z2a[j] > 0.f) ? da : 0.f;
-      wred(dz2a[j], gsm + Gs::b2a + j);
-      DZs[j * 128 + p] = dz2a[j];
+      Ss[(St::a2a + j) * 128 + p] = fmaxf(z2a[j], 0.f);
+      Ss[(St::dz2 + j) * 128 + p] = dz2a[j];
     }
-    // res_coeff.4
     float dz2b[18];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) wred(dco[c], gsm + Gs::b3b + c);
-#pragma unroll
     for (int j = 0; j < 18; ++j) {
-      const float a = fmaxf(z2b[j], 0.f);
-      float da = 0.f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        wred(dco[c] * a, gsm + Gs::w3b + c * 18 + j);      // res_coeff.4.weight is (3,18)
-        da = fmaf(dco[c], W3b[j * 4 + c], da);
-      }
+      float da = gr * fused * W3b[j * 4 + 0];
+      da = fmaf(gr * res_dist, W3b[j * 4 + 1], da);
+      da = fmaf(gr * shape, W3b[j * 4 + 2], da);
       dz2b[j] = (z2b[j] > 0.f) ? da : 0.f;
-      wred(dz2b[j], gsm + Gs::b2b + j);
-      DZs[(20 + j) * 128 + p] = dz2b[j];
+      Ss[(St::a2b + j) * 128 + p] = fmaxf(z2b[j], 0.f);
+      Ss[(St::dz2 + 20 + j) * 128 + p] = dz2b[j];
     }
-    // fuse_det.4
     float dz2c[8];
-    wred(dfused, gsm + Gs::b3c);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      wred(dfused * fmaxf(z2c[j], 0.f), gsm + Gs::w3c + j);
       dz2c[j] = (z2c[j] > 0.f) ? dfused * W3c[j] : 0.f;
-      wred(dz2c[j], gsm + Gs::b2c + j);
-      DZs[(40 + j) * 128 + p] = dz2c[j];
+      Ss[(St::a2c + j) * 128 + p] = fmaxf(z2c[j], 0.f);
+      Ss[(St::dz2 + 40 + j) * 128 + p] = dz2c[j];
     }
 
-    // d h1 -> dz1 -> tile sums for dPROJ_PREV (over d) and dPROJ_CUR (over t)
-    auto scatter = [&](int k, float dh) {
-      float dz1 = (H1s[k * 128 + p] > 0.f) ? dh : 0.f;
-      // over the 8 t of the tile: lanes l and l^16 hold the same d; 4 warps add through shared memory
-      const float sq = dz1 + __shfl_xor_sync(0xffffffffu, dz1, 16);
-      if (lane < 16) atomicAdd(dQs + di * kProj + k, sq);
-      // over the 16 d of the tile: butterfly inside each half warp, one owner per (t,k)
-      float sp = dz1;
-      sp += __shfl_xor_sync(0xffffffffu, sp, 8);
-      sp += __shfl_xor_sync(0xffffffffu, sp, 4);
-      sp += __shfl_xor_sync(0xffffffffu, sp, 2);
-      sp += __shfl_xor_sync(0xffffffffu, sp, 1);
-      if (di == 0) dPs[ti * kProj + k] += sp;
+    // d h1 -> dz1 -> tile sums for dPROJ_PREV (over the 16 d) and dPROJ_CUR (over the 8 t), 16 k at a time:
+    // half-warp butterfly for the d sums, one xor-16 exchange + 4-warp shared-memory add for the t sums
+    auto scatter16 = [&](int kbase, float (&dz1)[16], int nvalid) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float sq = dz1[e] + __shfl_xor_sync(0xffffffffu, dz1[e], 16);
+        if (lane < 16 && e < nvalid) atomicAdd(dQs + di * kProj + kbase + e, sq);
+      }
+#pragma unroll
+      for (int s = 8; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+          const float send = up ? dz1[i] : dz1[i + s];
+          const float keep = up ? dz1[i + s] : dz1[i];
+          dz1[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+      if (di < nvalid) dPs[ti * kProj + kbase + di] += dz1[0];   // lane di of the half warp owns k = kbase + di
     };
-#pragma unroll 2
-    for (int k = 0; k < 40; ++k) {
-      float dh = 0.f;
+    // fuse_shape block: k 0..39 (two groups of 16 + one of 8 padded)
+#pragma unroll 1
+    for (int kb = 0; kb < 48; kb += 16) {
+      float dz1[16];
 #pragma unroll
-      for (int j4 = 0; j4 < 5; ++j4) {
-        const float4 w = *reinterpret_cast<const float4*>(W2a + k * 20 + j4 * 4);
-        dh = fmaf(dz2a[j4 * 4 + 0], w.x, dh), dh = fmaf(dz2a[j4 * 4 + 1], w.y, dh);
-        dh = fmaf(dz2a[j4 * 4 + 2], w.z, dh), dh = fmaf(dz2a[j4 * 4 + 3], w.w, dh);
-      }
-      scatter(k, dh);
-    }
-#pragma unroll 2
-    for (int k = 0; k < 72; ++k) {
-      float dh = 0.f;
+      for (int e = 0; e < 16; ++e) {
+        const int k = kb + e;
+        float dh = 0.f;
+        if (k < 40) {
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        const float4 w = *reinterpret_cast<const float4*>(W2b + k * 20 + j4 * 4);
-        dh = fmaf(dz2b[j4 * 4 + 0], w.x, dh), dh = fmaf(dz2b[j4 * 4 + 1], w.y, dh);
-        dh = fmaf(dz2b[j4 * 4 + 2], w.z, dh), dh = fmaf(dz2b[j4 * 4 + 3], w.w, dh);
+          for (int j4 = 0; j4 < 5; ++j4) {
+            const float4 w = *reinterpret_cast<const float4*>(W2a + k * 20 + j4 * 4);
+            dh = fmaf(dz2a[j4 * 4 + 0], w.x, dh), dh = fmaf(dz2a[j4 * 4 + 1], w.y, dh);
+            dh = fmaf(dz2a[j4 * 4 + 2], w.z, dh), dh = fmaf(dz2a[j4 * 4 + 3], w.w, dh);
+          }
+          dh = (prow[k] + qrow[k] > 0.f) ? dh : 0.f;
+        }
+        dz1[e] = dh;
       }
-      const float2 w2 = *reinterpret_cast<const float2*>(W2b + k * 20 + 16);
-      dh = fmaf(dz2b[16], w2.x, dh), dh = fmaf(dz2b[17], w2.y, dh);
-      scatter(40 + k, dh);
+      scatter16(kb, dz1, min(16, 40 - kb));   // the last group has 8 real columns
     }
-#pragma unroll 2
-    for (int k = 0; k < 32; ++k) {
-      const float4 w0 = *reinterpret_cast<const float4*>(W2c + k * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(W2c + k * 8 + 4);
-      float dh = dz2c[0] * w0.x;
-      dh = fmaf(dz2c[1], w0.y, dh), dh = fmaf(dz2c[2], w0.z, dh), dh = fmaf(dz2c[3], w0.w, dh);
-      dh = fmaf(dz2c[4], w1.x, dh), dh = fmaf(dz2c[5], w1.y, dh), dh = fmaf(dz2c[6], w1.z, dh);
-      dh = fmaf(dz2c[7], w1.w, dh);
-      scatter(112 + k, dh);
+    // res_coeff block: k 40..111
+#pragma unroll 1
+    for (int kb = 0; kb < 80; kb += 16) {
+      float dz1[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int k = kb + e;
+        float dh = 0.f;
+        if (k < 72) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 w = *reinterpret_cast<const float4*>(W2b + k * 20 + j4 * 4);
+            dh = fmaf(dz2b[j4 * 4 + 0], w.x, dh), dh = fmaf(dz2b[j4 * 4 + 1], w.y, dh);
+            dh = fmaf(dz2b[j4 * 4 + 2], w.z, dh), dh = fmaf(dz2b[j4 * 4 + 3], w.w, dh);
+          }
+          const float2 w2 = *reinterpret_cast<const float2*>(W2b + k * 20 + 16);
+          dh = fmaf(dz2b[16], w2.x, dh), dh = fmaf(dz2b[17], w2.y, dh);
+          dh = (prow[40 + k] + qrow[40 + k] > 0.f) ? dh : 0.f;
+        }
+        dz1[e] = dh;
+      }
+      scatter16(40 + kb, dz1, min(16, 72 - kb));
     }
-    __syncthreads();   // H1s / DZs / dPs complete
+    // fuse_det block: k 112..143
+#pragma unroll 1
+    for (int kb = 0; kb < 32; kb += 16) {
+      float dz1[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int k = kb + e;
+        const float4 w0 = *reinterpret_cast<const float4*>(W2c + k * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(W2c + k * 8 + 4);
+        float dh = dz2c[0] * w0.x;
+        dh = fmaf(dz2c[1], w0.y, dh), dh = fmaf(dz2c[2], w0.z, dh), dh = fmaf(dz2c[3], w0.w, dh);
+        dh = fmaf(dz2c[4], w1.x, dh), dh = fmaf(dz2c[5], w1.y, dh), dh = fmaf(dz2c[6], w1.z, dh);
+        dh = fmaf(dz2c[7], w1.w, dh);
+        dz1[e] = (prow[112 + k] + qrow[112 + k] > 0.f) ? dh : 0.f;
+      }
+      scatter16(112 + kb, dz1, 16);
+    }
+    __syncthreads();   // stash / dPs complete
 
-    // ================= pass B: layer-2 weight gradients, dW2[j][k] += sum_pairs dz2[j] h1[k] =================
+    // ================= pass B: reductions over the 128 pairs of the tile =================
+    // (1) layer-2 weight gradients dW2[j][k] += sum_pairs dz2[j] h1[k]; h1 is recomputed from the staged projections
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (!tv[u]) continue;
-      const float* dzr = DZs + tj[u] * 128;
-      const float* hr = H1s + tk[u] * 128;
+      const float* dzr = Ss + (St::dz2 + tj[u]) * 128;
+      const int k0 = tk[u];
 #pragma unroll 2
       for (int q = 0; q < 128; q += 4) {
-        float4 dv[4], hv[4];
+        const float4 pv = *reinterpret_cast<const float4*>(Ps + (q >> 4) * kProj + k0);
+        float hq[4][4];   // [pair in group][k]
 #pragma unroll
-        for (int a = 0; a < 4; ++a) dv[a] = *reinterpret_cast<const float4*>(dzr + a * 128 + q);
+        for (int e = 0; e < 4; ++e) {
+          const float4 qv = *reinterpret_cast<const float4*>(Qs + ((q & 15) + e) * kPbQStride + k0);
+          hq[e][0] = fmaxf(pv.x + qv.x, 0.f), hq[e][1] = fmaxf(pv.y + qv.y, 0.f);
+          hq[e][2] = fmaxf(pv.z + qv.z, 0.f), hq[e][3] = fmaxf(pv.w + qv.w, 0.f);
+        }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) hv[c] = *reinterpret_cast<const float4*>(hr + c * 128 + q);
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a) {
+          const float4 dv = *reinterpret_cast<const float4*>(dzr + a * 128 + q);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float s = wacc[u][a * 4 + c];
-            s = fmaf(dv[a].x, hv[c].x, s), s = fmaf(dv[a].y, hv[c].y, s);
-            s = fmaf(dv[a].z, hv[c].z, s), s = fmaf(dv[a].w, hv[c].w, s);
+            s = fmaf(dv.x, hq[0][c], s), s = fmaf(dv.y, hq[1][c], s);
+            s = fmaf(dv.z, hq[2][c], s), s = fmaf(dv.w, hq[3][c], s);
             wacc[u][a * 4 + c] = s;
           }
+        }
       }
+    }
+    // (2) small layers and biases: one owner thread per output, dot product of two stash rows
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      if (srb[u] < 0) continue;
+      const float4* ra = reinterpret_cast<const float4*>(Ss + sra[u] * 128);
+      const float4* rb = reinterpret_cast<const float4*>(Ss + srb[u] * 128);
+      float s = sacc[u];
+#pragma unroll 8
+      for (int q = 0; q < 32; ++q) {
+        const float4 x = ra[q], y = rb[q];
+        s = fmaf(x.x, y.x, s), s = fmaf(x.y, y.y, s), s = fmaf(x.z, y.z, s), s = fmaf(x.w, y.w, s);
+      }
+      sacc[u] = s;
     }
     // dPROJ_PREV of this tile's 8 rows: other CTAs (other d blocks) add to the same rows
     for (int v = p; v < 8 * kProj; v += kPbThreads) {
       const int tr = v / kProj;
       if (t0 + tr < T) atomicAdd(dproj_prev + ((size_t)b * T + t0 + tr) * kProj + (v % kProj), dPs[v]);
     }
-    __syncthreads();   // before the next tile overwrites the stashes
+    __syncthreads();   // before the next tile overwrites the stash
   }
 
   // ---- CTA epilogue: dPROJ_CUR rows are owned by this CTA; weight gradients go out with atomics ----
@@ -387,8 +465,11 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
         }
       }
   }
-  for (int v = p; v < Gs::total; v += kPbThreads) {
-    const float x = gsm[v];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int v = p + u * kPbThreads;
+    if (v >= Gs::total || srb[u] < 0) continue;
+    const float x = sacc[u];
     float* dst = nullptr;
     if (v == Gs::b4a) dst = g.b4a;
     else if (v < Gs::b3a) dst = g.w4a + (v - Gs::w4a);
@@ -512,7 +593,7 @@ int launch_backward_pair(const shasta_grads_t& gr, const float* packed, int B, i
   g.w2c = gr.fuse_det_w[1], g.b2c = gr.fuse_det_b[1], g.w3c = gr.fuse_det_w[2], g.b3c = gr.fuse_det_b[2];
   const int wcount = (int)(P.pair_end - P.l2a);
   const size_t smem = sizeof(float) * (8 * kProj + 16 * kPbQStride + 64 + 128 + 16 + (wcount + 3) / 4 * 4 +
-                                       kProj * 128 + kPbDzRows * 128 + 8 * kProj + 16 * kProj + Gs::total);
+                                       St::rows * 128 + 8 * kProj + 16 * kProj);
   static bool configured = false;
   if (!configured) {
     SHASTA_CUDA(cudaFuncSetAttribute(pair_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
