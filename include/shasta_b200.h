@@ -123,7 +123,10 @@ enum shasta_region {
   SHASTA_WS_PROJ_CUR_T = 13,
   SHASTA_WS_DPROJ_PREV = 14, /* (B,T,144) gradients of the first-layer projections (backward pass only) */
   SHASTA_WS_DPROJ_CUR = 15,
-  SHASTA_WS_NUM_REGIONS = 16
+  SHASTA_WS_ANCH_H = 16,  /* (B,4,5M) recomputed hidden activations of aug_shape.i   (backward pass only) */
+  SHASTA_WS_ANCH_DY = 17, /* (B,4,320) gradients at the outputs of aug_shape.i.2 */
+  SHASTA_WS_ANCH_DZ = 18, /* (B,4,5M) gradients at the pre-activations of aug_shape.i.0 */
+  SHASTA_WS_NUM_REGIONS = 19
 };
 
 /* Runtime options (process-wide, not thread-safe; meant for tests and benchmarks).
@@ -213,9 +216,11 @@ SHASTA_API int shasta_forward_f32(const shasta_params_t* host_params, const floa
  *   aff.*    gradients and d residual                                   (shasta.py:323)
  *   fuse_shape.*, res_coeff.*, fuse_det.* gradients (all layers, incl. the decomposed first ones) and the
  *            gradients of the per-object projections                    (shasta.py:286-319)
- * and accumulates into the non-NULL entries of `host_grads` (the aff group and the pairwise group must each be given
- * completely or not at all). aug_shape.* / aug_dets.* (anchor generators) are not differentiated yet: those entries are
- * ignored.
+ *   aug_shape.* gradients (the four anchor shape generators, 99 % of the parameters)   (shasta.py:241-247)
+ * The aff group, the pairwise group (fuse_shape / fuse_det / res_coeff) and the aug_shape group must each be given
+ * completely or not at all; aug_shape needs the pairwise group. aff and pairwise gradients are ACCUMULATED (+=) into
+ * the caller's buffers, aug_shape gradients are ASSIGNED (their 1 GB need not be zeroed first). aug_dets.* (anchor box
+ * generators) are not differentiated yet: those entries are ignored.
  * The workspace regions LOGITS / RESIDUAL are overwritten with dlogits / d residual. */
 SHASTA_API int shasta_backward_f32(const shasta_params_t* host_params, const shasta_grads_t* host_grads,
                                    const float* packed, int batch, float* workspace, size_t workspace_bytes,

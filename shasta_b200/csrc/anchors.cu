@@ -276,6 +276,13 @@ int anchor_tc_splits(int M, int B);  // anchors_tc.cu
 int launch_anchor_hidden_tc(const shasta_params_t& p, const float* feat_cur, const float* feat_prev, int B, int S,
                             float* part, cudaStream_t s);
 
+int anchor_splits_in_use(int M, int B) {
+  const int mode = g_options[SHASTA_OPT_ANCHOR_PATH];
+  if (mode == 2 || (mode == 0 && B > 8)) return anchor_tc2_splits(M, B);
+  if (mode == 3) return anchor_tc_splits(M, B);
+  return hidden_splits(M);
+}
+
 int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
                    const WsLayout& L, cudaStream_t s, cudaEvent_t mid) {
   const int M = p.max_obj;

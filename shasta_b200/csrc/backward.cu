@@ -214,6 +214,10 @@ int launch_backward(const shasta_params_t& p, const shasta_grads_t& g, const flo
   if (g.fuse_shape_w[0] != nullptr) {
     int rc = launch_backward_pair(g, packed, B, M, ws, L, s);
     if (rc) return rc;
+    if (g.aug_shape_w0[0] != nullptr) {
+      rc = launch_backward_anchor(p, g, B, anchor_splits_in_use(M, B), ws, L, s);
+      if (rc) return rc;
+    }
   }
   return 0;
 }

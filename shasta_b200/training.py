@@ -6,9 +6,10 @@ inference; ``torch.autograd`` only sees one node whose backward calls ``shasta_b
 dual-softmax backward, the aff row-MLP backward, the pairwise-MLP backward and the first-layer weight gradients.
 
 Gradient coverage of this revision: ``aff.*``, ``fuse_shape.*``, ``res_coeff.*``, ``fuse_det.*`` (the pairwise MLPs
-incl. their decomposed first layers) — BASELINE.json config 5's "forward + backward of the pairwise MLP and the
-softmax". The anchor generators (``aug_shape.*``, ``aug_dets.*``) and ``shared_conv`` are not differentiated yet (their
-parameters receive no gradient, like the frozen trunk); DESIGN.md §7 tracks it.
+incl. their decomposed first layers) and ``aug_shape.*`` (the anchor shape generators, 99 % of the parameters).
+``aug_dets.*`` (anchor boxes: needs the backward of the hand-designed residual incl. F.normalize) and ``shared_conv``
+(needs the gather's scatter-add) are not differentiated yet; their parameters receive no gradient, like the frozen
+trunk. DESIGN.md §7 tracks it.
 """
 import ctypes
 
@@ -22,17 +23,22 @@ GROUPS = (("aff", AFF_LAYERS), ("fuse_shape", (0, 2, 4, 6)), ("fuse_det", (0, 2,
 
 def differentiable_parameters(model):
     """Parameters that receive gradients from the CUDA backward, in the order the autograd node expects them:
-    aff.*, fuse_shape.*, fuse_det.*, res_coeff.* (weight, bias per layer)."""
+    aff.*, fuse_shape.*, fuse_det.*, res_coeff.* (weight, bias per layer), then aug_shape.{0..3}.{0,2}."""
     out = []
     for name, layers in GROUPS:
         seq = getattr(model, name)
         for li in layers:
             out += [seq[li].weight, seq[li].bias]
+    for i in range(4):
+        for li in (0, 2):
+            out += [model.aug_shape[i][li].weight, model.aug_shape[i][li].bias]
     return out
 
 
 def differentiable_parameter_names():
-    return ["%s.%d.%s" % (name, li, k) for name, layers in GROUPS for li in layers for k in ("weight", "bias")]
+    names = ["%s.%d.%s" % (name, li, k) for name, layers in GROUPS for li in layers for k in ("weight", "bias")]
+    names += ["aug_shape.%d.%d.%s" % (i, li, k) for i in range(4) for li in (0, 2) for k in ("weight", "bias")]
+    return names
 
 
 class _AffinityFunction(torch.autograd.Function):
@@ -54,7 +60,10 @@ class _AffinityFunction(torch.autograd.Function):
         gm2 = torch.zeros_like(m2) if gm2 is None else gm2.contiguous().float()
         lib = _cabi.lib()
         params = differentiable_parameters(model)
-        grads = [torch.zeros_like(p) for p in params]
+        n_small = 2 * sum(len(layers) for _, layers in GROUPS)
+        # aff / pairwise gradients are accumulated by the kernels (zero-initialised here); the aug_shape gradients
+        # (1 GB at M = 200) are assigned by the kernels, so they are allocated uninitialised
+        grads = [torch.zeros_like(p) for p in params[:n_small]] + [torch.empty_like(p) for p in params[n_small:]]
         g = _cabi.ShastaGrads()
         it = iter(grads)
         for name, layers in GROUPS:
@@ -62,6 +71,11 @@ class _AffinityFunction(torch.autograd.Function):
             for n in range(len(layers)):
                 gw[n] = next(it).data_ptr()
                 gb[n] = next(it).data_ptr()
+        for i in range(4):
+            g.aug_shape_w0[i] = next(it).data_ptr()
+            g.aug_shape_b0[i] = next(it).data_ptr()
+            g.aug_shape_w2[i] = next(it).data_ptr()
+            g.aug_shape_b2[i] = next(it).data_ptr()
         device = m1.device
         with torch.cuda.device(device):
             rc = lib.shasta_backward_f32(

@@ -66,7 +66,7 @@ def test_gradients_match_autograd_through_oracle(name):
         print("%-22s grad max err / scale = %.3g (scale %.3g)" % (n, err, scale))
         assert err < 2e-3, "%s: grad max err / scale = %g" % (n, err)
     # parameters outside the differentiated set get no gradient in this revision
-    assert sd["aug_shape.0.0.weight"].grad is None
+    assert sd["aug_dets.0.0.weight"].grad is None
 
 
 def test_training_steps_lower_the_loss():
