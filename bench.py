@@ -363,7 +363,7 @@ def run_train(a):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "impl": "b200", "mode": "train", "loss": float(loss),
                 "config": config_dict(a, {"differentiated_parameters": training.differentiable_parameter_names(),
-                                          "note": "BASELINE.json config 5; anchors (aug_shape/aug_dets) frozen"}),
+                                          "note": "BASELINE.json config 5: every head parameter trained (258 M), shared_conv / trunk frozen"}),
                 "clocks": clocks, "gpu_launches": (lib.shasta_last_launch_count() + 6) * a.steps}
         print(json.dumps(line))
     if dist is not None:

@@ -126,7 +126,9 @@ enum shasta_region {
   SHASTA_WS_ANCH_H = 16,  /* (B,4,5M) recomputed hidden activations of aug_shape.i   (backward pass only) */
   SHASTA_WS_ANCH_DY = 17, /* (B,4,320) gradients at the outputs of aug_shape.i.2 */
   SHASTA_WS_ANCH_DZ = 18, /* (B,4,5M) gradients at the pre-activations of aug_shape.i.0 */
-  SHASTA_WS_NUM_REGIONS = 19
+  SHASTA_WS_RAW_XY = 19,  /* (B,M,2) x,y of the current boxes before back-projection (inputs of aug_dets.0/1) */
+  SHASTA_WS_BOX_BWD = 20, /* scratch of the anchor-box backward: (B,4,8) d box, (B,4,8) dy, 2 x (B,4,7M/32), (B,4,7M) */
+  SHASTA_WS_NUM_REGIONS = 21
 };
 
 /* Runtime options (process-wide, not thread-safe; meant for tests and benchmarks).
@@ -219,8 +221,10 @@ SHASTA_API int shasta_forward_f32(const shasta_params_t* host_params, const floa
  *   aug_shape.* gradients (the four anchor shape generators, 99 % of the parameters)   (shasta.py:241-247)
  * The aff group, the pairwise group (fuse_shape / fuse_det / res_coeff) and the aug_shape group must each be given
  * completely or not at all; aug_shape needs the pairwise group. aff and pairwise gradients are ACCUMULATED (+=) into
- * the caller's buffers, aug_shape gradients are ASSIGNED (their 1 GB need not be zeroed first). aug_dets.* (anchor box
- * generators) are not differentiated yet: those entries are ignored.
+ * the caller's buffers, aug_shape and aug_dets gradients are ASSIGNED (1 GB at M = 200 need not be zeroed first).
+ *   aug_dets.* gradients (the four anchor box generators) through the first-layer box columns and the hand-designed
+ *            residual incl. the F.normalize backward                                    (shasta.py:260-283)
+ * The aug_dets group needs the pairwise group as well.
  * The workspace regions LOGITS / RESIDUAL are overwritten with dlogits / d residual. */
 SHASTA_API int shasta_backward_f32(const shasta_params_t* host_params, const shasta_grads_t* host_grads,
                                    const float* packed, int batch, float* workspace, size_t workspace_bytes,

@@ -58,7 +58,7 @@ class ShastaGeom(ctypes.Structure):
 # region ids (enum shasta_region)
 WS_FEAT_CUR, WS_FEAT_PREV, WS_BOX_CUR, WS_BOX_PREV, WS_HIDDEN_PART, WS_PROJ_PREV, WS_PROJ_CUR, WS_AUX_PREV, \
     WS_AUX_CUR, WS_COLNORM, WS_RESIDUAL, WS_LOGITS, WS_ANCHOR_BOX, WS_PROJ_CUR_T, WS_DPROJ_PREV, WS_DPROJ_CUR, WS_ANCH_H, \
-    WS_ANCH_DY, WS_ANCH_DZ = range(19)
+    WS_ANCH_DY, WS_ANCH_DZ, WS_RAW_XY, WS_BOX_BWD = range(21)
 
 OPT_ANCHOR_PATH = 0
 OPT_TC_RAW_HI = 1

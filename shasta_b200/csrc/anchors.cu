@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256)
 anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, const float* __restrict__ det_boxes,
                      const float* __restrict__ prev_boxes, int B, int M, float* __restrict__ feat_cur,
                      float* __restrict__ feat_prev, float* __restrict__ box_cur, float* __restrict__ box_prev,
-                     float* __restrict__ anchor_box, int nbx) {
+                     float* __restrict__ anchor_box, int nbx, float* __restrict__ raw_xy) {
   extern __shared__ __align__(16) float sm[];
   const int T = M + 2, N5 = 5 * M, H7 = (7 * M) / 32;
   const int role = blockIdx.x;
@@ -144,6 +144,8 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
       float* oc = box_cur + ((size_t)b * T + m) * 8;
       float* op = box_prev + ((size_t)b * T + m) * 8;
       const float dt = d[9];
+      raw_xy[((size_t)b * M + m) * 2 + 0] = d[0];   // kept for the backward pass (aug_dets reads the raw boxes)
+      raw_xy[((size_t)b * M + m) * 2 + 1] = d[1];
       oc[0] = __fsub_rn(d[0], __fmul_rn(d[7], dt));
       oc[1] = __fsub_rn(d[1], __fmul_rn(d[8], dt));
 #pragma unroll
@@ -354,10 +356,10 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   float* ab = ws + L.off[SHASTA_WS_ANCHOR_BOX];
   if (BG == 8)
     anchor_finish_kernel<8><<<fgrid, 256, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev, bc,
-                                                     bp, ab, nbx);
+                                                     bp, ab, nbx, ws + L.off[SHASTA_WS_RAW_XY]);
   else
     anchor_finish_kernel<4><<<fgrid, 256, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev, bc,
-                                                     bp, ab, nbx);
+                                                     bp, ab, nbx, ws + L.off[SHASTA_WS_RAW_XY]);
   SHASTA_CHECK_LAUNCH("anchor_finish_kernel");
   return 0;
 }

@@ -347,6 +347,14 @@ int shasta_backward_f32(const shasta_params_t* host_params, const shasta_grads_t
       set_error("aug_shape gradients must be given completely (and together with the pairwise group) or not at all");
       return SHASTA_ERR_ARG;
     }
+    given = 0;
+    for (int i = 0; i < 4; ++i)
+      given += (host_grads->aug_dets_w0[i] != nullptr) + (host_grads->aug_dets_b0[i] != nullptr) +
+               (host_grads->aug_dets_w2[i] != nullptr) + (host_grads->aug_dets_b2[i] != nullptr);
+    if (given != 0 && (given != 16 || host_grads->fuse_shape_w[0] == nullptr)) {
+      set_error("aug_dets gradients must be given completely (and together with the pairwise group) or not at all");
+      return SHASTA_ERR_ARG;
+    }
   }
   if (batch == 0) return 0;
   return launch_backward(*host_params, *host_grads, packed, batch, workspace, ws_layout(batch, M), matched1, matched2,

@@ -218,6 +218,10 @@ int launch_backward(const shasta_params_t& p, const shasta_grads_t& g, const flo
       rc = launch_backward_anchor(p, g, B, anchor_splits_in_use(M, B), ws, L, s);
       if (rc) return rc;
     }
+    if (g.aug_dets_w0[0] != nullptr) {
+      rc = launch_backward_box(p, g, B, ws, L, s);
+      if (rc) return rc;
+    }
   }
   return 0;
 }

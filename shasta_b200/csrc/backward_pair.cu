@@ -80,7 +80,7 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
                 const float* __restrict__ proj_cur_t, const float* __restrict__ aux_prev,
                 const float* __restrict__ aux_cur, const float* __restrict__ colnorm,
                 const float* __restrict__ dres, PairGrads g, float* __restrict__ dproj_prev,
-                float* __restrict__ dproj_cur) {
+                float* __restrict__ dproj_cur, float* __restrict__ ddist) {
   extern __shared__ __align__(16) float sm[];
   const int T = M + 2, D = M + 2, RS = row_stride(M);
   const int b = blockIdx.y, d0 = blockIdx.x * 16;
@@ -267,6 +267,7 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
 
     // ================= backward: per-pair quantities go to the stash, reductions over pairs happen in pass B =========
     const float dshape = gr * omega, dfused = gr * alpha;
+    if (valid && ddist != nullptr) ddist[((size_t)b * T + t) * RS + d] = gr * beta;   // d residual_dist (anchor boxes)
     Ss[St::ds * 128 + p] = dshape;
     Ss[St::df * 128 + p] = dfused;
     Ss[(St::dco + 0) * 128 + p] = gr * fused;
@@ -603,7 +604,8 @@ int launch_backward_pair(const shasta_grads_t& gr, const float* packed, int B, i
   pair_bwd_kernel<<<grid, kPbThreads, smem, s>>>(packed, P, B, M, ws + L.off[SHASTA_WS_PROJ_PREV],
                                                  ws + L.off[SHASTA_WS_PROJ_CUR_T], ws + L.off[SHASTA_WS_AUX_PREV],
                                                  ws + L.off[SHASTA_WS_AUX_CUR], ws + L.off[SHASTA_WS_COLNORM],
-                                                 ws + L.off[SHASTA_WS_RESIDUAL], g, dpp, dpc);
+                                                 ws + L.off[SHASTA_WS_RESIDUAL], g, dpp, dpc,
+                                                 ws + L.off[SHASTA_WS_LOGITS]);  // dlogits is dead by now
   SHASTA_CHECK_LAUNCH("pair_bwd_kernel");
 
   FirstGrads fg;

@@ -53,6 +53,8 @@ __host__ inline WsLayout ws_layout(int B, int M) {
   sz[SHASTA_WS_ANCH_H] = (size_t)B * 4 * 5 * M;
   sz[SHASTA_WS_ANCH_DY] = (size_t)B * 4 * kF;
   sz[SHASTA_WS_ANCH_DZ] = (size_t)B * 4 * 5 * M;
+  sz[SHASTA_WS_RAW_XY] = (size_t)B * M * 2;
+  sz[SHASTA_WS_BOX_BWD] = (size_t)B * 4 * (16 + 2 * (size_t)((7 * M) / 32 + 1) + 7 * (size_t)M);
   size_t o = 0;
   for (int i = 0; i < SHASTA_WS_NUM_REGIONS; ++i) {
     L.off[i] = o;
@@ -208,6 +210,8 @@ int launch_backward_pair(const shasta_grads_t& g, const float* packed, int B, in
                          cudaStream_t s);
 int launch_backward_anchor(const shasta_params_t& p, const shasta_grads_t& g, int B, int S, float* ws,
                            const WsLayout& L, cudaStream_t s);
+int launch_backward_box(const shasta_params_t& p, const shasta_grads_t& g, int B, float* ws, const WsLayout& L,
+                        cudaStream_t s);
 int anchor_splits_in_use(int M, int B);  // split-K count the forward anchors kernel uses for this (M, B)
 int launch_decode(const float* m1, const float* m2, const int32_t* n_prev, const int32_t* n_det, int B, int M,
                   int32_t* prev_state, int32_t* prev_argmax, float* fn_score, int32_t* det_state,

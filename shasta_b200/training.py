@@ -6,10 +6,10 @@ inference; ``torch.autograd`` only sees one node whose backward calls ``shasta_b
 dual-softmax backward, the aff row-MLP backward, the pairwise-MLP backward and the first-layer weight gradients.
 
 Gradient coverage of this revision: ``aff.*``, ``fuse_shape.*``, ``res_coeff.*``, ``fuse_det.*`` (the pairwise MLPs
-incl. their decomposed first layers) and ``aug_shape.*`` (the anchor shape generators, 99 % of the parameters).
-``aug_dets.*`` (anchor boxes: needs the backward of the hand-designed residual incl. F.normalize) and ``shared_conv``
-(needs the gather's scatter-add) are not differentiated yet; their parameters receive no gradient, like the frozen
-trunk. DESIGN.md §7 tracks it.
+incl. their decomposed first layers), ``aug_shape.*`` (the anchor shape generators, 99 % of the parameters) and
+``aug_dets.*`` (anchor boxes, through the first-layer box columns and the hand-designed residual incl. the F.normalize
+backward) - i.e. every parameter of the head. ``shared_conv`` (the producer left of the path; needs the gather's
+scatter-add) is not differentiated yet and receives no gradient, like the frozen trunk. DESIGN.md §7 tracks it.
 """
 import ctypes
 
@@ -23,21 +23,24 @@ GROUPS = (("aff", AFF_LAYERS), ("fuse_shape", (0, 2, 4, 6)), ("fuse_det", (0, 2,
 
 def differentiable_parameters(model):
     """Parameters that receive gradients from the CUDA backward, in the order the autograd node expects them:
-    aff.*, fuse_shape.*, fuse_det.*, res_coeff.* (weight, bias per layer), then aug_shape.{0..3}.{0,2}."""
+    aff.*, fuse_shape.*, fuse_det.*, res_coeff.* (weight, bias per layer), then aug_shape.{0..3}.{0,2} and
+    aug_dets.{0..3}.{0,2} - every trainable tensor of the head except shared_conv."""
     out = []
     for name, layers in GROUPS:
         seq = getattr(model, name)
         for li in layers:
             out += [seq[li].weight, seq[li].bias]
-    for i in range(4):
-        for li in (0, 2):
-            out += [model.aug_shape[i][li].weight, model.aug_shape[i][li].bias]
+    for mods in (model.aug_shape, model.aug_dets):
+        for i in range(4):
+            for li in (0, 2):
+                out += [mods[i][li].weight, mods[i][li].bias]
     return out
 
 
 def differentiable_parameter_names():
     names = ["%s.%d.%s" % (name, li, k) for name, layers in GROUPS for li in layers for k in ("weight", "bias")]
-    names += ["aug_shape.%d.%d.%s" % (i, li, k) for i in range(4) for li in (0, 2) for k in ("weight", "bias")]
+    for grp in ("aug_shape", "aug_dets"):
+        names += ["%s.%d.%d.%s" % (grp, i, li, k) for i in range(4) for li in (0, 2) for k in ("weight", "bias")]
     return names
 
 
@@ -71,11 +74,12 @@ class _AffinityFunction(torch.autograd.Function):
             for n in range(len(layers)):
                 gw[n] = next(it).data_ptr()
                 gb[n] = next(it).data_ptr()
-        for i in range(4):
-            g.aug_shape_w0[i] = next(it).data_ptr()
-            g.aug_shape_b0[i] = next(it).data_ptr()
-            g.aug_shape_w2[i] = next(it).data_ptr()
-            g.aug_shape_b2[i] = next(it).data_ptr()
+        for grp in ("aug_shape", "aug_dets"):
+            for i in range(4):
+                getattr(g, grp + "_w0")[i] = next(it).data_ptr()
+                getattr(g, grp + "_b0")[i] = next(it).data_ptr()
+                getattr(g, grp + "_w2")[i] = next(it).data_ptr()
+                getattr(g, grp + "_b2")[i] = next(it).data_ptr()
         device = m1.device
         with torch.cuda.device(device):
             rc = lib.shasta_backward_f32(

@@ -99,7 +99,7 @@ def test_cabi_host_side_queries(shasta_lib):
     assert lib.shasta_packed_weight_bytes(200, 3) > 0 and lib.shasta_packed_weight_bytes(200, 7) == 0
     assert lib.shasta_workspace_bytes(0, 200) >= 0
     n = lib.shasta_workspace_bytes(4, 200)
-    offs = [lib.shasta_workspace_offset(4, 200, r) for r in range(19)]
+    offs = [lib.shasta_workspace_offset(4, 200, r) for r in range(21)]
     assert offs == sorted(offs) and offs[0] == 0 and offs[-1] * 4 < n
     assert all(o % 64 == 0 for o in offs)                      # 256-byte aligned regions
     assert lib.shasta_workspace_offset(4, 200, 99) == 2 ** 64 - 1
