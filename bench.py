@@ -45,12 +45,13 @@ def parse():
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0, help="kernel variant flags (see shasta_b200.h)")
     ap.add_argument("--anchor-path", type=int, default=0, help="0 auto, 1 streaming CUDA-core, 2 tcgen05")
     ap.add_argument("--raw-hi", type=int, default=1)
-    ap.add_argument("--dbg", type=int, default=0, help="kernel experiment bits (results invalid when non-zero)")
+    ap.add_argument("--dbg", type=lambda x: int(x, 0), default=0, help="kernel experiment bits (results invalid when non-zero)")
     ap.add_argument("--splits", type=int, default=0, help="force the split-K count of the anchors GEMM (experiment)")
     ap.add_argument("--train", action="store_true",
                     help="BASELINE.json config 5: training step (forward + loss + CUDA backward + gradient all-reduce "
                          "+ Adam on the differentiated parameters) instead of inference")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -87,6 +88,8 @@ class ClockSampler:
 
     def start(self):
         try:
+            if os.environ.get("SHASTA_NO_SAMPLER"):
+                raise RuntimeError("sampler disabled")
             import pynvml as nv
             nv.nvmlInit()
             try:
@@ -113,7 +116,7 @@ class ClockSampler:
                 self.rows.append((time.time(), mhz, reasons))
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(float(os.environ.get("SHASTA_SAMPLER_PERIOD", "0.02")))
 
     def stop(self, t_begin=None, t_end=None):
         """Summary of the samples taken inside [t_begin, t_end]."""
@@ -170,6 +173,7 @@ def build_model(a, pc_start, device):
         model = build_track(cfg)
     model.eval()
     model.kernel_flags = a.flags
+    model.cuda_graphs = not getattr(a, "no_graph", False)
     return model
 
 
@@ -514,7 +518,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": n_warm, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "b200",
-                "config": config_dict(a, {"flags": a.flags, "anchor_path": a.anchor_path}), "clocks": clocks, "roofline": roofline,
+                "config": config_dict(a, {"flags": a.flags, "anchor_path": a.anchor_path, "cuda_graph": not a.no_graph}), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * a.steps}
         print(json.dumps(line))
     if dist is not None:

@@ -272,11 +272,17 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
 
 // ------------------------------------------------------------------------------------------------
 int anchor_tc2_splits(int M, int B);  // anchors_tc2.cu
-int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, const float* feat_prev, int B, int S,
-                             float* part, cudaStream_t s);
+int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, const float* feat_prev,
+                             float* featlo_cur, float* featlo_prev, bool featlo_ready, int B, int S, float* part,
+                             cudaStream_t s);
 int anchor_tc_splits(int M, int B);  // anchors_tc.cu
 int launch_anchor_hidden_tc(const shasta_params_t& p, const float* feat_cur, const float* feat_prev, int B, int S,
                             float* part, cudaStream_t s);
+
+bool anchor_uses_featlo(int M, int B) {
+  const int mode = g_options[SHASTA_OPT_ANCHOR_PATH];
+  return mode == 2 || (mode == 0 && B > 8);
+}
 
 int anchor_splits_in_use(int M, int B) {
   const int mode = g_options[SHASTA_OPT_ANCHOR_PATH];
@@ -286,7 +292,7 @@ int anchor_splits_in_use(int M, int B) {
 }
 
 int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
-                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid) {
+                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid, bool featlo_ready) {
   const int M = p.max_obj;
   const int N5 = 5 * M;
   float* feat_cur = ws + L.off[SHASTA_WS_FEAT_CUR];
@@ -299,7 +305,8 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   int S;
   if (mode == 2 || (mode == 0 && B > 8)) {        // tcgen05, weights on the M side, TMEM-resident low parts
     S = anchor_tc2_splits(M, B);
-    int rc = launch_anchor_hidden_tc2(p, feat_cur, feat_prev, B, S, part, s);
+    int rc = launch_anchor_hidden_tc2(p, feat_cur, feat_prev, ws + L.off[SHASTA_WS_FEATLO_CUR],
+                                      ws + L.off[SHASTA_WS_FEATLO_PREV], featlo_ready, B, S, part, s);
     if (rc) return rc;
   } else if (mode == 3) {                         // first-generation tcgen05 kernel (kept for comparison)
     S = anchor_tc_splits(M, B);

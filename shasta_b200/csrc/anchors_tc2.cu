@@ -46,6 +46,7 @@ struct T2Cfg {
 struct AnchorT2Maps {
   CUtensorMap w[4];  // aug_shape.i.0.weight (5M, 320M), box 32 x 128
   CUtensorMap x[2];  // FEAT_CUR / FEAT_PREV as (B, 320M) with row stride (M+2)*320, box 32 x BN
+  CUtensorMap xlo[2];  // FEATLO_CUR / FEATLO_PREV (B, 320M) compact: the tf32 low parts of the same elements
 };
 
 __device__ __forceinline__ void t2_tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
 anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M, int S, int ntiles_n, int raw_hi,
                          float* __restrict__ part, int dbg) {
   using C = T2Cfg<BN>;
+  const int nst = (dbg >> 12) > 0 ? min(dbg >> 12, C::kStages) : C::kStages;  // experiment: fewer pipeline stages
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N5 = 5 * M;
@@ -111,22 +113,28 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int st = 0;
       uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(empty_bar(st), ph ^ 1);
         const uint32_t sb = base + st * C::kStageBytes;
-        mbar_expect_tx(full_bar(st), kT2WTile + C::kXTile);
+        if (dbg & 4) {  // timing experiment: no loads (results are garbage)
+          mbar_arrive(full_bar(st));
+          if (++st == nst) st = 0, ph ^= 1;
+          continue;
+        }
+        mbar_expect_tx(full_bar(st), kT2WTile + 2 * C::kXTile);
         const int k0 = (kb_beg + kb) * kT2BK;
         tma_load_2d(sb, &maps.w[i], full_bar(st), k0, n0, kEvictFirst);                  // weights: streamed once
         tma_load_2d(sb + kT2WTile, &maps.x[i >> 1], full_bar(st), k0, b0, kEvictLast);   // activations: reused
-        if (++st == C::kStages) st = 0, ph ^= 1;
+        tma_load_2d(sb + kT2WTile + C::kXTile, &maps.xlo[i >> 1], full_bar(st), k0, b0, kEvictLast);
+        if (++st == nst) st = 0, ph ^= 1;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc(kFmtTF32, kT2BM, BN);
       constexpr uint32_t idesc2 = umma_idesc(kFmtTF32, kT2BM, 2 * BN > 256 ? 256 : 2 * BN);
       int st = 0;
@@ -150,16 +158,17 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M
           if (dbg & 1) break;  // timing experiment: no MMAs (results are garbage)
           const uint64_t adv = (uint64_t)((k * 32) >> 4);
           if (C::kFuseX) {
+            if (!(dbg & 0x10))
             mma_tf32(d, dwh + adv, dxh + adv, idesc2, !(first && k == 0));   // [Xhi; Xlo] as one 128-row operand
           } else {
             mma_tf32(d, dwh + adv, dxh + adv, idesc, !(first && k == 0));
             mma_tf32(d, dwh + adv, dxl + adv, idesc, 1);
           }
-          t2_mma_ts_tf32(d, wl + (uint32_t)(k * 8), dxh + adv, idesc, 1);
+          if (!(dbg & 0x20)) t2_mma_ts_tf32((dbg & 8) ? tmem + 448u : d, wl + (uint32_t)(k * 8), dxh + adv, idesc, 1);
         }
         mma_commit(empty_bar(st));
         if ((kb % kT2Flush) == kT2Flush - 1 || kb == nkb - 1) mma_commit(dfull_bar(buf));
-        if (++st == C::kStages) st = 0, ph ^= 1;
+        if (++st == nst) st = 0, ph ^= 1;
       }
     }
   } else if (warp >= 4) {
@@ -202,57 +211,58 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M
     for (int kb = 0; kb < nkb; ++kb) {
       // chunk c is complete once the MMAs of K block (c+1)*kFlush-1 retired; the pipeline guarantees that by the
       // time the splitter sees K block (c+1)*kFlush-1+kStages, so this wait does not stall
-      if (next_flush < nchunks - 1 && kb >= (next_flush + 1) * kT2Flush - 1 + C::kStages) flush(next_flush++);
+      if (next_flush < nchunks - 1 && kb >= (next_flush + 1) * kT2Flush - 1 + nst) flush(next_flush++);
 
       mbar_wait(full_bar(st), ph);
       uint8_t* sg = gen_base + st * C::kStageBytes;
       if (dbg & 2) {  // timing experiment: no split work
         tc_fence_before();
         mbar_arrive(split_bar(st));
-        if (++st == C::kStages) st = 0, ph ^= 1;
+        if (++st == nst) st = 0, ph ^= 1;
         continue;
       }
-      // --- weight tile: row r, 8 chunks of 16 bytes, 128B-swizzled (chunk c lives at c ^ (r & 7))
+      // --- weight tile: row r, 8 chunks of 16 bytes, 128B-swizzled (chunk c lives at c ^ (r & 7)). All eight loads
+      // are issued before the first TMEM store (the stores are ordered asm statements): one shared-memory latency
+      // per stage instead of four. The activations need no work here: their low parts arrive by TMA (FEATLO_*).
+      float4 w[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) w[c] = *reinterpret_cast<const float4*>(sg + r * 128 + ((c ^ (r & 7)) << 4));
 #pragma unroll
       for (int c = 0; c < 8; c += 2) {
         uint32_t lo[8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          float4* p = reinterpret_cast<float4*>(sg + r * 128 + (((c + h) ^ (r & 7)) << 4));
-          const float4 w = *p;
+          const float4 v = w[c + h];
           float4 wh;
-          wh.x = __uint_as_float(__float_as_uint(w.x) & 0xffffe000u);
-          wh.y = __uint_as_float(__float_as_uint(w.y) & 0xffffe000u);
-          wh.z = __uint_as_float(__float_as_uint(w.z) & 0xffffe000u);
-          wh.w = __uint_as_float(__float_as_uint(w.w) & 0xffffe000u);
-          lo[h * 4 + 0] = __float_as_uint(w.x - wh.x);
-          lo[h * 4 + 1] = __float_as_uint(w.y - wh.y);
-          lo[h * 4 + 2] = __float_as_uint(w.z - wh.z);
-          lo[h * 4 + 3] = __float_as_uint(w.w - wh.w);
-          if (!raw_hi) *p = wh;
+          wh.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          wh.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          wh.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          wh.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          lo[h * 4 + 0] = __float_as_uint(v.x - wh.x);
+          lo[h * 4 + 1] = __float_as_uint(v.y - wh.y);
+          lo[h * 4 + 2] = __float_as_uint(v.z - wh.z);
+          lo[h * 4 + 3] = __float_as_uint(v.w - wh.w);
+          if (!raw_hi) *reinterpret_cast<float4*>(sg + r * 128 + (((c + h) ^ (r & 7)) << 4)) = wh;
         }
         t2_tmem_st8(lane_base + (uint32_t)(C::kColWl + st * 32 + c * 4), lo);
       }
-      // --- activation tile: elementwise, layout-agnostic
-      float4* xh = reinterpret_cast<float4*>(sg + kT2WTile);
-      float4* xl = reinterpret_cast<float4*>(sg + kT2WTile + C::kXTile);
+      if (!raw_hi) {  // explicit tf32 truncation of the activation high parts too (the default feeds raw fp32)
+        float4* xh = reinterpret_cast<float4*>(sg + kT2WTile);
 #pragma unroll
-      for (int j = 0; j < C::kXTile / 16 / 128; ++j) {
-        const int idx = j * 128 + t;
-        const float4 a = xh[idx];
-        float4 ah, al;
-        ah.x = __uint_as_float(__float_as_uint(a.x) & 0xffffe000u), al.x = a.x - ah.x;
-        ah.y = __uint_as_float(__float_as_uint(a.y) & 0xffffe000u), al.y = a.y - ah.y;
-        ah.z = __uint_as_float(__float_as_uint(a.z) & 0xffffe000u), al.z = a.z - ah.z;
-        ah.w = __uint_as_float(__float_as_uint(a.w) & 0xffffe000u), al.w = a.w - ah.w;
-        xl[idx] = al;
-        if (!raw_hi) xh[idx] = ah;
+        for (int j = 0; j < C::kXTile / 16 / 128; ++j) {
+          float4 a = xh[j * 128 + t];
+          a.x = __uint_as_float(__float_as_uint(a.x) & 0xffffe000u);
+          a.y = __uint_as_float(__float_as_uint(a.y) & 0xffffe000u);
+          a.z = __uint_as_float(__float_as_uint(a.z) & 0xffffe000u);
+          a.w = __uint_as_float(__float_as_uint(a.w) & 0xffffe000u);
+          xh[j * 128 + t] = a;
+        }
       }
       t2_tmem_st_wait();
-      fence_proxy_async_smem();
+      if (!raw_hi) fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(split_bar(st));
-      if (++st == C::kStages) st = 0, ph ^= 1;
+      if (++st == nst) st = 0, ph ^= 1;
     }
     while (next_flush < nchunks) flush(next_flush++);
 
@@ -324,8 +334,28 @@ int anchor_tc2_splits(int M, int B) {
   return best;
 }
 
-int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, const float* feat_prev, int B, int S,
-                             float* part, cudaStream_t s) {
+// FEATLO = FEAT - tf32_trunc(FEAT) for the M gathered rows of every frame pair (stage-API path; the fused forward lets
+// the gather kernel write it)
+__global__ void feat_lo_kernel(const float* __restrict__ feat0, const float* __restrict__ feat1, float* __restrict__ lo0,
+                               float* __restrict__ lo1, int B, int M) {
+  const float* __restrict__ feat = blockIdx.y ? feat1 : feat0;
+  float* __restrict__ lo = blockIdx.y ? lo1 : lo0;
+  const size_t per = (size_t)M * kF / 4, total = (size_t)B * per;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = v / per, e = v % per;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(feat + b * (size_t)(M + 2) * kF) + e);
+    float4 r;
+    r.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+    r.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+    r.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+    r.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+    reinterpret_cast<float4*>(lo)[v] = r;
+  }
+}
+
+int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, const float* feat_prev,
+                             float* featlo_cur, float* featlo_prev, bool featlo_ready, int B, int S, float* part,
+                             cudaStream_t s) {
   const int M = p.max_obj;
   const int bn = t2_bn(B);
   const uint64_t K = (uint64_t)kF * M, N5 = 5ull * M, ld = (uint64_t)(M + 2) * kF;
@@ -338,6 +368,14 @@ int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, co
   if (rc) return rc;
   rc = make_map2(&maps.x[1], feat_prev, (uint64_t)B, K, ld, (uint32_t)bn);
   if (rc) return rc;
+  rc = make_map2(&maps.xlo[0], featlo_cur, (uint64_t)B, K, K, (uint32_t)bn);
+  if (rc) return rc;
+  rc = make_map2(&maps.xlo[1], featlo_prev, (uint64_t)B, K, K, (uint32_t)bn);
+  if (rc) return rc;
+  if (!featlo_ready) {
+    feat_lo_kernel<<<dim3(592, 2), 256, 0, s>>>(feat_cur, feat_prev, featlo_cur, featlo_prev, B, M);
+    SHASTA_CHECK_LAUNCH("feat_lo_kernel");
+  }
   static bool configured = false;
   if (!configured) {
     SHASTA_CUDA(cudaFuncSetAttribute(anchor_hidden_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,

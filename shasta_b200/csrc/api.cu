@@ -278,11 +278,16 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
   if (ev) cudaEventRecord(ev[i], s)
   STAGE_MARK(0);
   // a1-a2: both frames in one launch (blockIdx.y selects the frame)
+  // the tcgen05 anchors GEMM takes the tf32 low parts of the features as a second TMA operand: the gather writes them
+  const bool featlo = anchor_uses_featlo(M, batch);
   rc = launch_gather(bev, det_boxes, workspace + L.off[SHASTA_WS_FEAT_CUR], prev_bev, prev_det_boxes,
-                     workspace + L.off[SHASTA_WS_FEAT_PREV], 2, 11, batch, M, *host_geom, fstride, (int)(flags & 1u), s);
+                     workspace + L.off[SHASTA_WS_FEAT_PREV], 2, 11, batch, M, *host_geom, fstride, (int)(flags & 1u), s,
+                     featlo ? workspace + L.off[SHASTA_WS_FEATLO_CUR] : nullptr,
+                     featlo ? workspace + L.off[SHASTA_WS_FEATLO_PREV] : nullptr);
   if (rc) return rc;
   STAGE_MARK(1);
-  rc = launch_anchors(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, s, ev ? ev[2] : nullptr);  // a3-a4
+  rc = launch_anchors(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, s, ev ? ev[2] : nullptr,
+                      featlo);  // a3-a4
   if (rc) return rc;
   STAGE_MARK(3);
   rc = launch_project(packed, batch, M, workspace, L, det_boxes, s);  // first layers, aux, colnorm, back-projection

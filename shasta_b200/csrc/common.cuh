@@ -54,6 +54,8 @@ __host__ inline WsLayout ws_layout(int B, int M) {
   sz[SHASTA_WS_ANCH_DY] = (size_t)B * 4 * kF;
   sz[SHASTA_WS_ANCH_DZ] = (size_t)B * 4 * 5 * M;
   sz[SHASTA_WS_RAW_XY] = (size_t)B * M * 2;
+  sz[SHASTA_WS_FEATLO_CUR] = (size_t)B * M * kF;
+  sz[SHASTA_WS_FEATLO_PREV] = (size_t)B * M * kF;
   sz[SHASTA_WS_BOX_BWD] = (size_t)B * 4 * (16 + 2 * (size_t)((7 * M) / 32 + 1) + 7 * (size_t)M);
   size_t o = 0;
   for (int i = 0; i < SHASTA_WS_NUM_REGIONS; ++i) {
@@ -92,6 +94,12 @@ struct PackLayout {
   size_t tc16_begin;  // bf16 block (counted in floats): w2a (6x32x8 bf16), w2b (10x32x8), w2c (4x16x8)
   size_t tc16_w2a, tc16_w2b, tc16_w2c;
   size_t tc16_end;
+  // aff on tensor cores (only built when D = M+2 <= 208): 8 weight chunks, each [hi image | lo image] in the UMMA
+  // canonical K-major layout [k/4][N][4]: aff.0 in two K halves of aff_tc_kc, aff.2, aff.4, aff.6, aff.8, aff.10
+  // (N padded to aff_tc_np) in two K halves of 64
+  size_t aff_tc[8];
+  size_t aff_tc_floats[8];   // floats per chunk (hi + lo)
+  int aff_tc_kc, aff_tc_np;  // 0 when the tensor-core aff kernel is not available for this M
   size_t total;       // floats
 };
 
@@ -145,6 +153,16 @@ __host__ inline PackLayout pack_layout(int M) {
   P.tc16_w2b = take(10 * 32 * 8 / 2);  // K = 72 padded to 80
   P.tc16_w2c = take(4 * 16 * 8 / 2);
   P.tc16_end = o;
+  P.aff_tc_kc = 0, P.aff_tc_np = 0;
+  for (int i = 0; i < 8; ++i) P.aff_tc[i] = 0, P.aff_tc_floats[i] = 0;
+  if (D <= 208) {
+    const int kc = (((int)D + 7) / 8 * 8 / 2 + 7) / 8 * 8;   // half of K0 = round_up(D, 8), itself a multiple of 8
+    const int np = ((int)D + 15) / 16 * 16;
+    P.aff_tc_kc = kc, P.aff_tc_np = np;
+    const size_t fl[8] = {2ull * kc * 128, 2ull * kc * 128, 2ull * 128 * 64, 2ull * 64 * 32,
+                          2ull * 32 * 64,  2ull * 64 * 128, 2ull * 64 * np,  2ull * 64 * np};
+    for (int i = 0; i < 8; ++i) P.aff_tc_floats[i] = fl[i], P.aff_tc[i] = take(fl[i]);
+  }
   P.total = o;
   return P;
 }
@@ -193,10 +211,12 @@ int launch_bilinear(const float* im, int H, int W, int C, const float* xs, const
                     cudaStream_t s);
 int launch_gather(const float* bev0, const float* boxes0, float* feat0, const float* bev1, const float* boxes1,
                   float* feat1, int nframes, int box_stride, int B, int M, const shasta_geom_t& g,
-                  size_t feat_batch_stride, int variant, cudaStream_t s);
+                  size_t feat_batch_stride, int variant, cudaStream_t s, float* featlo0 = nullptr,
+                  float* featlo1 = nullptr);
 // `mid` (optional) is recorded between the two kernels of a stage (per-kernel timing for bench.py)
+// `featlo_ready`: the FEATLO_* regions already hold the tf32 low parts of FEAT_* (written by the fused gather)
 int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
-                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid);
+                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid, bool featlo_ready = false);
 int launch_project(const float* packed, int B, int M, float* ws, const WsLayout& L, float* det_boxes_inout,
                    cudaStream_t s);
 int launch_pairwise(const float* packed, int B, int M, float* ws, const WsLayout& L, int variant,
@@ -212,6 +232,7 @@ int launch_backward_anchor(const shasta_params_t& p, const shasta_grads_t& g, in
                            const WsLayout& L, cudaStream_t s);
 int launch_backward_box(const shasta_params_t& p, const shasta_grads_t& g, int B, float* ws, const WsLayout& L,
                         cudaStream_t s);
+bool anchor_uses_featlo(int M, int B);  // true when the anchors path in use for (M, B) reads the FEATLO_* regions
 int anchor_splits_in_use(int M, int B);  // split-K count the forward anchors kernel uses for this (M, B)
 int launch_decode(const float* m1, const float* m2, const int32_t* n_prev, const int32_t* n_det, int B, int M,
                   int32_t* prev_state, int32_t* prev_argmax, float* fn_score, int32_t* det_state,

@@ -76,7 +76,15 @@ struct GatherJob {
   const float* bev[2];
   const float* boxes[2];
   float* feat[2];
+  float* featlo[2];  // optional (B, 320M): x - tf32_trunc(x), the low operand of the 3xTF32 anchors GEMM
 };
+
+__device__ __forceinline__ float tf32_lo(float v) {
+  return __fsub_rn(v, __uint_as_float(__float_as_uint(v) & 0xffffe000u));
+}
+__device__ __forceinline__ float4 tf32_lo4(float4 v) {
+  return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+}
 
 __device__ __forceinline__ void box_point_pixels(const float* __restrict__ bx, int p, const shasta_geom_t& g,
                                                  float& xs, float& ys) {
@@ -136,7 +144,10 @@ gather_ldg_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, 
   const float4 c = __ldg(base + ((size_t)t.y0 * g.width + t.x1) * (kC / 4) + lane16);
   const float4 d = __ldg(base + ((size_t)t.y1 * g.width + t.x1) * (kC / 4) + lane16);
   float4* dst = reinterpret_cast<float4*>(feat + (size_t)b * feat_batch_stride + (size_t)m * kF + p * kC);
-  dst[lane16] = blend4(a, bb, c, d, t);
+  const float4 v = blend4(a, bb, c, d, t);
+  dst[lane16] = v;
+  if (job.featlo[f] != nullptr)
+    reinterpret_cast<float4*>(job.featlo[f] + ((size_t)b * M + m) * kF + p * kC)[lane16] = tf32_lo4(v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -154,6 +165,7 @@ gather_bulk_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g,
   __shared__ __align__(128) float s_taps[kPointsPerCta1][4][kC];  // 32 KB
   __shared__ Taps s_t[kPointsPerCta1];
   __shared__ long long s_dst[kPointsPerCta1];
+  __shared__ long long s_dstlo[kPointsPerCta1];
   __shared__ __align__(8) unsigned long long s_bar;
 
   const int f = blockIdx.y;
@@ -184,6 +196,7 @@ gather_bulk_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g,
     const Taps t = make_taps(xs, ys, g.height, g.width);
     s_t[threadIdx.x] = t;
     s_dst[threadIdx.x] = (long long)((size_t)b * feat_batch_stride + (size_t)m * kF + p * kC);
+    s_dstlo[threadIdx.x] = (long long)(((size_t)b * M + m) * kF + p * kC);
     const float* base = bev + (size_t)b * g.height * g.width * kC;
     const float* src[4] = {base + ((size_t)t.y0 * g.width + t.x0) * kC, base + ((size_t)t.y1 * g.width + t.x0) * kC,
                            base + ((size_t)t.y0 * g.width + t.x1) * kC, base + ((size_t)t.y1 * g.width + t.x1) * kC};
@@ -217,7 +230,9 @@ gather_bulk_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g,
     const float4 bb = reinterpret_cast<const float4*>(&s_taps[pt][1][0])[q];
     const float4 c = reinterpret_cast<const float4*>(&s_taps[pt][2][0])[q];
     const float4 d = reinterpret_cast<const float4*>(&s_taps[pt][3][0])[q];
-    reinterpret_cast<float4*>(feat + s_dst[pt])[q] = blend4(a, bb, c, d, t);
+    const float4 v = blend4(a, bb, c, d, t);
+    reinterpret_cast<float4*>(feat + s_dst[pt])[q] = v;
+    if (job.featlo[f] != nullptr) reinterpret_cast<float4*>(job.featlo[f] + s_dstlo[pt])[q] = tf32_lo4(v);
   }
 }
 
@@ -234,8 +249,9 @@ int launch_bilinear(const float* im, int H, int W, int C, const float* xs, const
 
 int launch_gather(const float* bev0, const float* boxes0, float* feat0, const float* bev1, const float* boxes1,
                   float* feat1, int nframes, int box_stride, int B, int M, const shasta_geom_t& g,
-                  size_t feat_batch_stride, int variant, cudaStream_t s) {
+                  size_t feat_batch_stride, int variant, cudaStream_t s, float* featlo0, float* featlo1) {
   GatherJob job;
+  job.featlo[0] = featlo0, job.featlo[1] = featlo1;
   job.bev[0] = bev0, job.boxes[0] = boxes0, job.feat[0] = feat0;
   job.bev[1] = bev1, job.boxes[1] = boxes1, job.feat[1] = feat1;
   const long long total = (long long)B * M * 5;

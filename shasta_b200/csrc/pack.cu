@@ -29,6 +29,27 @@ __global__ void umma_b_image_kernel(float* __restrict__ hi, float* __restrict__ 
   bf[(k / 8) * (n_pad * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(v);
 }
 
+// tf32 hi/lo image of the K slice [k0, k0 + kc) of a Linear weight (n_valid x k_valid, leading dimension src_ld):
+// hi[(k-k0)/4][n][(k-k0)%4], lo directly behind it; rows n >= n_valid and columns k >= k_valid are zero.
+__global__ void umma_b_slice_kernel(float* __restrict__ img, const float* __restrict__ src, int src_ld, int n_valid,
+                                    int k_valid, int n_pad, int k0, int kc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pad * kc) return;
+  const int n = idx / kc, kk = idx % kc, k = k0 + kk;
+  const float v = (n < n_valid && k < k_valid) ? src[(size_t)n * src_ld + k] : 0.f;
+  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  const size_t o = (size_t)(kk / 4) * (n_pad * 4) + n * 4 + (kk % 4);
+  img[o] = h;
+  img[(size_t)n_pad * kc + o] = v - h;
+}
+
+static int bslice(float* img, const float* src, int src_ld, int n_valid, int k_valid, int n_pad, int k0, int kc,
+                  cudaStream_t s) {
+  umma_b_slice_kernel<<<(n_pad * kc + 255) / 256, 256, 0, s>>>(img, src, src_ld, n_valid, k_valid, n_pad, k0, kc);
+  SHASTA_CHECK_LAUNCH("umma_b_slice_kernel");
+  return 0;
+}
+
 static int bimage(float* hi, float* lo, float* bf, const float* src, int src_ld, int n_valid, int n_pad, int K,
                   cudaStream_t s) {
   umma_b_image_kernel<<<(n_pad * K + 255) / 256, 256, 0, s>>>(hi, lo, reinterpret_cast<__nv_bfloat16*>(bf), src,
@@ -104,6 +125,18 @@ int launch_pack(const shasta_params_t& p, float* packed, cudaStream_t s) {
     copy_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(packed + P.aff_wn[i], (win[i] + 3) / 4 * 4, p.aff_w[i],
                                                                  win[i], wout[i], win[i]);
     SHASTA_CHECK_LAUNCH("copy_rows_kernel");
+  }
+  if (P.aff_tc_kc > 0) {   // tensor-core aff: chunked hi/lo images of the six layers
+    const int kc = P.aff_tc_kc, np = P.aff_tc_np;
+    int rc2 = bslice(packed + P.aff_tc[0], p.aff_w[0], D, 128, D, 128, 0, kc, s);
+    if (!rc2) rc2 = bslice(packed + P.aff_tc[1], p.aff_w[0], D, 128, D, 128, kc, kc, s);
+    if (!rc2) rc2 = bslice(packed + P.aff_tc[2], p.aff_w[1], 128, 64, 128, 64, 0, 128, s);
+    if (!rc2) rc2 = bslice(packed + P.aff_tc[3], p.aff_w[2], 64, 32, 64, 32, 0, 64, s);
+    if (!rc2) rc2 = bslice(packed + P.aff_tc[4], p.aff_w[3], 32, 64, 32, 64, 0, 32, s);
+    if (!rc2) rc2 = bslice(packed + P.aff_tc[5], p.aff_w[4], 64, 128, 64, 128, 0, 64, s);
+    if (!rc2) rc2 = bslice(packed + P.aff_tc[6], p.aff_w[5], 128, D, 128, np, 0, 64, s);
+    if (!rc2) rc2 = bslice(packed + P.aff_tc[7], p.aff_w[5], 128, D, 128, np, 64, 64, s);
+    if (rc2) return rc2;
   }
   // tensor-core operand images of fuse_shape.2 (20x40), res_coeff.2 (18x72), fuse_det.2 (8x32)
   int rc = bimage(packed + P.tc32_w2a_hi, packed + P.tc32_w2a_lo, packed + P.tc16_w2a, p.fuse_shape_w[1], 40, 20, 32, 40, s);

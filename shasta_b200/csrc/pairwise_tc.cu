@@ -193,7 +193,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
 
   if (warp == 8) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       // B images: [k chunk][n][16 bytes]; chunk stride (LBO) = N*16 bytes, 8-row group stride (SBO) = 128 bytes
       const uint32_t bi = sbase;
       uint32_t off_a_hi, off_a_lo, off_b_hi, off_b_lo, off_c_hi, off_c_lo;

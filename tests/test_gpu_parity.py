@@ -344,6 +344,31 @@ def test_forward_batch_rows_independent():
             assert torch.allclose(s2[0], m2[b], rtol=1e-6, atol=1e-9)
 
 
+@pytest.mark.parametrize("M,B", [(20, 3), (200, 12)])
+def test_cuda_graph_replay_matches_eager(M, B):
+    """cuda_graphs=True captures the launch sequence once and replays it: results (and the in-place back-projection)
+    are bit-identical to the eager launches, also after the input buffers were refilled in place."""
+    H = W = 32
+    pc_start = (-W * 0.3, -H * 0.3)
+    model = G.make_model(M, pc_start, synthetic.make_weights(M, seed=5))
+    d0 = synthetic.make_frame_pairs(B, M, H, W, 31, pc_start=pc_start)
+    d1 = synthetic.make_frame_pairs(B, M, H, W, 32, pc_start=pc_start)
+    bufs = [G.t(d0[k]) for k in ("bev", "prev_bev", "det_boxes", "prev_det_boxes")]
+    with torch.no_grad():
+        for rep, d in enumerate((d0, d1, d0)):
+            src = [G.t(d[k]) for k in ("bev", "prev_bev", "det_boxes", "prev_det_boxes")]
+            model.cuda_graphs = False
+            det_e = src[2].clone()
+            e1, e2 = model.affinity(src[0], src[1], det_e, src[3])
+            model.cuda_graphs = True
+            for dst, s_ in zip(bufs, src):
+                dst.copy_(s_)
+            g1, g2 = model.affinity(*bufs)
+            assert torch.equal(g1, e1) and torch.equal(g2, e2), rep
+            assert torch.equal(bufs[2], det_e), rep
+    assert len(model._graphs) == 1
+
+
 def test_forward_empty_batch_and_bad_inputs():
     M = 6
     model = G.make_model(M, (-4.8, -4.8), synthetic.make_weights(M, seed=1))
