@@ -139,8 +139,18 @@ enum shasta_region {
  *                           low parts, bounded accumulation chains), 3 = the first-generation tcgen05 kernel.
  *   SHASTA_OPT_TC_RAW_HI:   1 (default) = the tcgen05 anchors kernels feed the raw fp32 tile as the tf32 "high" part:
  *                           kind::tf32 ignores the low 13 mantissa bits (measured on B200: identical accuracy),
- *                           0 = write tf32-exact high parts back to shared memory first. */
-enum shasta_option { SHASTA_OPT_ANCHOR_PATH = 0, SHASTA_OPT_TC_RAW_HI = 1, SHASTA_OPT_COUNT = 4 };
+ *                           0 = write tf32-exact high parts back to shared memory first.
+ *   (2, 3: kernel experiment knobs of bench.py: debug bits, forced split-K count.)
+ *   SHASTA_OPT_AFF_PATH:    0 = auto (tcgen05 3xTF32 row tiles when max_obj + 2 <= 224, CUDA-core tiles otherwise),
+ *                           1 = always the CUDA-core kernel, 2 = always the tcgen05 kernel (error if unavailable).
+ *   SHASTA_OPT_PROJECT_PATH: same values for the first-layer projection GEMM. */
+enum shasta_option {
+  SHASTA_OPT_ANCHOR_PATH = 0,
+  SHASTA_OPT_TC_RAW_HI = 1,
+  SHASTA_OPT_AFF_PATH = 4,
+  SHASTA_OPT_PROJECT_PATH = 5,
+  SHASTA_OPT_COUNT = 6
+};
 SHASTA_API int shasta_set_option(int option, int value);
 SHASTA_API int shasta_get_option(int option);
 

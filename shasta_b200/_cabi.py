@@ -62,6 +62,8 @@ WS_FEAT_CUR, WS_FEAT_PREV, WS_BOX_CUR, WS_BOX_PREV, WS_HIDDEN_PART, WS_PROJ_PREV
 
 OPT_ANCHOR_PATH = 0
 OPT_TC_RAW_HI = 1
+OPT_AFF_PATH = 4      # 0 auto, 1 CUDA cores, 2 tcgen05
+OPT_PROJECT_PATH = 5  # same values
 ANCHOR_AUTO, ANCHOR_STREAM, ANCHOR_TC, ANCHOR_TC_GEN1 = 0, 1, 2, 3
 
 # every symbol include/shasta_b200.h declares: name -> (restype, argtypes)

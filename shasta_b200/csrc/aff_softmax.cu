@@ -95,10 +95,24 @@ col_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __rest
   }
 }
 
+bool aff_tc_available(int M);  // aff_tc.cu
+int launch_aff_tc(const float* packed, int B, int M, const float* residual, float* logits, float* matched1,
+                  cudaStream_t s);
+
 int launch_aff_softmax(const float* packed, int B, int M, float* ws, const WsLayout& L, float* matched1,
                        float* matched2, cudaStream_t s, cudaEvent_t mid) {
   const PackLayout P = pack_layout(M);
   const int T = M + 2;
+  const int mode = g_options[SHASTA_OPT_AFF_PATH];
+  if (mode == 2 || (mode == 0 && aff_tc_available(M))) {
+    int rc = launch_aff_tc(packed, B, M, ws + L.off[SHASTA_WS_RESIDUAL], ws + L.off[SHASTA_WS_LOGITS], matched1, s);
+    if (rc) return rc;
+    if (mid) cudaEventRecord(mid, s);
+    dim3 grid((M + 31) / 32, B), block(32, 8);
+    col_softmax_kernel<<<grid, block, 0, s>>>(B, M, ws + L.off[SHASTA_WS_LOGITS], matched2);
+    SHASTA_CHECK_LAUNCH("col_softmax_kernel");
+    return 0;
+  }
   const size_t smem = sizeof(float) * (((size_t)T + 256) * kAffRows + 2 * kAffKC * kAffNT);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {

@@ -66,6 +66,85 @@ __host__ inline WsLayout ws_layout(int B, int M) {
   return L;
 }
 
+// ---- tensor-core aff plan (aff_tc.cu) -----------------------------------------------------------------
+// The six aff layers run as TS-mode UMMAs on 128-row tiles: activations live in TENSOR MEMORY (lane = row, column = k,
+// tf32 hi/lo parts), weights stream through a shared-memory ring as "pieces": a K slice [k0, k0+ks) of one layer in
+// the canonical K-major UMMA layout [ks/4][N][4] (hi image, then the lo image). Layer 0 (K = D) is cut into chunks
+// of 64 K so that its A operand fits a 2 x 128-column TMEM ring.
+constexpr int kAffTcMaxPieces = 64;
+constexpr int kAffTcSlotFloats = 4096;   // 16 KB ring slot
+constexpr int kAffTcMaxD = 224;          // row tile + weight ring must fit 227 KB of shared memory
+struct AffTcPiece {
+  uint32_t off;       // float offset from PackLayout::aff_tc_begin
+  uint16_t n;         // UMMA N (outputs padded to a multiple of 16)
+  uint16_t ks;        // K extent (multiple of 8)
+  uint16_t a_col;     // TMEM column of the A operand (hi part) for the first k of the piece
+  uint16_t a_lo;      // column distance from the hi to the lo part
+  uint16_t d_col;     // accumulator column
+  uint8_t layer;
+  uint8_t first;      // first piece of its layer: the first MMA overwrites the accumulator
+  int8_t wait_a;      // barrier slot (AffTcBars) to wait on before this piece, -1 = none
+  uint8_t wait_parity;
+  int8_t commit_a;    // layer-0 A ring slot (0/1) released after this piece, -1 = none
+  uint8_t commit_d;   // 1: the layer's accumulator is complete after this piece
+  uint16_t k0, src_k, src_n;  // packing: K offset in the layer, valid K and N of the layer's weight (n_valid x k_valid)
+};
+struct AffTcPlan {
+  int npieces, nchunk0, kp0, np5;
+  size_t floats;
+  AffTcPiece p[kAffTcMaxPieces];
+};
+__host__ __device__ inline int aff_tc_dcol(int layer) { return (layer == 5) ? 256 : ((layer & 1) ? 384 : 256); }
+__host__ inline AffTcPlan aff_tc_plan(int M) {
+  AffTcPlan A;
+  A.npieces = 0, A.floats = 0;
+  const int D = M + 2;
+  A.kp0 = round_up(D, 8), A.np5 = round_up(D, 16), A.nchunk0 = (A.kp0 + 63) / 64;
+  if (D > kAffTcMaxD) {
+    A.nchunk0 = 0;
+    return A;
+  }
+  const int K[6] = {A.kp0, 128, 64, 32, 64, 128};
+  const int N[6] = {128, 64, 32, 64, 128, A.np5};
+  const int kv[6] = {D, 128, 64, 32, 64, 128};      // valid K / N of the PyTorch weights (out, in)
+  const int nv[6] = {128, 64, 32, 64, 128, D};
+  size_t off = 0;
+  for (int l = 0; l < 6; ++l) {
+    int ks_max = (kAffTcSlotFloats / 2 / N[l]) / 8 * 8;
+    const int nseg = (l == 0) ? A.nchunk0 : 1;
+    for (int sg = 0; sg < nseg; ++sg) {
+      const int kbeg = (l == 0) ? sg * 64 : 0;
+      const int kend = (l == 0) ? ((kbeg + 64 < K[0]) ? kbeg + 64 : K[0]) : K[l];
+      for (int k0 = kbeg; k0 < kend; k0 += ks_max) {
+        AffTcPiece& q = A.p[A.npieces++];
+        q.off = (uint32_t)off;
+        q.n = (uint16_t)N[l];
+        q.ks = (uint16_t)((kend - k0 < ks_max) ? kend - k0 : ks_max);
+        q.layer = (uint8_t)l;
+        q.first = (k0 == 0);
+        q.a_lo = (uint16_t)((l == 0) ? 64 : K[l]);
+        q.a_col = (uint16_t)((l == 0) ? (sg & 1) * 128 + (k0 - kbeg) : k0);
+        q.d_col = (uint16_t)aff_tc_dcol(l);
+        q.wait_a = -1, q.wait_parity = 0, q.commit_a = -1, q.commit_d = 0;
+        if (k0 == kbeg) {   // first piece of a segment: its A operand must have been written
+          if (l == 0)
+            q.wait_a = (int8_t)(sg & 1), q.wait_parity = (uint8_t)((sg >> 1) & 1);
+          else
+            q.wait_a = (int8_t)(1 + l);   // a_ready[l] lives in slot 1 + l (slots 0,1 = layer-0 ring)
+        }
+        if (k0 + q.ks >= kend) {
+          if (l == 0) q.commit_a = (int8_t)(sg & 1);
+          if (kend == K[l]) q.commit_d = 1;
+        }
+        q.k0 = (uint16_t)k0, q.src_k = (uint16_t)kv[l], q.src_n = (uint16_t)nv[l];
+        off += 2 * (size_t)q.ks * N[l];
+      }
+    }
+  }
+  A.floats = off;
+  return A;
+}
+
 // ---- packed small-layer weights (float offsets) ------------------------------------------------
 // All matrices are stored k-major ("transposed": [in][out]) so that consecutive threads / vector lanes
 // read consecutive outputs.
@@ -94,12 +173,8 @@ struct PackLayout {
   size_t tc16_begin;  // bf16 block (counted in floats): w2a (6x32x8 bf16), w2b (10x32x8), w2c (4x16x8)
   size_t tc16_w2a, tc16_w2b, tc16_w2c;
   size_t tc16_end;
-  // aff on tensor cores (only built when D = M+2 <= 208): 8 weight chunks, each [hi image | lo image] in the UMMA
-  // canonical K-major layout [k/4][N][4]: aff.0 in two K halves of aff_tc_kc, aff.2, aff.4, aff.6, aff.8, aff.10
-  // (N padded to aff_tc_np) in two K halves of 64
-  size_t aff_tc[8];
-  size_t aff_tc_floats[8];   // floats per chunk (hi + lo)
-  int aff_tc_kc, aff_tc_np;  // 0 when the tensor-core aff kernel is not available for this M
+  // aff on tensor cores (aff_tc.cu; only when D = M+2 <= kAffTcMaxD): weight pieces of AffTcPlan, each [hi image | lo image]
+  size_t aff_tc_begin, aff_tc_floats;   // aff_tc_floats == 0 when the tensor-core aff kernel is unavailable for this M
   size_t total;       // floats
 };
 
@@ -153,16 +228,8 @@ __host__ inline PackLayout pack_layout(int M) {
   P.tc16_w2b = take(10 * 32 * 8 / 2);  // K = 72 padded to 80
   P.tc16_w2c = take(4 * 16 * 8 / 2);
   P.tc16_end = o;
-  P.aff_tc_kc = 0, P.aff_tc_np = 0;
-  for (int i = 0; i < 8; ++i) P.aff_tc[i] = 0, P.aff_tc_floats[i] = 0;
-  if (D <= 208) {
-    const int kc = (((int)D + 7) / 8 * 8 / 2 + 7) / 8 * 8;   // half of K0 = round_up(D, 8), itself a multiple of 8
-    const int np = ((int)D + 15) / 16 * 16;
-    P.aff_tc_kc = kc, P.aff_tc_np = np;
-    const size_t fl[8] = {2ull * kc * 128, 2ull * kc * 128, 2ull * 128 * 64, 2ull * 64 * 32,
-                          2ull * 32 * 64,  2ull * 64 * 128, 2ull * 64 * np,  2ull * 64 * np};
-    for (int i = 0; i < 8; ++i) P.aff_tc_floats[i] = fl[i], P.aff_tc[i] = take(fl[i]);
-  }
+  P.aff_tc_floats = aff_tc_plan(M).floats;
+  P.aff_tc_begin = take(P.aff_tc_floats);
   P.total = o;
   return P;
 }

@@ -126,17 +126,15 @@ int launch_pack(const shasta_params_t& p, float* packed, cudaStream_t s) {
                                                                  win[i], wout[i], win[i]);
     SHASTA_CHECK_LAUNCH("copy_rows_kernel");
   }
-  if (P.aff_tc_kc > 0) {   // tensor-core aff: chunked hi/lo images of the six layers
-    const int kc = P.aff_tc_kc, np = P.aff_tc_np;
-    int rc2 = bslice(packed + P.aff_tc[0], p.aff_w[0], D, 128, D, 128, 0, kc, s);
-    if (!rc2) rc2 = bslice(packed + P.aff_tc[1], p.aff_w[0], D, 128, D, 128, kc, kc, s);
-    if (!rc2) rc2 = bslice(packed + P.aff_tc[2], p.aff_w[1], 128, 64, 128, 64, 0, 128, s);
-    if (!rc2) rc2 = bslice(packed + P.aff_tc[3], p.aff_w[2], 64, 32, 64, 32, 0, 64, s);
-    if (!rc2) rc2 = bslice(packed + P.aff_tc[4], p.aff_w[3], 32, 64, 32, 64, 0, 32, s);
-    if (!rc2) rc2 = bslice(packed + P.aff_tc[5], p.aff_w[4], 64, 128, 64, 128, 0, 64, s);
-    if (!rc2) rc2 = bslice(packed + P.aff_tc[6], p.aff_w[5], 128, D, 128, np, 0, 64, s);
-    if (!rc2) rc2 = bslice(packed + P.aff_tc[7], p.aff_w[5], 128, D, 128, np, 64, 64, s);
-    if (rc2) return rc2;
+  if (P.aff_tc_floats > 0) {   // tensor-core aff: the weight pieces of AffTcPlan, hi | lo images
+    const AffTcPlan A = aff_tc_plan(M);
+    const int lds[6] = {(int)D, 128, 64, 32, 64, 128};
+    for (int i = 0; i < A.npieces; ++i) {
+      const AffTcPiece& q = A.p[i];
+      int rc2 = bslice(packed + P.aff_tc_begin + q.off, p.aff_w[q.layer], lds[q.layer], q.src_n, q.src_k, q.n, q.k0,
+                       q.ks, s);
+      if (rc2) return rc2;
+    }
   }
   // tensor-core operand images of fuse_shape.2 (20x40), res_coeff.2 (18x72), fuse_det.2 (8x32)
   int rc = bimage(packed + P.tc32_w2a_hi, packed + P.tc32_w2a_lo, packed + P.tc16_w2a, p.fuse_shape_w[1], 40, 20, 32, 40, s);

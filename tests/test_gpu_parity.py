@@ -259,8 +259,45 @@ def test_project_and_pairwise_stage(name):
         assert err < tol, "variant %d residual max err / scale = %g" % (variant, err)
 
 
+@pytest.fixture(params=[1, 2], ids=["ffma", "tcgen05"])
+def aff_path(request):
+    lib = _cabi.lib()
+    lib.shasta_set_option(_cabi.OPT_AFF_PATH, request.param)
+    yield request.param
+    lib.shasta_set_option(_cabi.OPT_AFF_PATH, 0)
+
+
+@pytest.mark.parametrize("M,B", [(200, 7), (222, 2), (90, 3), (20, 9), (6, 1)])
+def test_aff_paths_agree(M, B):
+    """tcgen05 3xTF32 row tiles vs the CUDA-core kernel on random residuals: partial last tile, K and N padding at
+    D = 202 / 224 / 92 / 22 / 8."""
+    lib = _cabi.lib()
+    T = M + 2
+    model = G.make_model(M, (-4.8, -4.8), synthetic.make_weights(M, seed=3, peaky=50.0))
+    st = G.Stages(model, B)
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    res = (torch.randn((B, T, T), generator=gen) * 4.0).to(G.DEV)
+    out = {}
+    for mode in (1, 2):
+        lib.shasta_set_option(_cabi.OPT_AFF_PATH, mode)
+        try:
+            st.region(_cabi.WS_RESIDUAL, (B, T, st.RS)).zero_()
+            st.region(_cabi.WS_RESIDUAL, (B, T, st.RS))[:, :, :T] = res
+            m1, m2 = st.aff_softmax()
+            out[mode] = (st.region(_cabi.WS_LOGITS, (B, T, st.RS))[:, :, :T].cpu().numpy().copy(), m1.cpu().numpy(),
+                         m2.cpu().numpy())
+        finally:
+            lib.shasta_set_option(_cabi.OPT_AFF_PATH, 0)
+    scale = np.abs(out[1][0]).max()
+    err = np.abs(out[1][0] - out[2][0]).max() / scale
+    print("aff tcgen05 vs CUDA cores: logits max err / scale = %.3g" % err)
+    assert err < 1e-5
+    assert G.rel_err(out[2][1], out[1][1]) < FP32_REL_TOL
+    assert G.rel_err(out[2][2], out[1][2]) < FP32_REL_TOL
+
+
 @pytest.mark.parametrize("name", golden_names())
-def test_aff_softmax_stage(name):
+def test_aff_softmax_stage(name, aff_path):
     c, pc_start, data, weights, g = load_golden(name)
     B, M = c["B"], c["M"]
     T = M + 2
