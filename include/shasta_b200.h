@@ -130,7 +130,8 @@ enum shasta_region {
   SHASTA_WS_BOX_BWD = 20, /* scratch of the anchor-box backward: (B,4,8) d box, (B,4,8) dy, 2 x (B,4,7M/32), (B,4,7M) */
   SHASTA_WS_FEATLO_CUR = 21, /* (B,320M) tf32 low parts x - tf32_trunc(x) of the gathered current features   */
   SHASTA_WS_FEATLO_PREV = 22, /* same for the previous frame: B operands of the 3xTF32 anchors GEMM (TMA-loaded) */
-  SHASTA_WS_NUM_REGIONS = 23
+  SHASTA_WS_COUNTERS = 23,   /* 64 ints: work-item counters of the persistent kernels */
+  SHASTA_WS_NUM_REGIONS = 24
 };
 
 /* Runtime options (process-wide, not thread-safe; meant for tests and benchmarks).

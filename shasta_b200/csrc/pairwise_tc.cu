@@ -20,10 +20,14 @@ namespace shasta {
 
 using namespace tc;
 
-constexpr int kPtTT = 16;           // t rows per CTA (two 8-row tile rows)
-constexpr int kPtDT = 64;           // d columns per CTA = 4 MMA tile columns; a CTA walks up to 2 x 4 tiles of 8 x 16 pairs
+// The kernel is PERSISTENT: 2 CTAs per SM loop over work items (one item = 16 t rows x 32 d columns of one frame pair
+// = up to 2 x 2 MMA tiles) handed out by an atomic counter. A producer warp stages the next item's operands
+// (PROJ_PREV / PROJ_CUR rows, AUX rows, column norms) with cp.async.bulk into the other half of a double buffer while
+// the workers are busy; the weight images are staged once per CTA.
+constexpr int kPtTT = 16;           // t rows per item (two 8-row tile rows)
+constexpr int kPtDT = 32;           // d columns per item (two 16-column tile columns)
 constexpr int kPtQStride = 148;     // floats per d row of the staged PROJ_CUR tile (148 % 32 = 20: conflict-free LDS.128)
-constexpr int kPtThreads = 288;     // 8 worker warps (two threads per pair) + 1 MMA warp
+constexpr int kPtThreads = 320;     // 8 worker warps (two threads per pair) + MMA warp + producer warp
 constexpr int kPtTmemCols = 256;
 
 // TMEM column map (per CTA): A operands share [0,144), accumulators live in [144,224)
@@ -104,79 +108,67 @@ __device__ __forceinline__ void build_a(const float* __restrict__ prow, const fl
   }
 }
 
-struct PtSmem {  // float offsets inside dynamic shared memory (after the 1 KB aligned base)
+struct PtBuf {   // float offsets of one item buffer
   static constexpr int ps = 0;                                  // [16][144]
-  static constexpr int qs = ps + kPtTT * kProj;                 // [64][148]
+  static constexpr int qs = ps + kPtTT * kProj;                 // [32][148]
   static constexpr int auxp = qs + kPtDT * kPtQStride;          // [16][8]
-  static constexpr int auxc = auxp + kPtTT * 8;                 // [64][8]
-  static constexpr int cn = auxc + kPtDT * 8;                   // [64]
-  static constexpr int shp = cn + kPtDT;                        // [2][128] fuse_shape results (group B -> group A)
-  static constexpr int w = shp + 256;                           // small-layer block (l2a .. pair_end of PackLayout)
+  static constexpr int auxc = auxp + kPtTT * 8;                 // [32][8]
+  static constexpr int cn = auxc + kPtDT * 8;                   // [32]
+  static constexpr int desc = cn + kPtDT;                       // int4 {b, t0, d0, valid}
+  static constexpr int floats = desc + 4;
 };
+static_assert(PtBuf::floats % 4 == 0, "item buffers must keep 16-byte alignment");
+
+__device__ __forceinline__ void pt_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 
 template <bool BF16>
 __global__ void __launch_bounds__(kPtThreads, 2)
 pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, const float* __restrict__ proj_prev,
                    const float* __restrict__ proj_cur_t, const float* __restrict__ aux_prev,
                    const float* __restrict__ aux_cur, const float* __restrict__ colnorm,
-                   float* __restrict__ residual) {
+                   float* __restrict__ residual, int* __restrict__ counter) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int T = M + 2, D = M + 2;
   const int RS = row_stride(M);
-  const int b = blockIdx.z, t0 = blockIdx.y * kPtTT, d0 = blockIdx.x * kPtDT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntb = (T + kPtTT - 1) / kPtTT, ndb = (D + kPtDT - 1) / kPtDT;
+  const int nitems = B * ntb * ndb;
 
-  // ---- shared memory carve-up: [B-operand images (128 B aligned)] [barriers] [float region]
+  // ---- shared memory carve-up: [B-operand images (128 B aligned)] [barriers] [small layers] [2 item buffers]
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
   const int bimg_floats = BF16 ? (int)(P.tc16_end - P.tc16_begin) : (int)(P.tc32_end - P.tc32_begin);
   float* bimg = reinterpret_cast<float*>(gbase);
-  const uint32_t bars = sbase + bimg_floats * 4;                     // 7 mbarriers + tmem slot
-  float* fl = reinterpret_cast<float*>(gbase + bimg_floats * 4 + 128);
-  float* Ps = fl + PtSmem::ps;
-  float* Qs = fl + PtSmem::qs;
-  float* Ap = fl + PtSmem::auxp;
-  float* Ac = fl + PtSmem::auxc;
-  float* Cn = fl + PtSmem::cn;
-  float* Sh = fl + PtSmem::shp;   // [2][128] fuse_shape outputs handed from group B to group A
-  float* Ws = fl + PtSmem::w;
+  const uint32_t bars = sbase + bimg_floats * 4;                     // 11 mbarriers + tmem slot
   const int wbase = (int)P.l2a, wcount = (int)(P.pair_end - P.l2a);
+  float* Ws = reinterpret_cast<float*>(gbase + bimg_floats * 4 + 128);
+  float* Sh = Ws + wcount;                                           // [2][128] fuse_shape results (group B -> A)
+  float* bufs = Sh + 256;
+  const uint32_t bufs_u32 = sbase + bimg_floats * 4 + 128 + (wcount + 256) * 4;
   auto bar_a = [&](int x) { return bars + 8u * x; };        // x: 0 det, 1 shape, 2 coeff  (A operand ready)
   auto bar_d = [&](int x) { return bars + 8u * (3 + x); };  // accumulator ready
   const uint32_t bar_s = bars + 48;                         // fuse_shape scalar ready
-  const uint32_t tmem_slot = bars + 56;
+  auto item_full = [&](int x) { return bars + 56u + 8u * x; };
+  auto item_empty = [&](int x) { return bars + 72u + 8u * x; };
+  const uint32_t tmem_slot = bars + 88;
 
   if (tid == 0) {
     mbar_init(bar_a(0), 128), mbar_init(bar_a(1), 128), mbar_init(bar_a(2), 256);
     for (int x = 0; x < 3; ++x) mbar_init(bar_d(x), 1);
     mbar_init(bar_s, 128);
+    for (int x = 0; x < 2; ++x) mbar_init(item_full(x), 1), mbar_init(item_empty(x), 256);
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, kPtTmemCols);
 
-  // ---- stage operands (all threads) ----
+  // ---- per-CTA constants (all threads): weight images and the small layers ----
   {
     const float4* src = reinterpret_cast<const float4*>(packed + (BF16 ? P.tc16_begin : P.tc32_begin));
     for (int v = tid; v < bimg_floats / 4; v += kPtThreads) reinterpret_cast<float4*>(bimg)[v] = __ldg(src + v);
-    const int nt = min(kPtTT, T - t0);
-    const float4* psrc = reinterpret_cast<const float4*>(proj_prev + ((size_t)b * T + t0) * kProj);
-    for (int v = tid; v < kPtTT * kProj / 4; v += kPtThreads)
-      reinterpret_cast<float4*>(Ps)[v] = (v < nt * kProj / 4) ? __ldg(psrc + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-    // PROJ_CUR_T is (B,T,144) object-major: 64 rows of 144 floats, padded to a stride of 148 in shared memory
-    const int ndq = max(0, min(kPtDT, D - d0));
-    const float4* qsrc = reinterpret_cast<const float4*>(proj_cur_t + ((size_t)b * T + d0) * kProj);
-    for (int v = tid; v < kPtDT * (kProj / 4); v += kPtThreads) {
-      const int dr = v / (kProj / 4), k4 = v % (kProj / 4);
-      reinterpret_cast<float4*>(Qs + dr * kPtQStride)[k4] =
-          (dr < ndq) ? __ldg(qsrc + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    const float4* apsrc = reinterpret_cast<const float4*>(aux_prev + ((size_t)b * T + t0) * 8);
-    if (tid < kPtTT * 2)
-      reinterpret_cast<float4*>(Ap)[tid] = (tid < nt * 2) ? __ldg(apsrc + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* acsrc = reinterpret_cast<const float4*>(aux_cur + ((size_t)b * T + d0) * 8);
-    for (int v = tid; v < kPtDT * 2; v += kPtThreads)
-      reinterpret_cast<float4*>(Ac)[v] = (v < ndq * 2) ? __ldg(acsrc + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid < kPtDT) Cn[tid] = (tid < ndq) ? colnorm[(size_t)b * T + d0 + tid] : 1.f;
     for (int v = tid; v < wcount / 4; v += kPtThreads)
       reinterpret_cast<float4*>(Ws)[v] = __ldg(reinterpret_cast<const float4*>(packed + wbase) + v);
   }
@@ -186,12 +178,42 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - sbase));
 
-  // only the tiles that contain real pairs (D = 202 -> 13 tile columns, not 16; T = 202 -> 26 tile rows)
-  const int ntd = min(kPtDT / 16, (D - d0 + 15) / 16);
-  const int ntt = min(kPtTT / 8, (T - t0 + 7) / 8);
-  const int ntiles = ntd * ntt;
-
-  if (warp == 8) {
+  if (warp == 9) {
+    // ===================== producer: next item's operands into the free buffer =====================
+    for (int it = 0;; ++it) {
+      const int buf = it & 1;
+      if (it >= 2) mbar_wait(item_empty(buf), (uint32_t)((it >> 1) - 1) & 1u);
+      int item = 0;
+      if (lane == 0) item = atomicAdd(counter, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      float* bf = bufs + buf * PtBuf::floats;
+      int* desc = reinterpret_cast<int*>(bf + PtBuf::desc);
+      if (item >= nitems) {
+        if (lane == 0) {
+          desc[3] = 0;
+          mbar_arrive(item_full(buf));
+        }
+        break;
+      }
+      const int db = item % ndb, tb = (item / ndb) % ntb, b = item / (ndb * ntb);
+      const int t0 = tb * kPtTT, d0 = db * kPtDT;
+      const int nt = min(kPtTT, T - t0), nd = min(kPtDT, D - d0);
+      if (lane == 0) desc[0] = b, desc[1] = t0, desc[2] = d0, desc[3] = 1;
+      bf[PtBuf::cn + lane] = (lane < nd) ? __ldg(colnorm + (size_t)b * T + d0 + lane) : 1.f;
+      __syncwarp();
+      const uint32_t bu = bufs_u32 + (uint32_t)(buf * PtBuf::floats) * 4u;
+      if (lane == 0) {
+        mbar_expect_tx(item_full(buf), (uint32_t)(nt + nd) * (kProj + 8) * 4u);
+        pt_bulk_load(bu + PtBuf::ps * 4, proj_prev + ((size_t)b * T + t0) * kProj, (uint32_t)nt * kProj * 4u, item_full(buf));
+        pt_bulk_load(bu + PtBuf::auxp * 4, aux_prev + ((size_t)b * T + t0) * 8, (uint32_t)nt * 32u, item_full(buf));
+        pt_bulk_load(bu + PtBuf::auxc * 4, aux_cur + ((size_t)b * T + d0) * 8, (uint32_t)nd * 32u, item_full(buf));
+      }
+      __syncwarp();
+      if (lane < nd)   // PROJ_CUR_T rows into rows padded to 148 floats
+        pt_bulk_load(bu + (PtBuf::qs + lane * kPtQStride) * 4, proj_cur_t + ((size_t)b * T + d0 + lane) * kProj,
+                     kProj * 4u, item_full(buf));
+    }
+  } else if (warp == 8) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       // B images: [k chunk][n][16 bytes]; chunk stride (LBO) = N*16 bytes, 8-row group stride (SBO) = 128 bytes
@@ -224,20 +246,29 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
           }
         }
       };
-      for (int tile = 0; tile < ntiles; ++tile) {
-        const uint32_t ph = tile & 1;
-        mbar_wait(bar_a(0), ph);
-        tc_fence_after();
-        run(BF16 ? 2 : 4, 16, idesc16, kColDDet, kColDetHi, kColDetLo, off_c_hi, off_c_lo);   // fuse_det.2, K = 32
-        mma_commit(bar_d(0));
-        mbar_wait(bar_a(1), ph);
-        tc_fence_after();
-        run(BF16 ? 3 : 5, 32, idesc32, kColDShp, kColShpHi, kColShpLo, off_a_hi, off_a_lo);   // fuse_shape.2, K = 40
-        mma_commit(bar_d(1));
-        mbar_wait(bar_a(2), ph);
-        tc_fence_after();
-        run(BF16 ? 5 : 9, 32, idesc32, kColDCof, kColCofHi, kColCofLo, off_b_hi, off_b_lo);   // res_coeff.2, K = 72
-        mma_commit(bar_d(2));
+      uint32_t seq = 0;
+      for (int it = 0;; ++it) {
+        const int buf = it & 1;
+        mbar_wait(item_full(buf), (uint32_t)(it >> 1) & 1u);
+        const volatile int* desc = reinterpret_cast<const volatile int*>(bufs + buf * PtBuf::floats + PtBuf::desc);
+        if (desc[3] == 0) break;
+        const int t0 = desc[1], d0 = desc[2];
+        const int ntiles = min(kPtDT / 16, (D - d0 + 15) / 16) * min(kPtTT / 8, (T - t0 + 7) / 8);
+        for (int tile = 0; tile < ntiles; ++tile, ++seq) {
+          const uint32_t ph = seq & 1;
+          mbar_wait(bar_a(0), ph);
+          tc_fence_after();
+          run(BF16 ? 2 : 4, 16, idesc16, kColDDet, kColDetHi, kColDetLo, off_c_hi, off_c_lo);   // fuse_det.2, K = 32
+          mma_commit(bar_d(0));
+          mbar_wait(bar_a(1), ph);
+          tc_fence_after();
+          run(BF16 ? 3 : 5, 32, idesc32, kColDShp, kColShpHi, kColShpLo, off_a_hi, off_a_lo);   // fuse_shape.2, K = 40
+          mma_commit(bar_d(1));
+          mbar_wait(bar_a(2), ph);
+          tc_fence_after();
+          run(BF16 ? 5 : 9, 32, idesc32, kColDCof, kColCofHi, kColCofLo, off_b_hi, off_b_lo);   // res_coeff.2, K = 72
+          mma_commit(bar_d(2));
+        }
       }
     }
   } else {
@@ -260,10 +291,28 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
     const float* W3c = Ws + (P.l3c - wbase);
     const float* B3c = Ws + (P.l3c_b - wbase);
 
-    for (int tile = 0; tile < ntiles; ++tile) {
-      const uint32_t ph = tile & 1;
-      const int tl = (tile / ntd) * 8 + ti;     // row of the staged PROJ_PREV block
-      const int dl = (tile % ntd) * 16 + di;    // row of the staged PROJ_CUR block
+    uint32_t seq = 0;
+    for (int it = 0;; ++it) {
+      const int buf = it & 1;
+      mbar_wait(item_full(buf), (uint32_t)(it >> 1) & 1u);
+      const float* bf = bufs + buf * PtBuf::floats;
+      const int* desc = reinterpret_cast<const int*>(bf + PtBuf::desc);
+      if (desc[3] == 0) break;
+      const int b = desc[0], t0 = desc[1], d0 = desc[2];
+      const float* Ps = bf + PtBuf::ps;
+      const float* Qs = bf + PtBuf::qs;
+      const float* Ap = bf + PtBuf::auxp;
+      const float* Ac = bf + PtBuf::auxc;
+      const float* Cn = bf + PtBuf::cn;
+      // only the tiles that contain real pairs
+      const int ntd = min(kPtDT / 16, (D - d0 + 15) / 16);
+      const int ntt = min(kPtTT / 8, (T - t0 + 7) / 8);
+      const int ntiles = ntd * ntt;
+
+    for (int tile = 0; tile < ntiles; ++tile, ++seq) {
+      const uint32_t ph = seq & 1;
+      const int tl = ((ntd == 2) ? (tile >> 1) : tile) * 8 + ti;     // row of the staged PROJ_PREV block
+      const int dl = ((ntd == 2) ? (tile & 1) : 0) * 16 + di;        // row of the staged PROJ_CUR block
       const int t = t0 + tl;
       const float* prow = Ps + tl * kProj;
       const float* qrow = Qs + dl * kPtQStride;
@@ -323,7 +372,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
           omega = fmaf(h, w.z, omega);
         }
         mbar_wait(bar_s, ph);
-        const float shape = Sh[(tile & 1) * 128 + r];
+        const float shape = Sh[(seq & 1) * 128 + r];
         const float out = __fadd_rn(__fadd_rn(__fmul_rn(alpha, fused), __fmul_rn(beta, res_dist)),
                                     __fmul_rn(omega, shape));
         const int d = d0 + dl;
@@ -380,13 +429,15 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         float sres = B4a[0];
 #pragma unroll
         for (int k = 0; k < 10; ++k) sres = fmaf(relu_f(a3[k]), W4a[k], sres);
-        Sh[(tile & 1) * 128 + r] = sres;
+        Sh[(seq & 1) * 128 + r] = sres;
         mbar_arrive(bar_s);   // mbarrier arrive has release semantics: the shared-memory write above is visible
         // the res_coeff MMAs read this group's TMEM columns: they must retire before the next tile rewrites them
         mbar_wait(bar_d(2), ph);
         tc_fence_after();
       }
-    }
+    }   // tiles of the item
+      mbar_arrive(item_empty(buf));   // this thread no longer reads the item buffer
+    }     // items
   }
   tc_fence_before();
   __syncthreads();
@@ -406,16 +457,23 @@ int launch_pairwise_tc(const float* packed, int B, int M, float* ws, const WsLay
   const int T = M + 2;
   const bool bf16 = variant == 2;
   const size_t bimg = (bf16 ? (P.tc16_end - P.tc16_begin) : (P.tc32_end - P.tc32_begin)) * sizeof(float);
-  const size_t smem = 128 + bimg + 128 + sizeof(float) * (PtSmem::w + (P.pair_end - P.l2a));
+  const size_t smem = 128 + bimg + 128 + sizeof(float) * ((P.pair_end - P.l2a) + 256 + 2 * PtBuf::floats);
   static bool configured[2] = {false, false};
+  static int sm_count = 0;
   if (!configured[bf16]) {
     if (bf16)
       SHASTA_CUDA(cudaFuncSetAttribute(pairwise_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else
       SHASTA_CUDA(cudaFuncSetAttribute(pairwise_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    SHASTA_CUDA(cudaGetDevice(&dev));
+    SHASTA_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     configured[bf16] = true;
   }
-  dim3 grid((T + kPtDT - 1) / kPtDT, (T + kPtTT - 1) / kPtTT, B);
+  const long long nitems = (long long)B * ((T + kPtTT - 1) / kPtTT) * ((T + kPtDT - 1) / kPtDT);
+  const int grid = (int)(nitems < 2LL * sm_count ? nitems : 2LL * sm_count);   // persistent: two CTAs per SM
+  int* counter = reinterpret_cast<int*>(ws + L.off[SHASTA_WS_COUNTERS]);
+  SHASTA_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
   const float* pp = ws + L.off[SHASTA_WS_PROJ_PREV];
   const float* pc = ws + L.off[SHASTA_WS_PROJ_CUR_T];
   const float* ap = ws + L.off[SHASTA_WS_AUX_PREV];
@@ -423,9 +481,9 @@ int launch_pairwise_tc(const float* packed, int B, int M, float* ws, const WsLay
   const float* cn = ws + L.off[SHASTA_WS_COLNORM];
   float* res = ws + L.off[SHASTA_WS_RESIDUAL];
   if (bf16)
-    pairwise_tc_kernel<true><<<grid, kPtThreads, smem, s>>>(packed, P, B, M, pp, pc, ap, ac, cn, res);
+    pairwise_tc_kernel<true><<<grid, kPtThreads, smem, s>>>(packed, P, B, M, pp, pc, ap, ac, cn, res, counter);
   else
-    pairwise_tc_kernel<false><<<grid, kPtThreads, smem, s>>>(packed, P, B, M, pp, pc, ap, ac, cn, res);
+    pairwise_tc_kernel<false><<<grid, kPtThreads, smem, s>>>(packed, P, B, M, pp, pc, ap, ac, cn, res, counter);
   SHASTA_CHECK_LAUNCH("pairwise_tc_kernel");
   return 0;
 }
