@@ -146,6 +146,9 @@ __host__ inline AffTcPlan aff_tc_plan(int M) {
   return A;
 }
 
+constexpr int kProjTcKs = 16;                 // K rows per weight piece of the tensor-core projection kernel
+constexpr int kProjTcPieces = kF / kProjTcKs;  // 20
+
 // ---- packed small-layer weights (float offsets) ------------------------------------------------
 // All matrices are stored k-major ("transposed": [in][out]) so that consecutive threads / vector lanes
 // read consecutive outputs.
@@ -176,6 +179,9 @@ struct PackLayout {
   size_t tc16_end;
   // aff on tensor cores (aff_tc.cu; only when D = M+2 <= kAffTcMaxD): weight pieces of AffTcPlan, each [hi image | lo image]
   size_t aff_tc_begin, aff_tc_floats;   // aff_tc_floats == 0 when the tensor-core aff kernel is unavailable for this M
+  // first-layer projections on tensor cores (project_tc.cu): per side (0 prev, 1 cur) kProjTcPieces pieces of
+  // kProjTcKs K rows, each [hi image | lo image] of the [320][112] projection matrix in the canonical layout
+  size_t proj_tc[2];
   size_t total;       // floats
 };
 
@@ -231,6 +237,7 @@ __host__ inline PackLayout pack_layout(int M) {
   P.tc16_end = o;
   P.aff_tc_floats = aff_tc_plan(M).floats;
   P.aff_tc_begin = take(P.aff_tc_floats);
+  for (int sd = 0; sd < 2; ++sd) P.proj_tc[sd] = take((size_t)2 * kF * kProjShape);
   P.total = o;
   return P;
 }

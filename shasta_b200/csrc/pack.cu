@@ -43,6 +43,19 @@ __global__ void umma_b_slice_kernel(float* __restrict__ img, const float* __rest
   img[(size_t)n_pad * kc + o] = v - h;
 }
 
+// same image from a k-major source matrix src[k][n] (ld = n_src): piece [k0, k0 + kc) x n_pad
+__global__ void umma_b_slice_kmajor_kernel(float* __restrict__ img, const float* __restrict__ src, int n_src, int n_pad,
+                                           int k0, int kc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pad * kc) return;
+  const int n = idx % n_pad, kk = idx / n_pad;
+  const float v = (n < n_src) ? src[(size_t)(k0 + kk) * n_src + n] : 0.f;
+  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  const size_t o = (size_t)(kk / 4) * (n_pad * 4) + n * 4 + (kk % 4);
+  img[o] = h;
+  img[(size_t)n_pad * kc + o] = v - h;
+}
+
 static int bslice(float* img, const float* src, int src_ld, int n_valid, int k_valid, int n_pad, int k0, int kc,
                   cudaStream_t s) {
   umma_b_slice_kernel<<<(n_pad * kc + 255) / 256, 256, 0, s>>>(img, src, src_ld, n_valid, k_valid, n_pad, k0, kc);
@@ -136,6 +149,14 @@ int launch_pack(const shasta_params_t& p, float* packed, cudaStream_t s) {
       if (rc2) return rc2;
     }
   }
+  // tensor-core images of the two [320][112] first-layer projection matrices (built from the k-major copies above)
+  for (int sd = 0; sd < 2; ++sd)
+    for (int pc = 0; pc < kProjTcPieces; ++pc) {
+      umma_b_slice_kmajor_kernel<<<(kProjShape * kProjTcKs + 255) / 256, 256, 0, s>>>(
+          packed + P.proj_tc[sd] + (size_t)pc * 2 * kProjTcKs * kProjShape, packed + (sd ? P.p1_cur : P.p1_prev),
+          kProjShape, kProjShape, pc * kProjTcKs, kProjTcKs);
+      SHASTA_CHECK_LAUNCH("umma_b_slice_kmajor_kernel");
+    }
   // tensor-core operand images of fuse_shape.2 (20x40), res_coeff.2 (18x72), fuse_det.2 (8x32)
   int rc = bimage(packed + P.tc32_w2a_hi, packed + P.tc32_w2a_lo, packed + P.tc16_w2a, p.fuse_shape_w[1], 40, 20, 32, 40, s);
   if (rc) return rc;

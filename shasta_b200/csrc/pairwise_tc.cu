@@ -46,7 +46,6 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4])
                "r"(v[2]), "r"(v[3])
                : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -182,7 +181,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
     // ===================== producer: next item's operands into the free buffer =====================
     for (int it = 0;; ++it) {
       const int buf = it & 1;
-      if (it >= 2) mbar_wait(item_empty(buf), (uint32_t)((it >> 1) - 1) & 1u);
+      if (it >= 2) mbar_wait_sleep(item_empty(buf), (uint32_t)((it >> 1) - 1) & 1u);
       int item = 0;
       if (lane == 0) item = atomicAdd(counter, 1);
       item = __shfl_sync(0xffffffffu, item, 0);
@@ -249,22 +248,22 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
       uint32_t seq = 0;
       for (int it = 0;; ++it) {
         const int buf = it & 1;
-        mbar_wait(item_full(buf), (uint32_t)(it >> 1) & 1u);
+        mbar_wait_sleep(item_full(buf), (uint32_t)(it >> 1) & 1u);
         const volatile int* desc = reinterpret_cast<const volatile int*>(bufs + buf * PtBuf::floats + PtBuf::desc);
         if (desc[3] == 0) break;
         const int t0 = desc[1], d0 = desc[2];
         const int ntiles = min(kPtDT / 16, (D - d0 + 15) / 16) * min(kPtTT / 8, (T - t0 + 7) / 8);
         for (int tile = 0; tile < ntiles; ++tile, ++seq) {
           const uint32_t ph = seq & 1;
-          mbar_wait(bar_a(0), ph);
+          mbar_wait_sleep(bar_a(0), ph);
           tc_fence_after();
           run(BF16 ? 2 : 4, 16, idesc16, kColDDet, kColDetHi, kColDetLo, off_c_hi, off_c_lo);   // fuse_det.2, K = 32
           mma_commit(bar_d(0));
-          mbar_wait(bar_a(1), ph);
+          mbar_wait_sleep(bar_a(1), ph);
           tc_fence_after();
           run(BF16 ? 3 : 5, 32, idesc32, kColDShp, kColShpHi, kColShpLo, off_a_hi, off_a_lo);   // fuse_shape.2, K = 40
           mma_commit(bar_d(1));
-          mbar_wait(bar_a(2), ph);
+          mbar_wait_sleep(bar_a(2), ph);
           tc_fence_after();
           run(BF16 ? 5 : 9, 32, idesc32, kColDCof, kColCofHi, kColCofLo, off_b_hi, off_b_lo);   // res_coeff.2, K = 72
           mma_commit(bar_d(2));
@@ -294,7 +293,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
     uint32_t seq = 0;
     for (int it = 0;; ++it) {
       const int buf = it & 1;
-      mbar_wait(item_full(buf), (uint32_t)(it >> 1) & 1u);
+      mbar_wait_sleep(item_full(buf), (uint32_t)(it >> 1) & 1u);
       const float* bf = bufs + buf * PtBuf::floats;
       const int* desc = reinterpret_cast<const int*>(bf + PtBuf::desc);
       if (desc[3] == 0) break;
@@ -327,8 +326,8 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         mbar_arrive(bar_a(0));
 
         // both first MMAs must have retired before their TMEM columns are recycled for res_coeff
-        mbar_wait(bar_d(0), ph);
-        mbar_wait(bar_d(1), ph);
+        mbar_wait_sleep(bar_d(0), ph);
+        mbar_wait_sleep(bar_d(1), ph);
         tc_fence_after();
         uint32_t vd[8];
         tmem_ld8(lane_base + kColDDet, vd);
@@ -354,7 +353,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         const float res_dist = __fadd_rn(__fadd_rn(dist, dim), rot);
 
         // res_coeff epilogue 18 -> 3
-        mbar_wait(bar_d(2), ph);
+        mbar_wait_sleep(bar_d(2), ph);
         tc_fence_after();
         uint32_t v[16], v2[8];
         tmem_ld16(lane_base + kColDCof, v);
@@ -371,7 +370,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
           beta = fmaf(h, w.y, beta);
           omega = fmaf(h, w.z, omega);
         }
-        mbar_wait(bar_s, ph);
+        mbar_wait_sleep(bar_s, ph);
         const float shape = Sh[(seq & 1) * 128 + r];
         const float out = __fadd_rn(__fadd_rn(__fmul_rn(alpha, fused), __fmul_rn(beta, res_dist)),
                                     __fmul_rn(omega, shape));
@@ -390,8 +389,8 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         tc_fence_before();
         mbar_arrive(bar_a(1));
 
-        mbar_wait(bar_d(0), ph);
-        mbar_wait(bar_d(1), ph);
+        mbar_wait_sleep(bar_d(0), ph);
+        mbar_wait_sleep(bar_d(1), ph);
         tc_fence_after();
         uint32_t v[16], v2[8];
         tmem_ld16(lane_base + kColDShp, v);
@@ -432,7 +431,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         Sh[(seq & 1) * 128 + r] = sres;
         mbar_arrive(bar_s);   // mbarrier arrive has release semantics: the shared-memory write above is visible
         // the res_coeff MMAs read this group's TMEM columns: they must retire before the next tile rewrites them
-        mbar_wait(bar_d(2), ph);
+        mbar_wait_sleep(bar_d(2), ph);
         tc_fence_after();
       }
     }   // tiles of the item

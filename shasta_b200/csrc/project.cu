@@ -23,7 +23,7 @@ project_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, int
                const float* __restrict__ box_cur, const float* __restrict__ box_prev, float* __restrict__ proj_prev,
                float* __restrict__ proj_cur, float* __restrict__ proj_cur_t, float* __restrict__ aux_prev,
                float* __restrict__ aux_cur,
-               float* __restrict__ colnorm, float* __restrict__ det_boxes_inout) {
+               float* __restrict__ colnorm, float* __restrict__ det_boxes_inout, int do_gemm) {
   const int T = M + 2;
   const int DP = proj_cur_stride(M);
   __shared__ __align__(16) float fs[kProjObjPerCta][kF];  // 40 KB
@@ -65,8 +65,9 @@ project_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, int
   const float* __restrict__ box = side ? box_cur : box_prev;
   float* __restrict__ aux = side ? aux_cur : aux_prev;
 
-  // stage features (coalesced float4 copy, zero-filled past the last object)
-  {
+  // stage features (coalesced float4 copy, zero-filled past the last object); skipped when the tensor-core kernel
+  // (project_tc.cu) computes the projections and this launch only produces AUX_*
+  if (do_gemm) {
     const float4* src = reinterpret_cast<const float4*>(feat + ((size_t)b * T + o0) * kF);
     float4* dst = reinterpret_cast<float4*>(&fs[0][0]);
     const int nvec = nobj * (kF / 4);
@@ -89,6 +90,7 @@ project_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, int
     }
     bs[o][0] = bx[0], bs[o][1] = bx[1], bs[o][2] = bx[2], bs[o][3] = 0.f;
   }
+  if (!do_gemm) return;
   __syncthreads();
 
   const int g = threadIdx.x >> 6;    // object group
@@ -169,9 +171,13 @@ project_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, int
   }
 }
 
+int launch_project_tc(const float* packed, int B, int M, float* ws, const WsLayout& L, cudaStream_t s);  // project_tc.cu
+
 int launch_project(const float* packed, int B, int M, float* ws, const WsLayout& L, float* det_boxes_inout,
                    cudaStream_t s) {
   const int T = M + 2;
+  const int mode = g_options[SHASTA_OPT_PROJECT_PATH];
+  const bool tc = mode == 2 || (mode == 0 && (long long)B * T >= 128);   // below one row tile the FFMA kernel wins
   const int tiles = (T + kProjObjPerCta - 1) / kProjObjPerCta;
   const int nproj = 2 * B * tiles;
   project_kernel<<<nproj + B, kProjThreads, 0, s>>>(
@@ -179,8 +185,9 @@ int launch_project(const float* packed, int B, int M, float* ws, const WsLayout&
       ws + L.off[SHASTA_WS_BOX_CUR], ws + L.off[SHASTA_WS_BOX_PREV], ws + L.off[SHASTA_WS_PROJ_PREV],
       ws + L.off[SHASTA_WS_PROJ_CUR], ws + L.off[SHASTA_WS_PROJ_CUR_T], ws + L.off[SHASTA_WS_AUX_PREV],
       ws + L.off[SHASTA_WS_AUX_CUR],
-      ws + L.off[SHASTA_WS_COLNORM], det_boxes_inout);
+      ws + L.off[SHASTA_WS_COLNORM], det_boxes_inout, tc ? 0 : 1);
   SHASTA_CHECK_LAUNCH("project_kernel");
+  if (tc) return launch_project_tc(packed, B, M, ws, L, s);
   return 0;
 }
 

@@ -213,8 +213,16 @@ def _fill_aug(st, c, data, g):
     return prev_aug, det_aug, f_prev, f_cur
 
 
+@pytest.fixture(params=[1, 2], ids=["ffma", "tcgen05"])
+def project_path(request):
+    lib = _cabi.lib()
+    lib.shasta_set_option(_cabi.OPT_PROJECT_PATH, request.param)
+    yield request.param
+    lib.shasta_set_option(_cabi.OPT_PROJECT_PATH, 0)
+
+
 @pytest.mark.parametrize("name", golden_names())
-def test_project_and_pairwise_stage(name):
+def test_project_and_pairwise_stage(name, project_path):
     c, pc_start, data, weights, g = load_golden(name)
     B, M = c["B"], c["M"]
     T = M + 2
