@@ -131,7 +131,9 @@ enum shasta_region {
   SHASTA_WS_FEATLO_CUR = 21, /* (B,320M) tf32 low parts x - tf32_trunc(x) of the gathered current features   */
   SHASTA_WS_FEATLO_PREV = 22, /* same for the previous frame: B operands of the 3xTF32 anchors GEMM (TMA-loaded) */
   SHASTA_WS_COUNTERS = 23,   /* 64 ints: work-item counters of the persistent kernels */
-  SHASTA_WS_NUM_REGIONS = 24
+  SHASTA_WS_HID = 24,        /* (4,B,5M) hidden activations of aug_shape.i (operand of the tcgen05 output GEMM) */
+  SHASTA_WS_HIDLO = 25,      /* their tf32 low parts */
+  SHASTA_WS_NUM_REGIONS = 26
 };
 
 /* Runtime options (process-wide, not thread-safe; meant for tests and benchmarks).

@@ -126,10 +126,10 @@ __global__ void __launch_bounds__(256)
 anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, const float* __restrict__ det_boxes,
                      const float* __restrict__ prev_boxes, int B, int M, float* __restrict__ feat_cur,
                      float* __restrict__ feat_prev, float* __restrict__ box_cur, float* __restrict__ box_prev,
-                     float* __restrict__ anchor_box, int nbx, float* __restrict__ raw_xy) {
+                     float* __restrict__ anchor_box, int nbx, float* __restrict__ raw_xy, int role0) {
   extern __shared__ __align__(16) float sm[];
   const int T = M + 2, N5 = 5 * M, H7 = (7 * M) / 32;
-  const int role = blockIdx.x;
+  const int role = blockIdx.x + role0;
   const int bg0 = blockIdx.z * kFinishBG;
   const int nb = min(kFinishBG, B - bg0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -160,57 +160,86 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
 
   if (role >= 5) {
     // ---- aug_dets.i : Linear(7M -> 7M/32) + ReLU + Linear(-> 7), abs on dims 3:6        shasta.py:69-76,260-267
-    if (blockIdx.y != 0) return;
     const int i = role - 5;
     const float* src = (i < 2) ? det_boxes : prev_boxes;  // boxes BEFORE back-projection
     const int K7 = 7 * M;
-    // as many frame pairs at once as fit in the shared memory this launch was given (nbx passed by the host)
-    float* xb = sm;                // [nbx][K7] flat (M,7) boxes
-    float* hd = sm + nbx * K7;     // [nbx][H7]
-    for (int bb = 0; bb < nb; bb += nbx) {
-      const int nb2 = min(nbx, nb - bb);
+    float* xb = sm;        // [K7] flat (M,7) boxes of one frame pair
+    float* hd = sm + K7;   // [H7]
+    const bool vec = (M % 4 == 0) && (((uintptr_t)a.dw0[i] & 15) == 0);
+    // the y slices of the grid share the frame pairs of the group: one frame pair at a time per CTA
+    for (int g = blockIdx.y; g < nb; g += gridDim.y) {
+      const int b = bg0 + g;
       __syncthreads();
-      for (int idx = threadIdx.x; idx < nb2 * K7; idx += blockDim.x) {
-        const int g = idx / K7, k = idx % K7;
-        xb[idx] = src[((size_t)(bg0 + bb + g) * M + k / 7) * 11 + (k % 7)];
+      const float* rows = src + (size_t)b * M * 11;   // coalesced over the 11-float rows, columns 7..10 dropped
+      for (int idx = threadIdx.x; idx < M * 11; idx += blockDim.x) {
+        const int m = idx / 11, c = idx - m * 11;
+        const float v = __ldg(rows + idx);
+        if (c < 7) xb[m * 7 + c] = v;
       }
-      for (int idx = nb2 * K7 + threadIdx.x; idx < nbx * K7; idx += blockDim.x) xb[idx] = 0.f;
       __syncthreads();
-      for (int h = warp; h < H7; h += 8) {
-        const float* wr = a.dw0[i] + (size_t)h * K7;
-        float acc[8];
+      // a warp owns hidden rows warp, warp+8, ... and works on kRH of them at a time: up to 2*kRH 16-byte weight loads
+      // in flight per lane (the loop is L2-latency bound: the whole layer is 7M x 7M/32 floats)
+      constexpr int kRH = 6;
+      for (int hb = warp; hb < H7; hb += 8 * kRH) {
+        float acc[kRH];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) acc[g] = 0.f;
-#pragma unroll 4
-        for (int k = lane; k < K7; k += 32) {
-          const float wv = __ldg(wr + k);
+        for (int j = 0; j < kRH; ++j) acc[j] = 0.f;
+        if (vec) {
+          const int K4 = K7 / 4;
+          const float4* x4 = reinterpret_cast<const float4*>(xb);
+          for (int k0 = lane; k0 < K4; k0 += 64) {
+            const bool two = k0 + 32 < K4;
+            const float4 x0 = x4[k0], x1 = two ? x4[k0 + 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 w0[kRH], w1[kRH];
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            if (g < nbx) acc[g] = fmaf(wv, xb[g * K7 + k], acc[g]);
-        }
-        const float bh = a.db0[i][h];
+            for (int j = 0; j < kRH; ++j) {
+              const int h = hb + 8 * j;
+              const float4* w4 = reinterpret_cast<const float4*>(a.dw0[i] + (size_t)min(h, H7 - 1) * K7);
+              w0[j] = __ldg(w4 + k0);
+              w1[j] = two ? __ldg(w4 + k0 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (g < nbx) {
-            const float v = warp_sum(acc[g]);
-            if (lane == 0) hd[g * H7 + h] = fmaxf(v + bh, 0.f);
+            for (int j = 0; j < kRH; ++j) {
+              acc[j] = fmaf(w0[j].x, x0.x, acc[j]), acc[j] = fmaf(w0[j].y, x0.y, acc[j]);
+              acc[j] = fmaf(w0[j].z, x0.z, acc[j]), acc[j] = fmaf(w0[j].w, x0.w, acc[j]);
+              acc[j] = fmaf(w1[j].x, x1.x, acc[j]), acc[j] = fmaf(w1[j].y, x1.y, acc[j]);
+              acc[j] = fmaf(w1[j].z, x1.z, acc[j]), acc[j] = fmaf(w1[j].w, x1.w, acc[j]);
+            }
+          }
+        } else {
+          for (int k = lane; k < K7; k += 32) {
+            const float x = xb[k];
+            float w[kRH];
+#pragma unroll
+            for (int j = 0; j < kRH; ++j) w[j] = __ldg(a.dw0[i] + (size_t)min(hb + 8 * j, H7 - 1) * K7 + k);
+#pragma unroll
+            for (int j = 0; j < kRH; ++j) acc[j] = fmaf(w[j], x, acc[j]);
           }
         }
+#pragma unroll
+        for (int j = 0; j < kRH; ++j) {
+          const int h = hb + 8 * j;
+          const float v = warp_sum(acc[j]);
+          if (lane == 0 && h < H7) hd[h] = fmaxf(v + a.db0[i][h], 0.f);
+        }
       }
       __syncthreads();
-      if (threadIdx.x < nb2 * 8) {
-        const int g = threadIdx.x >> 3, c = threadIdx.x & 7;
-        const int b = bg0 + bb + g;
-        float v = 0.f;
-        if (c < 7) {
-          float acc = 0.f;
-          for (int h = 0; h < H7; ++h) acc = fmaf(a.dw2[i][c * H7 + h], hd[g * H7 + h], acc);
-          v = acc + a.db2[i][c];
-          if (c >= 3 && c < 6) v = fabsf(v);
-          anchor_box[((size_t)b * 4 + i) * 7 + c] = v;
+      if (warp < 8) {   // output c = warp (7 outputs + one zero pad column), lanes over the hidden units
+        const int cc = warp;
+        float acc = 0.f;
+        if (cc < 7)
+          for (int h = lane; h < H7; h += 32) acc = fmaf(__ldg(a.dw2[i] + cc * H7 + h), hd[h], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          float v = 0.f;
+          if (cc < 7) {
+            v = acc + a.db2[i][cc];
+            if (cc >= 3 && cc < 6) v = fabsf(v);
+            anchor_box[((size_t)b * 4 + i) * 7 + cc] = v;
+          }
+          float* bdst = (i < 2) ? box_prev : box_cur;
+          bdst[((size_t)b * T + M + (i & 1)) * 8 + cc] = v;
         }
-        float* bdst = (i < 2) ? box_prev : box_cur;
-        bdst[((size_t)b * T + M + (i & 1)) * 8 + c] = v;
       }
     }
     return;
@@ -275,6 +304,8 @@ int anchor_tc2_splits(int M, int B);  // anchors_tc2.cu
 int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, const float* feat_prev,
                              float* featlo_cur, float* featlo_prev, bool featlo_ready, int B, int S, float* part,
                              cudaStream_t s);
+int launch_anchor_out_tc(const shasta_params_t& p, const float* part, int S, int B, float* hid, float* hidlo,
+                         float* feat_cur, float* feat_prev, cudaStream_t s);
 int anchor_tc_splits(int M, int B);  // anchors_tc.cu
 int launch_anchor_hidden_tc(const shasta_params_t& p, const float* feat_cur, const float* feat_prev, int B, int S,
                             float* part, cudaStream_t s);
@@ -303,7 +334,10 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   // tensor-core GEMM wins.  option 0: 0 = auto, 1 = streaming kernel, 2 = tcgen05 kernel, 3 = first-gen tcgen05
   const int mode = g_options[SHASTA_OPT_ANCHOR_PATH];
   int S;
+  bool out_tc = false;   // aug_shape.i.2 on tensor cores too (TMA needs 16-byte row pitch: 5M floats, M % 4 == 0)
   if (mode == 2 || (mode == 0 && B > 8)) {        // tcgen05, weights on the M side, TMEM-resident low parts
+    out_tc = (M % 4) == 0;
+    for (int i = 0; i < 4; ++i) out_tc = out_tc && (((uintptr_t)p.aug_shape_w2[i] & 15) == 0);
     S = anchor_tc2_splits(M, B);
     int rc = launch_anchor_hidden_tc2(p, feat_cur, feat_prev, ws + L.off[SHASTA_WS_FEATLO_CUR],
                                       ws + L.off[SHASTA_WS_FEATLO_PREV], featlo_ready, B, S, part, s);
@@ -328,6 +362,11 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
     SHASTA_CHECK_LAUNCH("anchor_hidden_kernel");
   }
   if (mid) cudaEventRecord(mid, s);
+  if (out_tc) {
+    int rc = launch_anchor_out_tc(p, part, S, B, ws + L.off[SHASTA_WS_HID], ws + L.off[SHASTA_WS_HIDLO], feat_cur,
+                                  feat_prev, s);
+    if (rc) return rc;
+  }
 
   AnchorFinishArgs a;
   for (int i = 0; i < 4; ++i) {
@@ -357,16 +396,17 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   }
   const int groups = (B + BG - 1) / BG;
   const int slices = (groups >= 16) ? 2 : (groups >= 6 ? 5 : 10);  // 320 outputs = 10 passes of 32 rows
-  dim3 fgrid(9, slices, groups);  // roles: 0-3 anchor shapes, 4 box copy, 5-8 anchor boxes
+  const int role0 = out_tc ? 4 : 0;
+  dim3 fgrid(9 - role0, slices, groups);  // roles: 0-3 anchor shapes, 4 box copy, 5-8 anchor boxes
   float* bc = ws + L.off[SHASTA_WS_BOX_CUR];
   float* bp = ws + L.off[SHASTA_WS_BOX_PREV];
   float* ab = ws + L.off[SHASTA_WS_ANCHOR_BOX];
   if (BG == 8)
     anchor_finish_kernel<8><<<fgrid, 256, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev, bc,
-                                                     bp, ab, nbx, ws + L.off[SHASTA_WS_RAW_XY]);
+                                                     bp, ab, nbx, ws + L.off[SHASTA_WS_RAW_XY], role0);
   else
     anchor_finish_kernel<4><<<fgrid, 256, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev, bc,
-                                                     bp, ab, nbx, ws + L.off[SHASTA_WS_RAW_XY]);
+                                                     bp, ab, nbx, ws + L.off[SHASTA_WS_RAW_XY], role0);
   SHASTA_CHECK_LAUNCH("anchor_finish_kernel");
   return 0;
 }

@@ -45,8 +45,20 @@ struct T2Cfg {
 
 struct AnchorT2Maps {
   CUtensorMap w[4];  // aug_shape.i.0.weight (5M, 320M), box 32 x 128
-  CUtensorMap x[2];  // FEAT_CUR / FEAT_PREV as (B, 320M) with row stride (M+2)*320, box 32 x BN
-  CUtensorMap xlo[2];  // FEATLO_CUR / FEATLO_PREV (B, 320M) compact: the tf32 low parts of the same elements
+  CUtensorMap x[4];    // activations of anchor i as (B, K): FEAT_CUR / FEAT_PREV rows (stride (M+2)*320) or HID
+  CUtensorMap xlo[4];  // the tf32 low parts of the same elements (FEATLO_* / HIDLO), compact
+};
+
+// The same streaming GEMM serves both Linear layers of aug_shape.i:
+//   mode 0  aug_shape.i.0: W (5M x 320M), X = gathered features, output = split-K partial sums `part`
+//   mode 1  aug_shape.i.2: W (320 x 5M),  X = hidden activations, output = |acc + bias| written into the anchor
+//           row of the augmented feature array (shasta.py:241-247); S must be 1
+struct AnchorT2Job {
+  int B, nrows, kblocks, S, ntiles_n, raw_hi, dbg, mode;
+  float* part;
+  const float* bias[4];
+  float* out[4];
+  size_t out_bstride;
 };
 
 __device__ __forceinline__ void t2_tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
@@ -67,14 +79,15 @@ __device__ __forceinline__ void t2_mma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a,
 
 template <int BN>
 __global__ void __launch_bounds__(kT2Threads, 1)
-anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M, int S, int ntiles_n, int raw_hi,
-                         float* __restrict__ part, int dbg) {
+anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, const __grid_constant__ AnchorT2Job job) {
   using C = T2Cfg<BN>;
+  const int B = job.B, S = job.S, ntiles_n = job.ntiles_n, raw_hi = job.raw_hi, dbg = job.dbg;
+  float* __restrict__ part = job.part;
   const int nst = (dbg >> 12) > 0 ? min(dbg >> 12, C::kStages) : C::kStages;  // experiment: fewer pipeline stages
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N5 = 5 * M;
-  const int kblocks = (kF * M) / kT2BK;
+  const int N5 = job.nrows;
+  const int kblocks = job.kblocks;
   const int nt = blockIdx.x % ntiles_n, bt = blockIdx.x / ntiles_n;
   const int i = blockIdx.y, s = blockIdx.z;
   const int kb_beg = (int)((long long)kblocks * s / S), kb_end = (int)((long long)kblocks * (s + 1) / S);
@@ -94,7 +107,7 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.w[i]);
-    tma_prefetch_desc(&maps.x[i >> 1]);
+    tma_prefetch_desc(&maps.x[i]);
   }
   if (warp == 1 && lane == 0) {
     for (int st = 0; st < C::kStages; ++st) {
@@ -127,8 +140,8 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M
         mbar_expect_tx(full_bar(st), kT2WTile + 2 * C::kXTile);
         const int k0 = (kb_beg + kb) * kT2BK;
         tma_load_2d(sb, &maps.w[i], full_bar(st), k0, n0, kEvictFirst);                  // weights: streamed once
-        tma_load_2d(sb + kT2WTile, &maps.x[i >> 1], full_bar(st), k0, b0, kEvictLast);   // activations: reused
-        tma_load_2d(sb + kT2WTile + C::kXTile, &maps.xlo[i >> 1], full_bar(st), k0, b0, kEvictLast);
+        tma_load_2d(sb + kT2WTile, &maps.x[i], full_bar(st), k0, b0, kEvictLast);        // activations: reused
+        tma_load_2d(sb + kT2WTile + C::kXTile, &maps.xlo[i], full_bar(st), k0, b0, kEvictLast);
         if (++st == nst) st = 0, ph ^= 1;
       }
     }
@@ -269,10 +282,20 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, int B, int M
     // ---- epilogue: registers -> split-K partial sums, coalesced along the weight-row dimension
     const int n = n0 + r;
     if (n < N5) {
+      if (job.mode == 0) {
 #pragma unroll
-      for (int j = 0; j < BN; ++j) {
-        const int b = b0 + j;
-        if (b < B) part[(((size_t)s * B + b) * 4 + i) * N5 + n] = acc[j];
+        for (int j = 0; j < BN; ++j) {
+          const int b = b0 + j;
+          if (b < B) part[(((size_t)s * B + b) * 4 + i) * N5 + n] = acc[j];
+        }
+      } else {
+        const float bn_ = __ldg(job.bias[i] + n);
+        float* __restrict__ o = job.out[i] + n;
+#pragma unroll
+        for (int j = 0; j < BN; ++j) {
+          const int b = b0 + j;
+          if (b < B) o[(size_t)b * job.out_bstride] = fabsf(acc[j] + bn_);
+        }
       }
     }
   }
@@ -353,6 +376,24 @@ __global__ void feat_lo_kernel(const float* __restrict__ feat0, const float* __r
   }
 }
 
+static int t2_launch(const AnchorT2Maps& maps, const AnchorT2Job& job, int bn, int ntb, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    SHASTA_CUDA(cudaFuncSetAttribute(anchor_hidden_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     T2Cfg<64>::kSmemBytes));
+    SHASTA_CUDA(cudaFuncSetAttribute(anchor_hidden_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     T2Cfg<128>::kSmemBytes));
+    configured = true;
+  }
+  dim3 grid(job.ntiles_n * ntb, 4, job.S);
+  if (bn == 64)
+    anchor_hidden_tc2_kernel<64><<<grid, kT2Threads, T2Cfg<64>::kSmemBytes, s>>>(maps, job);
+  else
+    anchor_hidden_tc2_kernel<128><<<grid, kT2Threads, T2Cfg<128>::kSmemBytes, s>>>(maps, job);
+  SHASTA_CHECK_LAUNCH("anchor_hidden_tc2_kernel");
+  return 0;
+}
+
 int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, const float* feat_prev,
                              float* featlo_cur, float* featlo_prev, bool featlo_ready, int B, int S, float* part,
                              cudaStream_t s) {
@@ -363,37 +404,69 @@ int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, co
   for (int i = 0; i < 4; ++i) {
     int rc = make_map2(&maps.w[i], p.aug_shape_w0[i], N5, K, K, 128);
     if (rc) return rc;
+    rc = make_map2(&maps.x[i], (i < 2) ? feat_cur : feat_prev, (uint64_t)B, K, ld, (uint32_t)bn);
+    if (rc) return rc;
+    rc = make_map2(&maps.xlo[i], (i < 2) ? featlo_cur : featlo_prev, (uint64_t)B, K, K, (uint32_t)bn);
+    if (rc) return rc;
   }
-  int rc = make_map2(&maps.x[0], feat_cur, (uint64_t)B, K, ld, (uint32_t)bn);
-  if (rc) return rc;
-  rc = make_map2(&maps.x[1], feat_prev, (uint64_t)B, K, ld, (uint32_t)bn);
-  if (rc) return rc;
-  rc = make_map2(&maps.xlo[0], featlo_cur, (uint64_t)B, K, K, (uint32_t)bn);
-  if (rc) return rc;
-  rc = make_map2(&maps.xlo[1], featlo_prev, (uint64_t)B, K, K, (uint32_t)bn);
-  if (rc) return rc;
   if (!featlo_ready) {
     feat_lo_kernel<<<dim3(592, 2), 256, 0, s>>>(feat_cur, feat_prev, featlo_cur, featlo_prev, B, M);
     SHASTA_CHECK_LAUNCH("feat_lo_kernel");
   }
-  static bool configured = false;
-  if (!configured) {
-    SHASTA_CUDA(cudaFuncSetAttribute(anchor_hidden_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     T2Cfg<64>::kSmemBytes));
-    SHASTA_CUDA(cudaFuncSetAttribute(anchor_hidden_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     T2Cfg<128>::kSmemBytes));
-    configured = true;
+  AnchorT2Job job = {};
+  job.B = B, job.nrows = (int)N5, job.kblocks = (int)(K / kT2BK), job.S = S;
+  job.ntiles_n = (int)((N5 + kT2BM - 1) / kT2BM);
+  job.raw_hi = g_options[SHASTA_OPT_TC_RAW_HI], job.dbg = g_options[2], job.mode = 0, job.part = part;
+  return t2_launch(maps, job, bn, (B + bn - 1) / bn, s);
+}
+
+// hidden = relu(sum over split-K partials + bias) and its tf32 low part, as (4, B, 5M)      aug_shape.i.0 + ReLU
+struct AnchorBias4 {
+  const float* b[4];
+};
+__global__ void anchor_reduce_kernel(const float* __restrict__ part, int S, int B, int N5, AnchorBias4 bias,
+                                     float* __restrict__ hid, float* __restrict__ hidlo) {
+  const size_t total = (size_t)4 * B * N5;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % N5);
+    const int b = (int)((idx / N5) % B), i = (int)(idx / ((size_t)N5 * B));
+    float sum = 0.f;
+    for (int sp = 0; sp < S; ++sp) sum += part[(((size_t)sp * B + b) * 4 + i) * N5 + n];   // fixed order
+    const float h = fmaxf(sum + __ldg(bias.b[i] + n), 0.f);
+    hid[idx] = h;
+    hidlo[idx] = h - __uint_as_float(__float_as_uint(h) & 0xffffe000u);
   }
-  const int ntn = (int)((N5 + kT2BM - 1) / kT2BM), ntb = (B + bn - 1) / bn;
-  dim3 grid(ntn * ntb, 4, S);
-  const int raw_hi = g_options[SHASTA_OPT_TC_RAW_HI];
-  const int dbg = g_options[2];
-  if (bn == 64)
-    anchor_hidden_tc2_kernel<64><<<grid, kT2Threads, T2Cfg<64>::kSmemBytes, s>>>(maps, B, M, S, ntn, raw_hi, part, dbg);
-  else
-    anchor_hidden_tc2_kernel<128><<<grid, kT2Threads, T2Cfg<128>::kSmemBytes, s>>>(maps, B, M, S, ntn, raw_hi, part, dbg);
-  SHASTA_CHECK_LAUNCH("anchor_hidden_tc2_kernel");
-  return 0;
+}
+
+// aug_shape.i.2 + abs on tensor cores: the anchor rows of the augmented feature arrays
+int launch_anchor_out_tc(const shasta_params_t& p, const float* part, int S, int B, float* hid, float* hidlo,
+                         float* feat_cur, float* feat_prev, cudaStream_t s) {
+  const int M = p.max_obj, N5 = 5 * M, T = M + 2;
+  AnchorBias4 b0;
+  for (int i = 0; i < 4; ++i) b0.b[i] = p.aug_shape_b0[i];
+  anchor_reduce_kernel<<<592, 256, 0, s>>>(part, S, B, N5, b0, hid, hidlo);
+  SHASTA_CHECK_LAUNCH("anchor_reduce_kernel");
+  const int bn = t2_bn(B);
+  AnchorT2Maps maps;
+  for (int i = 0; i < 4; ++i) {
+    int rc = make_map2(&maps.w[i], p.aug_shape_w2[i], (uint64_t)kF, (uint64_t)N5, (uint64_t)N5, 128);
+    if (rc) return rc;
+    rc = make_map2(&maps.x[i], hid + (size_t)i * B * N5, (uint64_t)B, (uint64_t)N5, (uint64_t)N5, (uint32_t)bn);
+    if (rc) return rc;
+    rc = make_map2(&maps.xlo[i], hidlo + (size_t)i * B * N5, (uint64_t)B, (uint64_t)N5, (uint64_t)N5, (uint32_t)bn);
+    if (rc) return rc;
+  }
+  AnchorT2Job job = {};
+  job.B = B, job.nrows = kF, job.kblocks = (N5 + kT2BK - 1) / kT2BK, job.S = 1;
+  job.ntiles_n = (kF + kT2BM - 1) / kT2BM;
+  job.raw_hi = g_options[SHASTA_OPT_TC_RAW_HI], job.dbg = 0, job.mode = 1, job.part = nullptr;
+  for (int i = 0; i < 4; ++i) {
+    job.bias[i] = p.aug_shape_b2[i];
+    // newborn/fp extend the T axis of the previous frame, dead/fn the D axis of the current frame
+    job.out[i] = ((i < 2) ? feat_prev : feat_cur) + (size_t)(M + (i & 1)) * kF;
+  }
+  job.out_bstride = (size_t)T * kF;
+  return t2_launch(maps, job, bn, (B + bn - 1) / bn, s);
 }
 
 }  // namespace shasta
