@@ -220,11 +220,23 @@ SHASTA_API int shasta_aff_softmax_f32(const float* packed, int batch, int max_ob
 /* Whole path, shasta.py:231-325 from the 64-channel channels-last maps: bev/prev_bev (B,H,W,64),
  * det_boxes/prev_det_boxes (B,M,11). det_boxes[:,:,:2] is back-projected IN PLACE like the reference.
  * Outputs matched1 (B,M,M+2), matched2 (B,M+2,M); the anchors stay in the workspace (ANCHOR_BOX).
- * flags: bit0 = TMA-staged gather, bits 4-7 = pairwise variant, bit8 = record per-kernel events (profiling). */
+ * flags: bit0 = TMA-staged gather, bits 4-7 = pairwise variant, bit8 = record per-kernel events (profiling),
+ * bit9 = the gather already ran on this workspace (shasta_gather_pair_f32): start at the anchors stage. */
+#define SHASTA_FLAG_TMA_GATHER 0x1u
+#define SHASTA_FLAG_PROFILE 0x100u
+#define SHASTA_FLAG_SKIP_GATHER 0x200u
 SHASTA_API int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, const float* bev,
                        const float* prev_bev, float* det_boxes, const float* prev_det_boxes, int batch,
                        const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes,
                        float* matched1, float* matched2, uint32_t flags, shasta_stream_t stream);
+
+/* First stage of shasta_forward_f32 on its own (a1-a2 for both frames, writing FEAT_* and, when the anchors path in
+ * use for (max_obj, batch) wants them, FEATLO_*), so that a caller can run it on another stream: the gather of the
+ * next batch (PCIe-bound when the BEV maps are host-resident and sampled in place) then overlaps the remaining stages
+ * of the current one. Follow with shasta_forward_f32(..., flags | SHASTA_FLAG_SKIP_GATHER) on the same workspace. */
+SHASTA_API int shasta_gather_pair_f32(const float* bev, const float* prev_bev, const float* det_boxes,
+                           const float* prev_det_boxes, int batch, int max_obj, const shasta_geom_t* host_geom,
+                           float* workspace, size_t workspace_bytes, uint32_t flags, shasta_stream_t stream);
 
 /* Backward of the head for the training configuration (tools/nusc_shasta/train.py:201-214, BASELINE.json config 5).
  * Call after shasta_forward_f32 on the SAME workspace (its regions hold the saved activations) with the forward's

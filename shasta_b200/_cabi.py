@@ -58,7 +58,8 @@ class ShastaGeom(ctypes.Structure):
 # region ids (enum shasta_region)
 WS_FEAT_CUR, WS_FEAT_PREV, WS_BOX_CUR, WS_BOX_PREV, WS_HIDDEN_PART, WS_PROJ_PREV, WS_PROJ_CUR, WS_AUX_PREV, \
     WS_AUX_CUR, WS_COLNORM, WS_RESIDUAL, WS_LOGITS, WS_ANCHOR_BOX, WS_PROJ_CUR_T, WS_DPROJ_PREV, WS_DPROJ_CUR, WS_ANCH_H, \
-    WS_ANCH_DY, WS_ANCH_DZ, WS_RAW_XY, WS_BOX_BWD = range(21)
+    WS_ANCH_DY, WS_ANCH_DZ, WS_RAW_XY, WS_BOX_BWD, WS_FEATLO_CUR, WS_FEATLO_PREV, WS_COUNTERS, WS_HID, WS_HIDLO = range(26)
+FLAG_TMA_GATHER, FLAG_PROFILE, FLAG_SKIP_GATHER = 0x1, 0x100, 0x200
 
 OPT_ANCHOR_PATH = 0
 OPT_TC_RAW_HI = 1
@@ -89,6 +90,7 @@ SYMBOLS = {
     "shasta_aff_softmax_f32": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "shasta_forward_f32": (_i, [ctypes.POINTER(ShastaParams), _vp, _vp, _vp, _vp, _vp, _i,
                                 ctypes.POINTER(ShastaGeom), _vp, _sz, _vp, _vp, _u32, _vp]),
+    "shasta_gather_pair_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, ctypes.POINTER(ShastaGeom), _vp, _sz, _u32, _vp]),
     "shasta_backward_f32": (_i, [ctypes.POINTER(ShastaParams), ctypes.POINTER(ShastaGrads), _vp, _i, _vp, _sz, _vp, _vp,
                                  _vp, _vp, _vp]),
     "shasta_profile_begin": (_i, [_i]),

@@ -280,11 +280,13 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
   // a1-a2: both frames in one launch (blockIdx.y selects the frame)
   // the tcgen05 anchors GEMM takes the tf32 low parts of the features as a second TMA operand: the gather writes them
   const bool featlo = anchor_uses_featlo(M, batch);
-  rc = launch_gather(bev, det_boxes, workspace + L.off[SHASTA_WS_FEAT_CUR], prev_bev, prev_det_boxes,
-                     workspace + L.off[SHASTA_WS_FEAT_PREV], 2, 11, batch, M, *host_geom, fstride, (int)(flags & 1u), s,
-                     featlo ? workspace + L.off[SHASTA_WS_FEATLO_CUR] : nullptr,
-                     featlo ? workspace + L.off[SHASTA_WS_FEATLO_PREV] : nullptr);
-  if (rc) return rc;
+  if (!(flags & SHASTA_FLAG_SKIP_GATHER)) {
+    rc = launch_gather(bev, det_boxes, workspace + L.off[SHASTA_WS_FEAT_CUR], prev_bev, prev_det_boxes,
+                       workspace + L.off[SHASTA_WS_FEAT_PREV], 2, 11, batch, M, *host_geom, fstride, (int)(flags & 1u),
+                       s, featlo ? workspace + L.off[SHASTA_WS_FEATLO_CUR] : nullptr,
+                       featlo ? workspace + L.off[SHASTA_WS_FEATLO_PREV] : nullptr);
+    if (rc) return rc;
+  }
   STAGE_MARK(1);
   rc = launch_anchors(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, s, ev ? ev[2] : nullptr,
                       featlo);  // a3-a4
@@ -302,6 +304,35 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
 #undef STAGE_MARK
   g_last_forward_launches = g_launch_count;
   return 0;
+}
+
+int shasta_gather_pair_f32(const float* bev, const float* prev_bev, const float* det_boxes,
+                           const float* prev_det_boxes, int batch, int max_obj, const shasta_geom_t* host_geom,
+                           float* workspace, size_t workspace_bytes, uint32_t flags, shasta_stream_t stream) {
+  int rc = check_dims(batch, max_obj);
+  if (rc) return rc;
+  rc = check_geom(host_geom);
+  if (rc) return rc;
+  NOT_NULL(bev);
+  NOT_NULL(prev_bev);
+  NOT_NULL(det_boxes);
+  NOT_NULL(prev_det_boxes);
+  NOT_NULL(workspace);
+  ALIGNED16(bev);
+  ALIGNED16(prev_bev);
+  ALIGNED16(workspace);
+  if (workspace_bytes < shasta_workspace_bytes(batch, max_obj)) {
+    set_error("workspace too small: %zu < %zu bytes", workspace_bytes, shasta_workspace_bytes(batch, max_obj));
+    return SHASTA_ERR_SIZE;
+  }
+  if (batch == 0) return 0;
+  const WsLayout L = ws_layout(batch, max_obj);
+  const bool featlo = anchor_uses_featlo(max_obj, batch);
+  return launch_gather(bev, det_boxes, workspace + L.off[SHASTA_WS_FEAT_CUR], prev_bev, prev_det_boxes,
+                       workspace + L.off[SHASTA_WS_FEAT_PREV], 2, 11, batch, max_obj, *host_geom,
+                       (size_t)(max_obj + 2) * kF, (int)(flags & 1u), (cudaStream_t)stream,
+                       featlo ? workspace + L.off[SHASTA_WS_FEATLO_CUR] : nullptr,
+                       featlo ? workspace + L.off[SHASTA_WS_FEATLO_PREV] : nullptr);
 }
 
 int shasta_backward_f32(const shasta_params_t* host_params, const shasta_grads_t* host_grads, const float* packed,

@@ -111,6 +111,11 @@ class Shasta(nn.Module):
         # entry and are overwritten by the next replay of the same entry. Off by default (fresh outputs per call).
         self.cuda_graphs = False
         self._graphs = {}
+        # host-resident (pinned) BEV maps are sampled in place over PCIe; with pipeline_host_inputs the box upload and
+        # the gather of a call run on a side stream into one of two workspaces, so they overlap the remaining stages
+        # (and the caller's device-to-host copies) of the previous call
+        self.pipeline_host_inputs = True
+        self._pipe = None
         self._packed = None
         self._pack_key = None
         self._cparams = None
@@ -243,6 +248,10 @@ class Shasta(nn.Module):
         prev_bev = prev_bev if prev_bev.is_contiguous() else prev_bev.contiguous()
         if (not bev.is_cuda or not prev_bev.is_cuda) and (self.kernel_flags & FLAG_TMA_GATHER):
             raise _cabi.ShastaLibraryError("host-resident BEV maps need the LDG sampler (kernel_flags bit 0 clear)")
+        if (self.pipeline_host_inputs and not bev.is_cuda and not prev_bev.is_cuda and not det_boxes.is_cuda
+                and not prev_det_boxes.is_cuda and not (self.kernel_flags & 0x100)
+                and not (torch.is_grad_enabled() and self.training)):
+            return self._affinity_pipelined(bev, prev_bev, det_boxes, prev_det_boxes, device)
         # boxes: device copies of host inputs (async from pinned memory); the back-projection is written back below
         prev_c = prev_det_boxes.to(device, non_blocking=True).contiguous()
         det_c = det_boxes.to(device, non_blocking=True).contiguous()
@@ -258,6 +267,59 @@ class Shasta(nn.Module):
                 det_boxes[:, :, :2] = det_c[:, :, :2]
             else:  # pinned host input: asynchronous write-back of the back-projected boxes (shasta.py:270)
                 det_boxes.copy_(det_c, non_blocking=True)
+        return m1, m2
+
+    def _affinity_pipelined(self, bev, prev_bev, det_boxes, prev_det_boxes, device):
+        """Host inputs, two-stage software pipeline over calls: stage 1 (side stream) uploads the boxes and gathers the
+        box features straight from the pinned maps; stage 2 (current stream) runs anchors ... softmax. The two stages
+        of consecutive calls use alternating workspaces and overlap. Semantics are those of asynchronous CUDA work on
+        pinned memory: inputs must stay unchanged until the gather ran, results (and the in-place back-projection of
+        ``det_boxes``) are complete once the current stream reaches this point."""
+        lib = _cabi.lib()
+        B, H, W, _ = bev.shape
+        M = self.max_obj
+        self._ensure_packed(device)
+        cur = torch.cuda.current_stream(device)
+        key = (B, device)
+        if self._pipe is None or self._pipe["key"] != key:
+            self._pipe = {"key": key, "idx": 0, "stream": torch.cuda.Stream(device=device),
+                          "ws": [_Workspace(B, M, device) for _ in range(2)],
+                          "det": [torch.empty((B, M, 11), dtype=torch.float32, device=device) for _ in range(2)],
+                          "prev": [torch.empty((B, M, 11), dtype=torch.float32, device=device) for _ in range(2)],
+                          "gathered": [torch.cuda.Event() for _ in range(2)],
+                          "consumed": [None, None]}
+        P = self._pipe
+        k = P["idx"]
+        P["idx"] = 1 - k
+        side, ws, det_c, prev_c = P["stream"], P["ws"][k], P["det"][k], P["prev"][k]
+        geom = self.bev_extractor.geom(H, W)
+        if P["consumed"][k] is not None:
+            side.wait_event(P["consumed"][k])      # stage 2 of the call that used this buffer set has finished
+        with torch.cuda.stream(side):
+            det_c.copy_(det_boxes, non_blocking=True)
+            prev_c.copy_(prev_det_boxes, non_blocking=True)
+            rc = lib.shasta_gather_pair_f32(bev.data_ptr(), prev_bev.data_ptr(), det_c.data_ptr(), prev_c.data_ptr(), B, M,
+                                            ctypes.byref(geom), ws.buf.data_ptr(), ws.nbytes, int(self.kernel_flags),
+                                            ctypes.c_void_p(side.cuda_stream))
+            _cabi.check(rc, "shasta_gather_pair_f32")
+            P["gathered"][k].record(side)
+        cur.wait_event(P["gathered"][k])
+        m1 = torch.empty((B, M, M + 2), dtype=torch.float32, device=device)
+        m2 = torch.empty((B, M + 2, M), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            rc = lib.shasta_forward_f32(
+                ctypes.byref(self._cparams), self._packed.data_ptr(), bev.data_ptr(), prev_bev.data_ptr(),
+                det_c.data_ptr(), prev_c.data_ptr(), B, ctypes.byref(geom), ws.buf.data_ptr(), ws.nbytes,
+                m1.data_ptr(), m2.data_ptr(), int(self.kernel_flags) | _cabi.FLAG_SKIP_GATHER,
+                ctypes.c_void_p(cur.cuda_stream))
+        _cabi.check(rc, "shasta_forward_f32")
+        det_boxes.copy_(det_c, non_blocking=True)  # back-projected boxes to the caller's pinned tensor (shasta.py:270)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        P["consumed"][k] = ev
+        anchors = ws.region(_cabi.WS_ANCHOR_BOX, B * 4 * 7).view(B, 4, 7)
+        self.newborn, self.fp = anchors[:, 0:1, :], anchors[:, 1:2, :]
+        self.dead_trk, self.fn = anchors[:, 2:3, :], anchors[:, 3:4, :]
         return m1, m2
 
     def _launch_forward(self, bev, prev_bev, det_c, prev_c, ws):

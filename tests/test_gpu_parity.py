@@ -414,6 +414,29 @@ def test_cuda_graph_replay_matches_eager(M, B):
     assert len(model._graphs) == 1
 
 
+def test_pipelined_host_inputs_match_device_path():
+    """Pinned host inputs run the gather on a side stream into alternating workspaces (two-stage pipeline over calls):
+    every call must return what the plain device path returns, including the in-place back-projection."""
+    M, B, H, W = 20, 3, 32, 32
+    pc_start = (-W * 0.3, -H * 0.3)
+    model = G.make_model(M, pc_start, synthetic.make_weights(M, seed=6))
+    outs = []
+    with torch.no_grad():
+        for seed in (41, 42, 43, 44, 45):
+            d = synthetic.make_frame_pairs(B, M, H, W, seed, pc_start=pc_start)
+            host = [torch.from_numpy(d[k]).pin_memory() for k in ("bev", "prev_bev", "det_boxes", "prev_det_boxes")]
+            m1, m2 = model.affinity(*host)          # asynchronous: do not synchronise between the calls
+            outs.append((d, host, m1, m2))
+        torch.cuda.synchronize()
+        assert model._pipe is not None
+        model.pipeline_host_inputs = False
+        for d, host, m1, m2 in outs:
+            dev = [G.t(d[k]) for k in ("bev", "prev_bev", "det_boxes", "prev_det_boxes")]
+            e1, e2 = model.affinity(*dev)
+            assert torch.equal(m1, e1) and torch.equal(m2, e2)
+            assert torch.equal(host[2], dev[2].cpu())
+
+
 def test_forward_empty_batch_and_bad_inputs():
     M = 6
     model = G.make_model(M, (-4.8, -4.8), synthetic.make_weights(M, seed=1))
