@@ -238,6 +238,21 @@ SHASTA_API int shasta_gather_pair_f32(const float* bev, const float* prev_bev, c
                            const float* prev_det_boxes, int batch, int max_obj, const shasta_geom_t* host_geom,
                            float* workspace, size_t workspace_bytes, uint32_t flags, shasta_stream_t stream);
 
+/* shared_conv producer (shasta.py:42-47,223-228): Conv2d(512 -> 64, 3x3, padding 1, bias) +
+ * BatchNorm2d with its running statistics (inference) + ReLU, result written channels-last (nmaps,H,W,64) - the
+ * layout the gather reads, so the reference's permute(0,2,3,1).contiguous() disappears. Implicit GEMM on tcgen05
+ * (3xTF32, fp32-equivalent): 16x8-pixel patches x [W_hi;W_lo], K = 9 taps x 512 channels, TMA zero-fill = padding.
+ *   shasta_shared_conv_pack: weight (64,512,3,3), bias/bn_* (64) -> packed (shasta_shared_conv_packed_bytes()).
+ *   shasta_shared_conv_f32:  x (nmaps,512,H,W) NCHW fp32; scratch holds its channels-last copy
+ *                            (shasta_shared_conv_scratch_bytes(nmaps,H,W)); out (nmaps,H,W,64). */
+SHASTA_API size_t shasta_shared_conv_packed_bytes(void);
+SHASTA_API size_t shasta_shared_conv_scratch_bytes(int nmaps, int height, int width);
+SHASTA_API int shasta_shared_conv_pack(const float* weight, const float* bias, const float* bn_weight,
+                            const float* bn_bias, const float* bn_mean, const float* bn_var, float bn_eps,
+                            float* packed, size_t packed_bytes, shasta_stream_t stream);
+SHASTA_API int shasta_shared_conv_f32(const float* packed, const float* x_nchw, int nmaps, int height, int width,
+                           float* scratch, size_t scratch_bytes, float* out_nhwc, shasta_stream_t stream);
+
 /* Backward of the head for the training configuration (tools/nusc_shasta/train.py:201-214, BASELINE.json config 5).
  * Call after shasta_forward_f32 on the SAME workspace (its regions hold the saved activations) with the forward's
  * outputs matched1/matched2 and the upstream gradients gm1 (B,M,M+2), gm2 (B,M+2,M) of the loss. Computes

@@ -21,6 +21,19 @@ import torch.nn.functional as Fn
 
 
 # --------------------------------------------------------------------------------------------------
+# a0 (producer): shared_conv + NHWC permute          (shasta.py:42-47, 223-228)
+# --------------------------------------------------------------------------------------------------
+def shared_conv_nhwc(w, x, eps=1e-5):
+    """``self.shared_conv(x).permute(0,2,3,1).contiguous()`` in inference mode: Conv2d(512->64, 3x3, padding 1,
+    bias) -> BatchNorm2d with running statistics -> ReLU. ``w`` holds the reference's state_dict entries
+    ``shared_conv.0.{weight,bias}``, ``shared_conv.1.{weight,bias,running_mean,running_var}``; x is (N,512,H,W)."""
+    y = Fn.conv2d(x, w["shared_conv.0.weight"], w["shared_conv.0.bias"], padding=1)
+    y = Fn.batch_norm(y, w["shared_conv.1.running_mean"], w["shared_conv.1.running_var"], w["shared_conv.1.weight"],
+                      w["shared_conv.1.bias"], training=False, eps=eps)
+    return torch.relu(y).permute(0, 2, 3, 1).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
 # a1: box -> 5 sample points          (shasta.py:121-161, box_torch_ops.py:24-59,145-158,184-203)
 # --------------------------------------------------------------------------------------------------
 def corners_nd_2d(dims):

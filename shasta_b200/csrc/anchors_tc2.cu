@@ -53,13 +53,19 @@ struct AnchorT2Maps {
 //   mode 0  aug_shape.i.0: W (5M x 320M), X = gathered features, output = split-K partial sums `part`
 //   mode 1  aug_shape.i.2: W (320 x 5M),  X = hidden activations, output = |acc + bias| written into the anchor
 //           row of the augmented feature array (shasta.py:241-247); S must be 1
+//   mode 2  shared_conv (shasta.py:42-47,223-228) as an implicit GEMM: the streamed M-side tile is a 16 x 8 pixel
+//           patch of the channels-last 512-channel map, fetched by a 4-D TMA box shifted by the 3x3 tap (zero padding =
+//           TMA out-of-bounds fill); the B operand is the packed [W_hi; W_lo] (128 x 4608) weight matrix; the epilogue
+//           applies the folded bias/BatchNorm and ReLU and writes the channels-last 64-channel map. blockIdx.y = map.
 struct AnchorT2Job {
   int B, nrows, kblocks, S, ntiles_n, raw_hi, dbg, mode;
   float* part;
-  const float* bias[4];
+  const float* bias[4];   // mode 2: bias[0] = scale[64], bias[1] = shift[64]
   float* out[4];
   size_t out_bstride;
+  int H, W, tiles_x;      // mode 2 geometry
 };
+constexpr int kConvTX = 16, kConvTY = 8;   // pixel patch of one M tile (128 pixels)
 
 __device__ __forceinline__ void t2_tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
@@ -88,8 +94,11 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N5 = job.nrows;
   const int kblocks = job.kblocks;
-  const int nt = blockIdx.x % ntiles_n, bt = blockIdx.x / ntiles_n;
-  const int i = blockIdx.y, s = blockIdx.z;
+  const bool conv = job.mode == 2;
+  const int nt = conv ? 0 : blockIdx.x % ntiles_n, bt = conv ? 0 : blockIdx.x / ntiles_n;
+  const int i = conv ? 0 : blockIdx.y, s = blockIdx.z;
+  const int px0 = conv ? (int)(blockIdx.x % job.tiles_x) * kConvTX : 0;   // patch origin (mode 2)
+  const int py0 = conv ? (int)(blockIdx.x / job.tiles_x) * kConvTY : 0;
   const int kb_beg = (int)((long long)kblocks * s / S), kb_end = (int)((long long)kblocks * (s + 1) / S);
   const int nkb = kb_end - kb_beg;
   const int n0 = nt * kT2BM, b0 = bt * BN;
@@ -139,6 +148,11 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, const __grid
         }
         mbar_expect_tx(full_bar(st), kT2WTile + 2 * C::kXTile);
         const int k0 = (kb_beg + kb) * kT2BK;
+        if (conv) {   // K block = (tap, 32 input channels): the pixel patch shifted by the tap, zero-filled outside
+          const int kbg = kb_beg + kb, tap = kbg >> 4, cb = kbg & 15;
+          tma_load_4d(sb, &maps.w[0], full_bar(st), cb * 32, px0 + tap % 3 - 1, py0 + tap / 3 - 1, (int)blockIdx.y,
+                      kEvictLast);
+        } else
         tma_load_2d(sb, &maps.w[i], full_bar(st), k0, n0, kEvictFirst);                  // weights: streamed once
         tma_load_2d(sb + kT2WTile, &maps.x[i], full_bar(st), k0, b0, kEvictLast);        // activations: reused
         tma_load_2d(sb + kT2WTile + C::kXTile, &maps.xlo[i], full_bar(st), k0, b0, kEvictLast);
@@ -281,7 +295,25 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, const __grid
 
     // ---- epilogue: registers -> split-K partial sums, coalesced along the weight-row dimension
     const int n = n0 + r;
-    if (n < N5) {
+    if (conv) {
+      // thread = pixel of the patch: 64 output channels = 256 contiguous bytes of the channels-last map
+      const int x = px0 + (r % kConvTX), y = py0 + (r / kConvTX);
+      if (x < job.W && y < job.H) {
+        float4* o = reinterpret_cast<float4*>(job.out[0] + (((size_t)blockIdx.y * job.H + y) * job.W + x) * 64);
+        const float4* sc = reinterpret_cast<const float4*>(job.bias[0]);
+        const float4* sh = reinterpret_cast<const float4*>(job.bias[1]);
+#pragma unroll
+        for (int j = 0; j < BN / 4; ++j) {
+          const float4 a = __ldg(sc + (j & 15)), c = __ldg(sh + (j & 15));
+          float4 v;
+          v.x = fmaxf(fmaf(acc[4 * j + 0], a.x, c.x), 0.f);
+          v.y = fmaxf(fmaf(acc[4 * j + 1], a.y, c.y), 0.f);
+          v.z = fmaxf(fmaf(acc[4 * j + 2], a.z, c.z), 0.f);
+          v.w = fmaxf(fmaf(acc[4 * j + 3], a.w, c.w), 0.f);
+          if (j < 16) o[j] = v;
+        }
+      }
+    } else if (n < N5) {
       if (job.mode == 0) {
 #pragma unroll
         for (int j = 0; j < BN; ++j) {
@@ -311,6 +343,39 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, const __grid
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn2 encode_fn() {
+  static EncodeTiledFn2 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn2>(p);
+  }
+  return fn;
+}
+
+// channels-last (nmaps, H, W, C) fp32 map, box = 32 channels x kConvTX x kConvTY x 1
+static int make_map_nhwc(CUtensorMap* m, const float* ptr, uint64_t nmaps, uint64_t H, uint64_t W, uint64_t C) {
+  EncodeTiledFn2 fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return SHASTA_ERR_UNSUPPORTED;
+  }
+  const cuuint64_t dims[4] = {C, W, H, nmaps};
+  const cuuint64_t strides[3] = {C * sizeof(float), W * C * sizeof(float), H * W * C * sizeof(float)};
+  const cuuint32_t box[4] = {(cuuint32_t)kT2BK, (cuuint32_t)kConvTX, (cuuint32_t)kConvTY, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (4-D) failed with CUresult %d", (int)r);
+    return SHASTA_ERR_ARG;
+  }
+  return 0;
+}
 
 static int make_map2(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   static EncodeTiledFn2 fn = nullptr;
@@ -467,6 +532,87 @@ int launch_anchor_out_tc(const shasta_params_t& p, const float* part, int S, int
   }
   job.out_bstride = (size_t)T * kF;
   return t2_launch(maps, job, bn, (B + bn - 1) / bn, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared_conv producer: Conv3x3(512 -> 64, pad 1, bias) + BatchNorm2d (inference statistics) + ReLU,
+// output channels-last (shasta.py:42-47, 223-228)
+// ------------------------------------------------------------------------------------------------
+constexpr int kConvCin = 512, kConvCout = 64, kConvK = 9 * kConvCin;
+
+// packed = [W_hi (64 x 4608) ; W_lo (64 x 4608)] with k = (ky*3 + kx)*512 + c, then scale[64], shift[64]
+__global__ void conv_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                 float* __restrict__ packed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < kConvCout * kConvK) {
+    const int o = idx / kConvK, k = idx % kConvK, tap = k / kConvCin, c = k % kConvCin;
+    const float v = w[((size_t)o * kConvCin + c) * 9 + tap];
+    packed[idx] = v;   // the tensor core ignores the low 13 mantissa bits of the "high" operand
+    packed[(size_t)kConvCout * kConvK + idx] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  }
+  if (idx < kConvCout) {
+    const float sc = gamma[idx] / sqrtf(var[idx] + eps);
+    packed[(size_t)2 * kConvCout * kConvK + idx] = sc;
+    packed[(size_t)2 * kConvCout * kConvK + kConvCout + idx] = (bias[idx] - mean[idx]) * sc + beta[idx];
+  }
+}
+
+// (nmaps, C, HW) -> (nmaps, HW, C), 32 x 32 tiles through shared memory
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  const size_t mo = (size_t)blockIdx.z * C * HW;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? in[mo + (size_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int p = p0 + j, c = c0 + threadIdx.x;
+    if (p < HW && c < C) out[mo + (size_t)p * C + c] = tile[threadIdx.x][j];
+  }
+}
+
+size_t shared_conv_packed_floats() { return (size_t)2 * kConvCout * kConvK + 2 * kConvCout; }
+
+int launch_shared_conv_pack(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,
+                            const float* var, float eps, float* packed, cudaStream_t s) {
+  conv_pack_kernel<<<(kConvCout * kConvK + 255) / 256, 256, 0, s>>>(w, bias, gamma, beta, mean, var, eps, packed);
+  SHASTA_CHECK_LAUNCH("conv_pack_kernel");
+  return 0;
+}
+
+int launch_shared_conv(const float* packed, const float* x_nchw, int nmaps, int H, int W, float* scratch,
+                       float* out_nhwc, cudaStream_t s) {
+  dim3 tg((H * W + 31) / 32, kConvCin / 32, nmaps), tb(32, 8);
+  nchw_to_nhwc_kernel<<<tg, tb, 0, s>>>(x_nchw, scratch, kConvCin, H * W);
+  SHASTA_CHECK_LAUNCH("nchw_to_nhwc_kernel");
+  AnchorT2Maps maps;
+  int rc = make_map_nhwc(&maps.w[0], scratch, (uint64_t)nmaps, (uint64_t)H, (uint64_t)W, kConvCin);
+  if (rc) return rc;
+  rc = make_map2(&maps.x[0], packed, kConvCout, kConvK, kConvK, 64);
+  if (rc) return rc;
+  rc = make_map2(&maps.xlo[0], packed + (size_t)kConvCout * kConvK, kConvCout, kConvK, kConvK, 64);
+  if (rc) return rc;
+  for (int i = 1; i < 4; ++i) maps.w[i] = maps.w[0], maps.x[i] = maps.x[0], maps.xlo[i] = maps.xlo[0];
+  AnchorT2Job job = {};
+  job.B = kConvCout, job.nrows = 128, job.kblocks = kConvK / kT2BK, job.S = 1, job.ntiles_n = 1;
+  job.raw_hi = 1, job.dbg = 0, job.mode = 2, job.part = nullptr;
+  job.bias[0] = packed + (size_t)2 * kConvCout * kConvK, job.bias[1] = job.bias[0] + kConvCout;
+  job.out[0] = out_nhwc;
+  job.H = H, job.W = W, job.tiles_x = (W + kConvTX - 1) / kConvTX;
+  static bool configured = false;
+  if (!configured) {
+    SHASTA_CUDA(cudaFuncSetAttribute(anchor_hidden_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     T2Cfg<64>::kSmemBytes));
+    configured = true;
+  }
+  dim3 grid(job.tiles_x * ((H + kConvTY - 1) / kConvTY), nmaps, 1);
+  anchor_hidden_tc2_kernel<64><<<grid, kT2Threads, T2Cfg<64>::kSmemBytes, s>>>(maps, job);
+  SHASTA_CHECK_LAUNCH("anchor_hidden_tc2_kernel(conv)");
+  return 0;
 }
 
 }  // namespace shasta

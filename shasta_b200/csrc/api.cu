@@ -335,6 +335,53 @@ int shasta_gather_pair_f32(const float* bev, const float* prev_bev, const float*
                        featlo ? workspace + L.off[SHASTA_WS_FEATLO_PREV] : nullptr);
 }
 
+size_t shasta_shared_conv_packed_bytes(void) { return shared_conv_packed_floats() * sizeof(float); }
+
+size_t shasta_shared_conv_scratch_bytes(int nmaps, int height, int width) {
+  if (nmaps < 0 || height < 1 || width < 1) return 0;
+  return (size_t)nmaps * height * width * 512 * sizeof(float);
+}
+
+int shasta_shared_conv_pack(const float* weight, const float* bias, const float* bn_weight, const float* bn_bias,
+                            const float* bn_mean, const float* bn_var, float bn_eps, float* packed,
+                            size_t packed_bytes, shasta_stream_t stream) {
+  NOT_NULL(weight);
+  NOT_NULL(bias);
+  NOT_NULL(bn_weight);
+  NOT_NULL(bn_bias);
+  NOT_NULL(bn_mean);
+  NOT_NULL(bn_var);
+  NOT_NULL(packed);
+  ALIGNED16(packed);
+  if (packed_bytes < shasta_shared_conv_packed_bytes()) {
+    set_error("shared_conv packed buffer too small");
+    return SHASTA_ERR_SIZE;
+  }
+  return launch_shared_conv_pack(weight, bias, bn_weight, bn_bias, bn_mean, bn_var, bn_eps, packed,
+                                 (cudaStream_t)stream);
+}
+
+int shasta_shared_conv_f32(const float* packed, const float* x_nchw, int nmaps, int height, int width, float* scratch,
+                           size_t scratch_bytes, float* out_nhwc, shasta_stream_t stream) {
+  NOT_NULL(packed);
+  NOT_NULL(x_nchw);
+  NOT_NULL(scratch);
+  NOT_NULL(out_nhwc);
+  ALIGNED16(packed);
+  ALIGNED16(scratch);
+  ALIGNED16(out_nhwc);
+  if (nmaps < 0 || nmaps > 65535 || height < 1 || width < 1) {
+    set_error("shared_conv: need 0 <= nmaps <= 65535 and H, W >= 1");
+    return SHASTA_ERR_ARG;
+  }
+  if (scratch_bytes < shasta_shared_conv_scratch_bytes(nmaps, height, width)) {
+    set_error("shared_conv scratch too small");
+    return SHASTA_ERR_SIZE;
+  }
+  if (nmaps == 0) return 0;
+  return launch_shared_conv(packed, x_nchw, nmaps, height, width, scratch, out_nhwc, (cudaStream_t)stream);
+}
+
 int shasta_backward_f32(const shasta_params_t* host_params, const shasta_grads_t* host_grads, const float* packed,
                         int batch, float* workspace, size_t workspace_bytes, const float* matched1,
                         const float* matched2, const float* gm1, const float* gm2, shasta_stream_t stream) {

@@ -309,6 +309,11 @@ int launch_backward_anchor(const shasta_params_t& p, const shasta_grads_t& g, in
                            const WsLayout& L, cudaStream_t s);
 int launch_backward_box(const shasta_params_t& p, const shasta_grads_t& g, int B, float* ws, const WsLayout& L,
                         cudaStream_t s);
+size_t shared_conv_packed_floats();
+int launch_shared_conv_pack(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,
+                            const float* var, float eps, float* packed, cudaStream_t s);
+int launch_shared_conv(const float* packed, const float* x_nchw, int nmaps, int H, int W, float* scratch,
+                       float* out_nhwc, cudaStream_t s);
 bool anchor_uses_featlo(int M, int B);  // true when the anchors path in use for (M, B) reads the FEATLO_* regions
 int anchor_splits_in_use(int M, int B);  // split-K count the forward anchors kernel uses for this (M, B)
 int launch_decode(const float* m1, const float* m2, const int32_t* n_prev, const int32_t* n_det, int B, int M,

@@ -322,6 +322,50 @@ class Shasta(nn.Module):
         self.dead_trk, self.fn = anchors[:, 2:3, :], anchors[:, 3:4, :]
         return m1, m2
 
+    # ------------------------------------------------------------------------------------------
+    def shared_conv_nhwc(self, x, maps_per_launch=8):
+        """``self.shared_conv(x).permute(0, 2, 3, 1).contiguous()`` (shasta.py:223-228) for inference: one tcgen05
+        implicit-GEMM kernel (3xTF32, fp32-equivalent) with the bias / BatchNorm (running statistics) / ReLU folded
+        into its epilogue, writing the channels-last map directly. x: (N,512,H,W) float32 CUDA tensor.
+        In training mode BatchNorm needs batch statistics: that case stays on the nn.Sequential (and receives no
+        gradient from the CUDA head)."""
+        conv, bn = self.shared_conv[0], self.shared_conv[1]
+        if self.training or not x.is_cuda:
+            if not x.is_cuda:
+                raise _cabi.ShastaLibraryError("shared_conv_nhwc needs a CUDA tensor: shasta_b200 has no CPU path")
+            return self.shared_conv(x).permute(0, 2, 3, 1).contiguous()
+        if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 512 or conv.out_channels != 64:
+            raise ValueError("shared_conv_nhwc expects a float32 (N,512,H,W) tensor and 64 output channels")
+        lib = _cabi.lib()
+        device = x.device
+        x = x if x.is_contiguous() else x.contiguous()
+        N, _, H, W = x.shape
+        tensors = (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        if getattr(self, "_conv_key", None) != key:
+            nbytes = lib.shasta_shared_conv_packed_bytes()
+            packed = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+            with torch.cuda.device(device):
+                rc = lib.shasta_shared_conv_pack(*[t.detach().contiguous().data_ptr() for t in tensors],
+                                                 ctypes.c_float(bn.eps), packed.data_ptr(), nbytes, stream)
+            _cabi.check(rc, "shasta_shared_conv_pack")
+            self._conv_packed, self._conv_key = packed, key
+        out = torch.empty((N, H, W, 64), dtype=torch.float32, device=device)
+        step = max(1, min(N, int(maps_per_launch)))
+        sbytes = lib.shasta_shared_conv_scratch_bytes(step, H, W)
+        scratch = getattr(self, "_conv_scratch", None)
+        if scratch is None or scratch.numel() * 4 < sbytes or scratch.device != device:
+            scratch = self._conv_scratch = torch.empty(sbytes // 4, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            for n0 in range(0, N, step):
+                n = min(step, N - n0)
+                rc = lib.shasta_shared_conv_f32(self._conv_packed.data_ptr(), x[n0:n0 + n].data_ptr(), n, H, W,
+                                                scratch.data_ptr(), scratch.numel() * 4, out[n0:n0 + n].data_ptr(),
+                                                stream)
+                _cabi.check(rc, "shasta_shared_conv_f32")
+        return out
+
     def _launch_forward(self, bev, prev_bev, det_c, prev_c, ws):
         """Enqueues the five forward kernels on the current stream. Inputs are validated, contiguous, boxes on the
         device; ``ws`` is the workspace the activations are left in (the backward pass reads them)."""
@@ -379,8 +423,8 @@ class Shasta(nn.Module):
             bev, prev_bev = example["bev_feature"], example["prev_bev_feature"]
         else:
             bev_map, _, prev_bev_map, _ = self.extract_feat(example)
-            bev = self.shared_conv(bev_map).permute(0, 2, 3, 1).contiguous()
-            prev_bev = self.shared_conv(prev_bev_map).permute(0, 2, 3, 1).contiguous()
+            bev = self.shared_conv_nhwc(bev_map)
+            prev_bev = self.shared_conv_nhwc(prev_bev_map)
             example["bev_feature"] = bev
         matched1, matched2 = self.affinity(bev, prev_bev, example["det_boxes"], example["prev_det_boxes"])
         return matched1, matched2, example
