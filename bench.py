@@ -306,7 +306,7 @@ def run_train(a):
         p_.requires_grad_(False)
     for p_ in params:
         p_.requires_grad_(True)
-    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-2)
+    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-2, fused=True)  # train.py:147 Adam, single multi-tensor kernel
     B, M = a.batch, a.max_obj
     det0 = torch.from_numpy(d["det_boxes"]).to(device)
     prev = torch.from_numpy(d["prev_det_boxes"]).to(device)

@@ -385,8 +385,9 @@ class Shasta(nn.Module):
                     ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
             _cabi.check(rc, "shasta_forward_f32")
 
+        # (not while training: the packed weights change every optimizer step, a capture would never be replayed)
         use_graph = (self.cuda_graphs and not (self.kernel_flags & 0x100) and bev.is_cuda and prev_bev.is_cuda
-                     and not torch.cuda.is_current_stream_capturing())
+                     and not self.training and not torch.cuda.is_current_stream_capturing())
         if use_graph:
             key = (bev.data_ptr(), prev_bev.data_ptr(), det_c.data_ptr(), prev_c.data_ptr(), B, H, W,
                    int(self.kernel_flags), ws.buf.data_ptr(), self._pack_key)
