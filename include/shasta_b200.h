@@ -238,6 +238,19 @@ SHASTA_API int shasta_gather_pair_f32(const float* bev, const float* prev_bev, c
                            const float* prev_det_boxes, int batch, int max_obj, const shasta_geom_t* host_geom,
                            float* workspace, size_t workspace_bytes, uint32_t flags, shasta_stream_t stream);
 
+/* Greedy centre-distance assignment of the ID tracker (tools/nusc_shasta/pub_tracker_merged.py:122-137,
+ * track_utils.py:3-14) for a batch of independent problems (one class of one frame each), all arrays padded:
+ *   dets (P,nmax,2) detection centres already moved by -velocity*time_lag, tracks (P,mmax,2) track centres,
+ *   max_diff (P,nmax) class velocity-error threshold of each detection, det_cat (P,nmax) / track_cat (P,mmax) labels,
+ *   n_det (P), n_track (P) real counts.
+ * Outputs: match (P,nmax) = matched track index or -1 (rows beyond n_det: -1); det_near (P,nmax) = 1 when some
+ * valid track lies within the threshold; track_near (P,mmax) likewise per track (pub_tracker_merged.py:176,197).
+ * Distances are float32 in numpy's operation order; ties resolve to the lowest index like numpy.argmin. */
+SHASTA_API int shasta_greedy_assign_f32(const float* dets, const float* tracks, const float* max_diff,
+                             const int32_t* det_cat, const int32_t* track_cat, const int32_t* n_det,
+                             const int32_t* n_track, int problems, int nmax, int mmax, int32_t* match,
+                             int32_t* det_near, int32_t* track_near, shasta_stream_t stream);
+
 /* shared_conv producer (shasta.py:42-47,223-228): Conv2d(512 -> 64, 3x3, padding 1, bias) +
  * BatchNorm2d with its running statistics (inference) + ReLU, result written channels-last (nmaps,H,W,64) - the
  * layout the gather reads, so the reference's permute(0,2,3,1).contiguous() disappears. Implicit GEMM on tcgen05

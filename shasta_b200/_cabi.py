@@ -91,6 +91,7 @@ SYMBOLS = {
     "shasta_forward_f32": (_i, [ctypes.POINTER(ShastaParams), _vp, _vp, _vp, _vp, _vp, _i,
                                 ctypes.POINTER(ShastaGeom), _vp, _sz, _vp, _vp, _u32, _vp]),
     "shasta_gather_pair_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, ctypes.POINTER(ShastaGeom), _vp, _sz, _u32, _vp]),
+    "shasta_greedy_assign_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "shasta_shared_conv_packed_bytes": (_sz, []),
     "shasta_shared_conv_scratch_bytes": (_sz, [_i, _i, _i]),
     "shasta_shared_conv_pack": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, _vp, _sz, _vp]),

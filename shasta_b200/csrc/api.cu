@@ -335,6 +335,31 @@ int shasta_gather_pair_f32(const float* bev, const float* prev_bev, const float*
                        featlo ? workspace + L.off[SHASTA_WS_FEATLO_PREV] : nullptr);
 }
 
+int shasta_greedy_assign_f32(const float* dets, const float* tracks, const float* max_diff, const int32_t* det_cat,
+                             const int32_t* track_cat, const int32_t* n_det, const int32_t* n_track, int problems,
+                             int nmax, int mmax, int32_t* match, int32_t* det_near, int32_t* track_near,
+                             shasta_stream_t stream) {
+  if (problems < 0 || nmax < 0 || mmax < 0 || problems > 1000000) {
+    set_error("greedy_assign: problems, nmax, mmax must be >= 0");
+    return SHASTA_ERR_ARG;
+  }
+  if (problems == 0 || nmax == 0) return 0;
+  NOT_NULL(dets);
+  NOT_NULL(max_diff);
+  NOT_NULL(det_cat);
+  NOT_NULL(n_det);
+  NOT_NULL(n_track);
+  NOT_NULL(match);
+  NOT_NULL(det_near);
+  if (mmax > 0) {
+    NOT_NULL(tracks);
+    NOT_NULL(track_cat);
+    NOT_NULL(track_near);
+  }
+  return launch_greedy_assign(dets, tracks, max_diff, det_cat, track_cat, n_det, n_track, problems, nmax, mmax, match,
+                              det_near, track_near, (cudaStream_t)stream);
+}
+
 size_t shasta_shared_conv_packed_bytes(void) { return shared_conv_packed_floats() * sizeof(float); }
 
 size_t shasta_shared_conv_scratch_bytes(int nmaps, int height, int width) {

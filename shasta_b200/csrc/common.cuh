@@ -309,6 +309,9 @@ int launch_backward_anchor(const shasta_params_t& p, const shasta_grads_t& g, in
                            const WsLayout& L, cudaStream_t s);
 int launch_backward_box(const shasta_params_t& p, const shasta_grads_t& g, int B, float* ws, const WsLayout& L,
                         cudaStream_t s);
+int launch_greedy_assign(const float* dets, const float* tracks, const float* max_diff, const int32_t* det_cat,
+                         const int32_t* track_cat, const int32_t* n_det, const int32_t* n_track, int problems, int nmax,
+                         int mmax, int32_t* match, int32_t* det_near, int32_t* track_near, cudaStream_t s);
 size_t shared_conv_packed_floats();
 int launch_shared_conv_pack(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,
                             const float* var, float eps, float* packed, cudaStream_t s);
