@@ -503,8 +503,16 @@ def main():
     ah_ms = stages["anchor_hidden"]
     achieved = ab / (ah_ms / 1e3) / 1e9 if ah_ms > 0 else 0.0
     tc_path = a.anchor_path == 2 or (a.anchor_path == 0 and B > 8)
-    roofline = {"kernel": "anchor_hidden_tc_kernel" if tc_path else "anchor_hidden_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+    traffic = None
+    if tc_path and M == 200 and B == 64:   # dram read+write of one launch from the committed ncu --set full capture
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[
+                "anchor_hidden_tc2_kernel<64>"]["traffic_bytes_per_launch"]
+        except Exception:  # noqa: BLE001
+            traffic = None
+    roofline = {"kernel": "anchor_hidden_tc2_kernel<64> (aug_shape.i.0, the 1.03 GB weight stream)" if tc_path
+                else "anchor_hidden_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab, "ms_per_launch": ah_ms, "dominant_stage_by_time": dom,
                 "stage_ms": stages, "step_share": ah_ms / max(sum(stages.values()), 1e-9),
                 "path_bytes_per_step": path_bytes(M, B, a.hw),
