@@ -502,7 +502,7 @@ def main():
     ab = algorithmic_bytes_anchor_hidden(M, B)
     ah_ms = stages["anchor_hidden"]
     achieved = ab / (ah_ms / 1e3) / 1e9 if ah_ms > 0 else 0.0
-    tc_path = a.anchor_path == 2 or (a.anchor_path == 0 and B > 8)
+    tc_path = a.anchor_path == 2 or (a.anchor_path == 0 and B > 4)
     traffic = None
     if tc_path and M == 200 and B == 64:   # dram read+write of one launch from the committed ncu --set full capture
         try:

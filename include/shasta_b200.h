@@ -137,7 +137,7 @@ enum shasta_region {
 };
 
 /* Runtime options (process-wide, not thread-safe; meant for tests and benchmarks).
- *   SHASTA_OPT_ANCHOR_PATH: 0 = auto (streaming CUDA-core kernel up to 8 frame pairs, tcgen05 3xTF32 GEMM above),
+ *   SHASTA_OPT_ANCHOR_PATH: 0 = auto (streaming CUDA-core kernel up to 4 frame pairs, tcgen05 3xTF32 GEMM above),
  *                           1 = always the streaming kernel, 2 = always the tcgen05 kernel (TMEM-resident weight
  *                           low parts, bounded accumulation chains), 3 = the first-generation tcgen05 kernel.
  *   SHASTA_OPT_TC_RAW_HI:   1 (default) = the tcgen05 anchors kernels feed the raw fp32 tile as the tf32 "high" part:

@@ -312,12 +312,12 @@ int launch_anchor_hidden_tc(const shasta_params_t& p, const float* feat_cur, con
 
 bool anchor_uses_featlo(int M, int B) {
   const int mode = g_options[SHASTA_OPT_ANCHOR_PATH];
-  return mode == 2 || (mode == 0 && B > 8);
+  return mode == 2 || (mode == 0 && B > kAnchorTcMinBatch);
 }
 
 int anchor_splits_in_use(int M, int B) {
   const int mode = g_options[SHASTA_OPT_ANCHOR_PATH];
-  if (mode == 2 || (mode == 0 && B > 8)) return anchor_tc2_splits(M, B);
+  if (mode == 2 || (mode == 0 && B > kAnchorTcMinBatch)) return anchor_tc2_splits(M, B);
   if (mode == 3) return anchor_tc_splits(M, B);
   return hidden_splits(M);
 }
@@ -334,10 +334,11 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   // tensor-core GEMM wins.  option 0: 0 = auto, 1 = streaming kernel, 2 = tcgen05 kernel, 3 = first-gen tcgen05
   const int mode = g_options[SHASTA_OPT_ANCHOR_PATH];
   int S;
-  bool out_tc = false;   // aug_shape.i.2 on tensor cores too (TMA needs 16-byte row pitch: 5M floats, M % 4 == 0)
-  if (mode == 2 || (mode == 0 && B > 8)) {        // tcgen05, weights on the M side, TMEM-resident low parts
-    out_tc = (M % 4) == 0;
-    for (int i = 0; i < 4; ++i) out_tc = out_tc && (((uintptr_t)p.aug_shape_w2[i] & 15) == 0);
+  // aug_shape.i.2 on tensor cores whatever kernel computed the hidden layer (TMA needs a 16-byte row pitch: 5M
+  // floats, M % 4 == 0); option 1 (streaming kernels only) keeps the CUDA-core finish kernel
+  bool out_tc = (M % 4) == 0 && mode != 1;
+  for (int i = 0; i < 4; ++i) out_tc = out_tc && (((uintptr_t)p.aug_shape_w2[i] & 15) == 0);
+  if (mode == 2 || (mode == 0 && B > kAnchorTcMinBatch)) {        // tcgen05, weights on the M side, TMEM-resident low parts
     S = anchor_tc2_splits(M, B);
     int rc = launch_anchor_hidden_tc2(p, feat_cur, feat_prev, ws + L.off[SHASTA_WS_FEATLO_CUR],
                                       ws + L.off[SHASTA_WS_FEATLO_PREV], featlo_ready, B, S, part, s);

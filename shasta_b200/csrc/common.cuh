@@ -18,6 +18,9 @@ constexpr int kNF = 3;
 constexpr int kAnchorKRange = 2048;   // floats of K one CTA of the hidden kernel covers
 constexpr int kAnchorKChunk = 1024;   // floats of K staged in shared memory at a time
 constexpr int kAnchorRowsPerCta = 32; // 8 warps x 4 weight rows
+// auto anchors path: the tcgen05 GEMM from 5 frame pairs on (measured at M = 200: streaming 0.156 / 0.177 / 0.250 ms
+// at B = 2 / 4 / 8, tcgen05 0.185 ms flat)
+constexpr int kAnchorTcMinBatch = 4;
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline int hidden_splits(int M) { return (kF * M + kAnchorKRange - 1) / kAnchorKRange; }
