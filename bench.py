@@ -577,6 +577,7 @@ def run_e2e(a, model, bev, prev_bev, det0, prev, device, dist, world):
     e0.record()
     for _ in range(a.steps):
         step()
+    enqueue_ms = (time.perf_counter() - t0) * 1e3
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -589,7 +590,7 @@ def run_e2e(a, model, bev, prev_bev, det0, prev, device, dist, world):
     h2d = 2 * B * M * 11 * 4 + taps
     d2h = B * (M * (M + 2) + (M + 2) * M) * 4 + B * M * 11 * 4
     return {"value": world * B * a.steps / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "ms_per_step": ms / a.steps,
+            "d2h_bytes_per_step": d2h, "ms_per_step": ms / a.steps, "host_enqueue_ms_per_step": enqueue_ms / a.steps,
             "note": "pinned host inputs; BEV maps sampled in place over PCIe (tap bytes counted), boxes copied, "
                     "matched1/matched2 and the back-projected boxes copied back; box upload + gather of step i+1 "
                     "overlap the other stages and the D2H copies of step i (side stream, two workspaces); a ring of "

@@ -146,13 +146,15 @@ enum shasta_region {
  *   (2, 3: kernel experiment knobs of bench.py: debug bits, forced split-K count.)
  *   SHASTA_OPT_AFF_PATH:    0 = auto (tcgen05 3xTF32 row tiles when max_obj + 2 <= 224, CUDA-core tiles otherwise),
  *                           1 = always the CUDA-core kernel, 2 = always the tcgen05 kernel (error if unavailable).
- *   SHASTA_OPT_PROJECT_PATH: same values for the first-layer projection GEMM. */
+ *   SHASTA_OPT_PROJECT_PATH: same values for the first-layer projection GEMM.
+ *   SHASTA_OPT_HOST_GATHER_CTAS: CTAs per frame of the narrow gather used for host-resident maps (0 = default). */
 enum shasta_option {
   SHASTA_OPT_ANCHOR_PATH = 0,
   SHASTA_OPT_TC_RAW_HI = 1,
   SHASTA_OPT_AFF_PATH = 4,
   SHASTA_OPT_PROJECT_PATH = 5,
-  SHASTA_OPT_COUNT = 6
+  SHASTA_OPT_HOST_GATHER_CTAS = 6,
+  SHASTA_OPT_COUNT = 7
 };
 SHASTA_API int shasta_set_option(int option, int value);
 SHASTA_API int shasta_get_option(int option);
@@ -220,9 +222,11 @@ SHASTA_API int shasta_aff_softmax_f32(const float* packed, int batch, int max_ob
 /* Whole path, shasta.py:231-325 from the 64-channel channels-last maps: bev/prev_bev (B,H,W,64),
  * det_boxes/prev_det_boxes (B,M,11). det_boxes[:,:,:2] is back-projected IN PLACE like the reference.
  * Outputs matched1 (B,M,M+2), matched2 (B,M+2,M); the anchors stay in the workspace (ANCHOR_BOX).
- * flags: bit0 = TMA-staged gather, bits 4-7 = pairwise variant, bit8 = record per-kernel events (profiling),
+ * flags: bits 0-1 = gather variant (0 LDG, 1 cp.async.bulk staged, 2 LDG on a narrow persistent grid - for
+ * host-resident maps, leaves the SMs to the compute kernels of another stream), bits 4-7 = pairwise variant, bit8 = record per-kernel events (profiling),
  * bit9 = the gather already ran on this workspace (shasta_gather_pair_f32): start at the anchors stage. */
 #define SHASTA_FLAG_TMA_GATHER 0x1u
+#define SHASTA_FLAG_NARROW_GATHER 0x2u
 #define SHASTA_FLAG_PROFILE 0x100u
 #define SHASTA_FLAG_SKIP_GATHER 0x200u
 SHASTA_API int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, const float* bev,

@@ -9,7 +9,7 @@ namespace shasta {
 static thread_local char g_error[512] = "";
 thread_local int g_launch_count = 0;
 static thread_local int g_last_forward_launches = 0;
-int g_options[SHASTA_OPT_COUNT] = {0, 1, 0, 0, 0, 0};  // anchor path auto, raw-hi on
+int g_options[SHASTA_OPT_COUNT] = {0, 1, 0, 0, 0, 0, 0};  // anchor path auto, raw-hi on
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -282,7 +282,7 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
   const bool featlo = anchor_uses_featlo(M, batch);
   if (!(flags & SHASTA_FLAG_SKIP_GATHER)) {
     rc = launch_gather(bev, det_boxes, workspace + L.off[SHASTA_WS_FEAT_CUR], prev_bev, prev_det_boxes,
-                       workspace + L.off[SHASTA_WS_FEAT_PREV], 2, 11, batch, M, *host_geom, fstride, (int)(flags & 1u),
+                       workspace + L.off[SHASTA_WS_FEAT_PREV], 2, 11, batch, M, *host_geom, fstride, (int)(flags & 3u),
                        s, featlo ? workspace + L.off[SHASTA_WS_FEATLO_CUR] : nullptr,
                        featlo ? workspace + L.off[SHASTA_WS_FEATLO_PREV] : nullptr);
     if (rc) return rc;
@@ -330,7 +330,7 @@ int shasta_gather_pair_f32(const float* bev, const float* prev_bev, const float*
   const bool featlo = anchor_uses_featlo(max_obj, batch);
   return launch_gather(bev, det_boxes, workspace + L.off[SHASTA_WS_FEAT_CUR], prev_bev, prev_det_boxes,
                        workspace + L.off[SHASTA_WS_FEAT_PREV], 2, 11, batch, max_obj, *host_geom,
-                       (size_t)(max_obj + 2) * kF, (int)(flags & 1u), (cudaStream_t)stream,
+                       (size_t)(max_obj + 2) * kF, (int)(flags & 3u), (cudaStream_t)stream,
                        featlo ? workspace + L.off[SHASTA_WS_FEATLO_CUR] : nullptr,
                        featlo ? workspace + L.off[SHASTA_WS_FEATLO_PREV] : nullptr);
 }

@@ -121,6 +121,7 @@ __device__ __forceinline__ void box_point_pixels(const float* __restrict__ bx, i
 // ------------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
 constexpr int kPointsPerCta0 = kGatherThreads / 16;
+constexpr int kHostGatherCtas = 16;   // per frame: variant 2 (host-resident maps)
 
 __global__ void __launch_bounds__(kGatherThreads)
 gather_ldg_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, size_t feat_batch_stride) {
@@ -129,9 +130,10 @@ gather_ldg_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, 
   const float* __restrict__ boxes = job.boxes[f];
   float* __restrict__ feat = job.feat[f];
   const int lane16 = threadIdx.x & 15;
-  const long long gp = (long long)blockIdx.x * kPointsPerCta0 + (threadIdx.x >> 4);
   const long long total = (long long)B * M * 5;
-  if (gp >= total) return;
+  // grid-stride over the sample points: variant 2 launches a narrow grid (see launch_gather)
+  for (long long gp = (long long)blockIdx.x * kPointsPerCta0 + (threadIdx.x >> 4); gp < total;
+       gp += (long long)gridDim.x * kPointsPerCta0) {
   const int b = (int)(gp / (5 * M));
   const int rem = (int)(gp % (5 * M));
   const int m = rem / 5, p = rem % 5;
@@ -148,6 +150,7 @@ gather_ldg_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, 
   dst[lane16] = v;
   if (job.featlo[f] != nullptr)
     reinterpret_cast<float4*>(job.featlo[f] + ((size_t)b * M + m) * kF + p * kC)[lane16] = tf32_lo4(v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -256,7 +259,17 @@ int launch_gather(const float* bev0, const float* boxes0, float* feat0, const fl
   job.bev[1] = bev1, job.boxes[1] = boxes1, job.feat[1] = feat1;
   const long long total = (long long)B * M * 5;
   if (total == 0) return 0;
-  if (variant == 1) {
+  if (variant == 2) {
+    // Host-resident (pinned, zero-copy) maps: every tap is a 256-byte PCIe read and the kernel lives as long as the
+    // bus needs (1.6 ms for 64 frame pairs at 55 GB/s). A full-width grid would park stalled warps on every SM and
+    // keep the compute kernels of the previous batch (other stream) from being scheduled; a narrow persistent grid
+    // keeps ~0.5 MB of reads in flight - several times what the bus needs - on a fraction of the SMs.
+    const long long need = (total + kPointsPerCta0 - 1) / kPointsPerCta0;
+    const long long cap = g_options[SHASTA_OPT_HOST_GATHER_CTAS] > 0 ? g_options[SHASTA_OPT_HOST_GATHER_CTAS] : kHostGatherCtas;
+    dim3 grid((unsigned)(need < cap ? need : cap), nframes);
+    gather_ldg_kernel<<<grid, kGatherThreads, 0, s>>>(job, box_stride, B, M, g, feat_batch_stride);
+    SHASTA_CHECK_LAUNCH("gather_ldg_kernel");
+  } else if (variant == 1) {
     dim3 grid((unsigned)((total + kPointsPerCta1 - 1) / kPointsPerCta1), nframes);
     gather_bulk_kernel<<<grid, kGatherThreads, 0, s>>>(job, box_stride, B, M, g, feat_batch_stride);
     SHASTA_CHECK_LAUNCH("gather_bulk_kernel");

@@ -299,7 +299,8 @@ class Shasta(nn.Module):
             det_c.copy_(det_boxes, non_blocking=True)
             prev_c.copy_(prev_det_boxes, non_blocking=True)
             rc = lib.shasta_gather_pair_f32(bev.data_ptr(), prev_bev.data_ptr(), det_c.data_ptr(), prev_c.data_ptr(), B, M,
-                                            ctypes.byref(geom), ws.buf.data_ptr(), ws.nbytes, int(self.kernel_flags),
+                                            ctypes.byref(geom), ws.buf.data_ptr(), ws.nbytes,
+                                            (int(self.kernel_flags) & ~3) | _cabi.FLAG_NARROW_GATHER,  # PCIe-bound: few CTAs suffice
                                             ctypes.c_void_p(side.cuda_stream))
             _cabi.check(rc, "shasta_gather_pair_f32")
             P["gathered"][k].record(side)

@@ -73,7 +73,7 @@ def test_bev_extractor_module_api():
 # ------------------------------------------------------------------------------------------------
 # a1+a2: fused box gather, both samplers
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("name", golden_names())
 def test_gather_from_boxes(name, variant):
     c, pc_start, data, weights, g = load_golden(name)
