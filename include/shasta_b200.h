@@ -224,11 +224,15 @@ SHASTA_API int shasta_aff_softmax_f32(const float* packed, int batch, int max_ob
  * Outputs matched1 (B,M,M+2), matched2 (B,M+2,M); the anchors stay in the workspace (ANCHOR_BOX).
  * flags: bits 0-1 = gather variant (0 LDG, 1 cp.async.bulk staged, 2 LDG on a narrow persistent grid - for
  * host-resident maps, leaves the SMs to the compute kernels of another stream), bits 4-7 = pairwise variant, bit8 = record per-kernel events (profiling),
- * bit9 = the gather already ran on this workspace (shasta_gather_pair_f32): start at the anchors stage. */
+ * bit9 = the gather already ran on this workspace (shasta_gather_pair_f32): start at the anchors stage,
+ * bit10 = no internal side stream. By default the kernels that only need the input boxes (box copy, aug_dets, AUX,
+ * column norms, back-projection) are forked onto a library-owned stream and joined before the projections, so they
+ * overlap the HBM-bound aug_shape GEMM; the caller only ever sees work ordered on `stream`. */
 #define SHASTA_FLAG_TMA_GATHER 0x1u
 #define SHASTA_FLAG_NARROW_GATHER 0x2u
 #define SHASTA_FLAG_PROFILE 0x100u
 #define SHASTA_FLAG_SKIP_GATHER 0x200u
+#define SHASTA_FLAG_NO_OVERLAP 0x400u   /* keep every kernel on `stream` (no internal side stream) */
 SHASTA_API int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, const float* bev,
                        const float* prev_bev, float* det_boxes, const float* prev_det_boxes, int batch,
                        const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes,

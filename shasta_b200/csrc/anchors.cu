@@ -180,7 +180,8 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
       // a warp owns hidden rows warp, warp+8, ... and works on kRH of them at a time: up to 2*kRH 16-byte weight loads
       // in flight per lane (the loop is L2-latency bound: the whole layer is 7M x 7M/32 floats)
       constexpr int kRH = 6;
-      for (int hb = warp; hb < H7; hb += 8 * kRH) {
+      const int nw = blockDim.x >> 5;   // 8 warps, or 4 when the launch shares the SMs with the anchors GEMM
+      for (int hb = warp; hb < H7; hb += nw * kRH) {
         float acc[kRH];
 #pragma unroll
         for (int j = 0; j < kRH; ++j) acc[j] = 0.f;
@@ -193,7 +194,7 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
             float4 w0[kRH], w1[kRH];
 #pragma unroll
             for (int j = 0; j < kRH; ++j) {
-              const int h = hb + 8 * j;
+              const int h = hb + nw * j;
               const float4* w4 = reinterpret_cast<const float4*>(a.dw0[i] + (size_t)min(h, H7 - 1) * K7);
               w0[j] = __ldg(w4 + k0);
               w1[j] = two ? __ldg(w4 + k0 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -211,21 +212,20 @@ anchor_finish_kernel(AnchorFinishArgs a, const float* __restrict__ part, int S, 
             const float x = xb[k];
             float w[kRH];
 #pragma unroll
-            for (int j = 0; j < kRH; ++j) w[j] = __ldg(a.dw0[i] + (size_t)min(hb + 8 * j, H7 - 1) * K7 + k);
+            for (int j = 0; j < kRH; ++j) w[j] = __ldg(a.dw0[i] + (size_t)min(hb + nw * j, H7 - 1) * K7 + k);
 #pragma unroll
             for (int j = 0; j < kRH; ++j) acc[j] = fmaf(w[j], x, acc[j]);
           }
         }
 #pragma unroll
         for (int j = 0; j < kRH; ++j) {
-          const int h = hb + 8 * j;
+          const int h = hb + nw * j;
           const float v = warp_sum(acc[j]);
           if (lane == 0 && h < H7) hd[h] = fmaxf(v + a.db0[i][h], 0.f);
         }
       }
       __syncthreads();
-      if (warp < 8) {   // output c = warp (7 outputs + one zero pad column), lanes over the hidden units
-        const int cc = warp;
+      for (int cc = warp; cc < 8; cc += nw) {   // 7 outputs + one zero pad column, lanes over the hidden units
         float acc = 0.f;
         if (cc < 7)
           for (int h = lane; h < H7; h += 32) acc = fmaf(__ldg(a.dw2[i] + cc * H7 + h), hd[h], acc);
@@ -322,23 +322,35 @@ int anchor_splits_in_use(int M, int B) {
   return hidden_splits(M);
 }
 
-int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
-                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid, bool featlo_ready) {
+// which kernels serve (M, B): hidden layer on tcgen05? output layer on tcgen05 (then anchor_finish only does the boxes)?
+static void anchor_plan(const shasta_params_t& p, int B, bool& tc_hidden, bool& out_tc) {
+  const int M = p.max_obj, mode = g_options[SHASTA_OPT_ANCHOR_PATH];
+  tc_hidden = mode == 2 || (mode == 0 && B > kAnchorTcMinBatch);
+  // aug_shape.i.2 on tensor cores whatever kernel computed the hidden layer (TMA needs a 16-byte row pitch: 5M
+  // floats, M % 4 == 0); option 1 (streaming kernels only) keeps the CUDA-core finish kernel
+  out_tc = (M % 4) == 0 && mode != 1;
+  for (int i = 0; i < 4; ++i) out_tc = out_tc && (((uintptr_t)p.aug_shape_w2[i] & 15) == 0);
+}
+
+bool anchor_boxes_independent(const shasta_params_t& p, int B) {
+  bool a, b;
+  anchor_plan(p, B, a, b);
+  return b;
+}
+
+// aug_shape.i.0 (+ aug_shape.i.2 when it runs on tensor cores); returns the split-K count in *S_out
+int launch_anchor_shapes(const shasta_params_t& p, int B, float* ws, const WsLayout& L, cudaStream_t s, cudaEvent_t mid,
+                         bool featlo_ready, int* S_out) {
   const int M = p.max_obj;
   const int N5 = 5 * M;
   float* feat_cur = ws + L.off[SHASTA_WS_FEAT_CUR];
   float* feat_prev = ws + L.off[SHASTA_WS_FEAT_PREV];
   float* part = ws + L.off[SHASTA_WS_HIDDEN_PART];
-
-  // small batches are pure weight streaming (HBM-bound on CUDA cores); from 9 frame pairs on the 3xTF32
-  // tensor-core GEMM wins.  option 0: 0 = auto, 1 = streaming kernel, 2 = tcgen05 kernel, 3 = first-gen tcgen05
   const int mode = g_options[SHASTA_OPT_ANCHOR_PATH];
+  bool tc_hidden, out_tc;
+  anchor_plan(p, B, tc_hidden, out_tc);
   int S;
-  // aug_shape.i.2 on tensor cores whatever kernel computed the hidden layer (TMA needs a 16-byte row pitch: 5M
-  // floats, M % 4 == 0); option 1 (streaming kernels only) keeps the CUDA-core finish kernel
-  bool out_tc = (M % 4) == 0 && mode != 1;
-  for (int i = 0; i < 4; ++i) out_tc = out_tc && (((uintptr_t)p.aug_shape_w2[i] & 15) == 0);
-  if (mode == 2 || (mode == 0 && B > kAnchorTcMinBatch)) {        // tcgen05, weights on the M side, TMEM-resident low parts
+  if (tc_hidden) {                                // tcgen05, weights on the M side, TMEM-resident low parts
     S = anchor_tc2_splits(M, B);
     int rc = launch_anchor_hidden_tc2(p, feat_cur, feat_prev, ws + L.off[SHASTA_WS_FEATLO_CUR],
                                       ws + L.off[SHASTA_WS_FEATLO_PREV], featlo_ready, B, S, part, s);
@@ -347,7 +359,7 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
     S = anchor_tc_splits(M, B);
     int rc = launch_anchor_hidden_tc(p, feat_cur, feat_prev, B, S, part, s);
     if (rc) return rc;
-  } else {
+  } else {                                        // small batches: pure weight streaming on CUDA cores
     S = hidden_splits(M);
     AnchorW0 w;
     for (int i = 0; i < 4; ++i) w.w0[i] = p.aug_shape_w0[i];
@@ -368,7 +380,22 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
                                   feat_prev, s);
     if (rc) return rc;
   }
+  if (S_out) *S_out = S;
+  return 0;
+}
 
+// anchor_finish_kernel: box copy + back-projection and aug_dets (roles 4-8) and, unless the output layer ran on
+// tensor cores, the aug_shape.i.2 roles 0-3 (those need the split-K partials: S). `light` = 128-thread CTAs with
+// the small shared-memory footprint, so that the launch can share the SMs with the anchors GEMM of another stream.
+int launch_anchor_boxes(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
+                        const WsLayout& L, int S, bool light, cudaStream_t s) {
+  const int M = p.max_obj;
+  const int N5 = 5 * M;
+  float* feat_cur = ws + L.off[SHASTA_WS_FEAT_CUR];
+  float* feat_prev = ws + L.off[SHASTA_WS_FEAT_PREV];
+  float* part = ws + L.off[SHASTA_WS_HIDDEN_PART];
+  bool tc_hidden, out_tc;
+  anchor_plan(p, B, tc_hidden, out_tc);
   AnchorFinishArgs a;
   for (int i = 0; i < 4; ++i) {
     a.b0[i] = p.aug_shape_b0[i];
@@ -381,11 +408,8 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
   }
   const int H7 = (7 * M) / 32;
   const int BG = (B > 4 && (size_t)8 * (N5 + H7 + 1) * sizeof(float) <= 200 * 1024) ? 8 : 4;
-  const size_t smem_shape = sizeof(float) * (size_t)BG * N5;
-  // anchor-box role: frame pairs staged at once (all BG of them unless that needs more than 160 KB)
-  int nbx = (int)((160u * 1024u) / (sizeof(float) * (size_t)(7 * M + (H7 > 0 ? H7 : 1))));
-  nbx = nbx > BG ? BG : (nbx < 1 ? 1 : nbx);
-  const size_t smem_dets = sizeof(float) * (size_t)nbx * (size_t)(7 * M + (H7 > 0 ? H7 : 1));
+  const size_t smem_shape = out_tc ? 0 : sizeof(float) * (size_t)BG * N5;
+  const size_t smem_dets = sizeof(float) * (size_t)(7 * M + (H7 > 0 ? H7 : 1));
   const size_t smem = smem_shape > smem_dets ? smem_shape : smem_dets;
   static size_t configured[2] = {0, 0};
   if (smem > 48 * 1024 && smem > configured[BG == 8]) {
@@ -395,21 +419,40 @@ int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float
       SHASTA_CUDA(cudaFuncSetAttribute(anchor_finish_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[BG == 8] = smem;
   }
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    // same shared-memory carve-out as the big-smem GEMM kernels: an SM only runs kernels of one carve-out at a time,
+    // and the light launch is meant to co-reside with the anchors GEMM
+    SHASTA_CUDA(cudaFuncSetAttribute(anchor_finish_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+    SHASTA_CUDA(cudaFuncSetAttribute(anchor_finish_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+    carveout_set = true;
+  }
   const int groups = (B + BG - 1) / BG;
   const int slices = (groups >= 16) ? 2 : (groups >= 6 ? 5 : 10);  // 320 outputs = 10 passes of 32 rows
   const int role0 = out_tc ? 4 : 0;
+  const int threads = (light && out_tc) ? 128 : 256;
   dim3 fgrid(9 - role0, slices, groups);  // roles: 0-3 anchor shapes, 4 box copy, 5-8 anchor boxes
   float* bc = ws + L.off[SHASTA_WS_BOX_CUR];
   float* bp = ws + L.off[SHASTA_WS_BOX_PREV];
   float* ab = ws + L.off[SHASTA_WS_ANCHOR_BOX];
   if (BG == 8)
-    anchor_finish_kernel<8><<<fgrid, 256, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev, bc,
-                                                     bp, ab, nbx, ws + L.off[SHASTA_WS_RAW_XY], role0);
+    anchor_finish_kernel<8><<<fgrid, threads, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev,
+                                                         bc, bp, ab, 1, ws + L.off[SHASTA_WS_RAW_XY], role0);
   else
-    anchor_finish_kernel<4><<<fgrid, 256, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev, bc,
-                                                     bp, ab, nbx, ws + L.off[SHASTA_WS_RAW_XY], role0);
+    anchor_finish_kernel<4><<<fgrid, threads, smem, s>>>(a, part, S, det_boxes, prev_boxes, B, M, feat_cur, feat_prev,
+                                                         bc, bp, ab, 1, ws + L.off[SHASTA_WS_RAW_XY], role0);
   SHASTA_CHECK_LAUNCH("anchor_finish_kernel");
   return 0;
+}
+
+int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
+                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid, bool featlo_ready) {
+  int S = 1;
+  int rc = launch_anchor_shapes(p, B, ws, L, s, mid, featlo_ready, &S);
+  if (rc) return rc;
+  return launch_anchor_boxes(p, det_boxes, prev_boxes, B, ws, L, S, false, s);
 }
 
 }  // namespace shasta

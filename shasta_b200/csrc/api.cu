@@ -31,6 +31,28 @@ cudaEvent_t* profile_slot() {
   return g_prof.ev + (size_t)(g_prof.steps++) * (kStages + 1);
 }
 
+// ---- side stream of the fused forward: the box half of the anchors stage and the AUX / column-norm kernel only
+// need the input boxes, so they run next to the (HBM-bound, one CTA per SM) anchors GEMM instead of after it -------
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream g_side[64];
+static SideStream* side_stream() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& ss = g_side[dev];
+  if (ss.stream == nullptr) {
+    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) {
+      ss = SideStream();
+      return nullptr;
+    }
+  }
+  return &ss;
+}
+
 static int check_dims(int batch, int max_obj) {
   if (batch < 0 || batch > 65535) {
     set_error("batch %d out of range [0, 65535]", batch);
@@ -288,12 +310,34 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
     if (rc) return rc;
   }
   STAGE_MARK(1);
-  rc = launch_anchors(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, s, ev ? ev[2] : nullptr,
-                      featlo);  // a3-a4
-  if (rc) return rc;
-  STAGE_MARK(3);
-  rc = launch_project(packed, batch, M, workspace, L, det_boxes, s);  // first layers, aux, colnorm, back-projection
-  if (rc) return rc;
+  SideStream* side = (ev == nullptr && !(flags & SHASTA_FLAG_NO_OVERLAP) && anchor_boxes_independent(*host_params, batch) &&
+                      project_uses_tc(batch, M))
+                         ? side_stream()
+                         : nullptr;
+  if (side != nullptr) {
+    // fork: [box copy, aug_dets, AUX, column norms, back-projection] || [aug_shape GEMMs]; join before the projections
+    SHASTA_CUDA(cudaEventRecord(side->fork, s));
+    SHASTA_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    // the GEMM is submitted FIRST: its one-CTA-per-SM grid takes its shared memory and registers, the light box
+    // kernels then fit into what is left of every SM (the other order parks them first and the GEMM CTAs wait)
+    rc = launch_anchor_shapes(*host_params, batch, workspace, L, s, nullptr, featlo, nullptr);  // a3
+    if (rc) return rc;
+    rc = launch_anchor_boxes(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, 1, true, side->stream);
+    if (rc) return rc;
+    rc = launch_project_aux(batch, M, workspace, L, det_boxes, side->stream);
+    if (rc) return rc;
+    SHASTA_CUDA(cudaEventRecord(side->join, side->stream));
+    SHASTA_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+    rc = launch_project_gemm_tc(packed, batch, M, workspace, L, s);  // decomposed first layers
+    if (rc) return rc;
+  } else {
+    rc = launch_anchors(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, s, ev ? ev[2] : nullptr,
+                        featlo);  // a3-a4
+    if (rc) return rc;
+    STAGE_MARK(3);
+    rc = launch_project(packed, batch, M, workspace, L, det_boxes, s);  // first layers, aux, colnorm, back-projection
+    if (rc) return rc;
+  }
   STAGE_MARK(4);
   rc = launch_pairwise(packed, batch, M, workspace, L, (int)((flags >> 4) & 15u), s);  // a5-a9
   if (rc) return rc;

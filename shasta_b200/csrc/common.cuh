@@ -320,6 +320,14 @@ int launch_shared_conv_pack(const float* w, const float* bias, const float* gamm
                             const float* var, float eps, float* packed, cudaStream_t s);
 int launch_shared_conv(const float* packed, const float* x_nchw, int nmaps, int H, int W, float* scratch,
                        float* out_nhwc, cudaStream_t s);
+bool anchor_boxes_independent(const shasta_params_t& p, int B);   // the box part of the anchors stage needs no GEMM result
+int launch_anchor_shapes(const shasta_params_t& p, int B, float* ws, const WsLayout& L, cudaStream_t s, cudaEvent_t mid,
+                         bool featlo_ready, int* S_out);
+int launch_anchor_boxes(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
+                        const WsLayout& L, int S, bool light, cudaStream_t s);
+bool project_uses_tc(int B, int M);
+int launch_project_aux(int B, int M, float* ws, const WsLayout& L, float* det_boxes_inout, cudaStream_t s);
+int launch_project_gemm_tc(const float* packed, int B, int M, float* ws, const WsLayout& L, cudaStream_t s);
 bool anchor_uses_featlo(int M, int B);  // true when the anchors path in use for (M, B) reads the FEATLO_* regions
 int anchor_splits_in_use(int M, int B);  // split-K count the forward anchors kernel uses for this (M, B)
 int launch_decode(const float* m1, const float* m2, const int32_t* n_prev, const int32_t* n_det, int B, int M,

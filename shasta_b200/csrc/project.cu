@@ -171,13 +171,85 @@ project_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, int
   }
 }
 
+// AUX_*, COLNORM and the in-place back-projection on their own (small shared-memory footprint: the launch can share the
+// SMs with the anchors GEMM of another stream). Blocks [0, naux): 128 objects each; blocks [naux, naux+B): column norms.
+__global__ void __launch_bounds__(kProjThreads)
+project_aux_kernel(int B, int M, int naux, const float* __restrict__ box_cur, const float* __restrict__ box_prev,
+                   float* __restrict__ aux_prev, float* __restrict__ aux_cur, float* __restrict__ colnorm,
+                   float* __restrict__ det_boxes_inout) {
+  const int T = M + 2;
+  extern __shared__ float sp[];   // column-norm blocks: T x 3 previous-box centres
+  if ((int)blockIdx.x >= naux) {
+    const int b = blockIdx.x - naux;
+    for (int idx = threadIdx.x; idx < T * 3; idx += blockDim.x)
+      sp[idx] = box_prev[((size_t)b * T + idx / 3) * 8 + idx % 3];
+    __syncthreads();
+    for (int d = threadIdx.x; d < T; d += blockDim.x) {
+      const float* c = box_cur + ((size_t)b * T + d) * 8;
+      const float cx = c[0], cy = c[1], cz = c[2];
+      float acc = 0.f;
+      for (int t = 0; t < T; ++t) {
+        const float dx = sp[t * 3] - cx, dy = sp[t * 3 + 1] - cy, dz = sp[t * 3 + 2] - cz;
+        const float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        acc = fmaf(dist, dist, acc);
+      }
+      colnorm[(size_t)b * T + d] = sqrtf(acc);
+      if (det_boxes_inout != nullptr && d < M) {
+        det_boxes_inout[((size_t)b * M + d) * 11 + 0] = cx;
+        det_boxes_inout[((size_t)b * M + d) * 11 + 1] = cy;
+      }
+    }
+    return;
+  }
+  const long long total = 2LL * B * T;   // side 0 = previous frame rows, side 1 = current frame rows
+  const long long o = (long long)blockIdx.x * kProjThreads + threadIdx.x;
+  if (o >= total) return;
+  const int side = (int)(o / ((long long)B * T));
+  const long long row = o % ((long long)B * T);
+  const float* box = (side ? box_cur : box_prev) + (size_t)row * 8;
+  float* aux = (side ? aux_cur : aux_prev) + (size_t)row * 8;
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(box)), hi = __ldg(reinterpret_cast<const float4*>(box) + 1);
+  const float eps = 1e-10f;
+  reinterpret_cast<float4*>(aux)[0] = make_float4(lo.x, lo.y, lo.z, logf(__fadd_rn(lo.w, eps)));
+  reinterpret_cast<float4*>(aux)[1] =
+      make_float4(logf(__fadd_rn(hi.x, eps)), logf(__fadd_rn(hi.y, eps)), cosf(hi.z), sinf(hi.z));
+}
+
 int launch_project_tc(const float* packed, int B, int M, float* ws, const WsLayout& L, cudaStream_t s);  // project_tc.cu
+
+bool project_uses_tc(int B, int M) {
+  const int mode = g_options[SHASTA_OPT_PROJECT_PATH];
+  return mode == 2 || (mode == 0 && (long long)B * (M + 2) >= 128);   // below one row tile the FFMA kernel wins
+}
+
+int launch_project_aux(int B, int M, float* ws, const WsLayout& L, float* det_boxes_inout, cudaStream_t s) {
+  const int T = M + 2;
+  const int naux = (int)((2LL * B * T + kProjThreads - 1) / kProjThreads);
+  static bool carveout_set = false;
+  if (!carveout_set) {   // co-resides with the anchors GEMM: same (maximum) shared-memory carve-out
+    SHASTA_CUDA(cudaFuncSetAttribute(project_aux_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+    carveout_set = true;
+  }
+  project_aux_kernel<<<naux + B, kProjThreads, sizeof(float) * 3 * T, s>>>(
+      B, M, naux, ws + L.off[SHASTA_WS_BOX_CUR], ws + L.off[SHASTA_WS_BOX_PREV], ws + L.off[SHASTA_WS_AUX_PREV],
+      ws + L.off[SHASTA_WS_AUX_CUR], ws + L.off[SHASTA_WS_COLNORM], det_boxes_inout);
+  SHASTA_CHECK_LAUNCH("project_aux_kernel");
+  return 0;
+}
+
+int launch_project_gemm_tc(const float* packed, int B, int M, float* ws, const WsLayout& L, cudaStream_t s) {
+  return launch_project_tc(packed, B, M, ws, L, s);
+}
 
 int launch_project(const float* packed, int B, int M, float* ws, const WsLayout& L, float* det_boxes_inout,
                    cudaStream_t s) {
   const int T = M + 2;
-  const int mode = g_options[SHASTA_OPT_PROJECT_PATH];
-  const bool tc = mode == 2 || (mode == 0 && (long long)B * T >= 128);   // below one row tile the FFMA kernel wins
+  if (project_uses_tc(B, M)) {
+    int rc = launch_project_aux(B, M, ws, L, det_boxes_inout, s);
+    if (rc) return rc;
+    return launch_project_tc(packed, B, M, ws, L, s);
+  }
   const int tiles = (T + kProjObjPerCta - 1) / kProjObjPerCta;
   const int nproj = 2 * B * tiles;
   project_kernel<<<nproj + B, kProjThreads, 0, s>>>(
@@ -185,9 +257,8 @@ int launch_project(const float* packed, int B, int M, float* ws, const WsLayout&
       ws + L.off[SHASTA_WS_BOX_CUR], ws + L.off[SHASTA_WS_BOX_PREV], ws + L.off[SHASTA_WS_PROJ_PREV],
       ws + L.off[SHASTA_WS_PROJ_CUR], ws + L.off[SHASTA_WS_PROJ_CUR_T], ws + L.off[SHASTA_WS_AUX_PREV],
       ws + L.off[SHASTA_WS_AUX_CUR],
-      ws + L.off[SHASTA_WS_COLNORM], det_boxes_inout, tc ? 0 : 1);
+      ws + L.off[SHASTA_WS_COLNORM], det_boxes_inout, 1);
   SHASTA_CHECK_LAUNCH("project_kernel");
-  if (tc) return launch_project_tc(packed, B, M, ws, L, s);
   return 0;
 }
 

@@ -414,6 +414,27 @@ def test_cuda_graph_replay_matches_eager(M, B):
     assert len(model._graphs) == 1
 
 
+def test_internal_side_stream_changes_nothing():
+    """The box-only kernels run on a library-owned stream next to the anchors GEMM (fork / join inside
+    shasta_forward_f32); flag 0x400 keeps everything on the caller's stream. Same kernels, same results."""
+    M, B, H, W = 200, 12, 32, 32
+    pc_start = (-W * 0.3, -H * 0.3)
+    model = G.make_model(M, pc_start, synthetic.make_weights(M, seed=8))
+    d = synthetic.make_frame_pairs(B, M, H, W, 51, pc_start=pc_start)
+    args = [G.t(d[k]) for k in ("bev", "prev_bev", "det_boxes", "prev_det_boxes")]
+    with torch.no_grad():
+        out = {}
+        for flags in (0, 0x400):
+            model.kernel_flags = flags
+            det = args[2].clone()
+            for _ in range(3):   # repeated calls reuse the side stream and its events
+                det.copy_(args[2])
+                m1, m2 = model.affinity(args[0], args[1], det, args[3])
+            out[flags] = (m1.clone(), m2.clone(), det.clone())
+    for a, b in zip(out[0], out[0x400]):
+        assert torch.equal(a, b)
+
+
 def test_pipelined_host_inputs_match_device_path():
     """Pinned host inputs run the gather on a side stream into alternating workspaces (two-stage pipeline over calls):
     every call must return what the plain device path returns, including the in-place back-projection."""
