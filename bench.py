@@ -414,11 +414,38 @@ def main():
     # multi-GPU: every step's compact decode output (4 int32 + 2 float32 planes of (B,M)) lands in one block that is
     # all-gathered ONCE at the end of the timed region - the only collective of the path
     dec_pack = torch.empty((a.steps, 6, B, M), dtype=torch.int32, device=device) if world > 1 else None
+    dec_one = torch.empty((6, B, M), dtype=torch.int32, device=device) if world > 1 else None
+    # one CUDA graph per step: box refresh + forward (+ decode when results are gathered across ranks); the model's own
+    # per-call graph cache is not needed on top of it
+    inner = bool(os.environ.get("BENCH_INNER_GRAPH"))   # A/B knob: the model's per-call graph instead of the step graph
+    model.cuda_graphs = inner and not a.no_graph
 
-    def step():
+    def step_body():
         det.copy_(det0)  # fresh boxes every step (the forward back-projects det_boxes in place)
         m1, m2 = model.affinity(bev, prev_bev, det, prev)
+        if world > 1:
+            o = [dec_one[i].data_ptr() for i in range(6)]  # prev_state, prev_argmax, fn_score, det_state, ...
+            rc = lib.shasta_decode_f32(m1.data_ptr(), m2.data_ptr(), n_prev.data_ptr(), n_det.data_ptr(), B, M,
+                                       o[0], o[1], o[2], o[3], o[4], o[5],
+                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            _cabi.check(rc, "decode")
         return m1, m2
+
+    step_graph = {"g": None, "out": None}
+
+    def step():
+        if a.no_graph or inner:
+            return step_body()
+        if step_graph["g"] is None:
+            for _ in range(2):   # eager runs first: one-time kernel attribute set-up must not happen inside a capture
+                step_body()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step_graph["out"] = step_body()
+            step_graph["g"] = g
+        step_graph["g"].replay()
+        return step_graph["out"]
 
     def barrier():
         if dist is not None:
@@ -448,11 +475,7 @@ def main():
         for it in range(a.steps):
             m1, m2 = step()
             if world > 1:
-                o = [dec_pack[it, i].data_ptr() for i in range(6)]  # prev_state, prev_argmax, fn_score, det_state, ...
-                rc = lib.shasta_decode_f32(m1.data_ptr(), m2.data_ptr(), n_prev.data_ptr(), n_det.data_ptr(), B, M,
-                                           o[0], o[1], o[2], o[3], o[4], o[5],
-                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-                _cabi.check(rc, "decode")
+                dec_pack[it].copy_(dec_one)   # this step's compact decode output
         if world > 1:  # NCCL only gathers the per-rank results
             gathered = sharding.gather_rank_blocks(dec_pack)  # (world, steps, 6, B, M) on every rank
             assert gathered.shape[0] == world
@@ -478,7 +501,7 @@ def main():
         model.kernel_flags = a.flags | 0x100
         _cabi.check(lib.shasta_profile_begin(a.steps), "profile_begin")
         for _ in range(a.steps):
-            step()
+            step_body()
         stage_ms = (ctypes.c_float * 7)()
         nsteps = ctypes.c_int(0)
         _cabi.check(lib.shasta_profile_end(stage_ms, ctypes.byref(nsteps)), "profile_end")

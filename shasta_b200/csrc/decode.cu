@@ -45,12 +45,31 @@ decode_kernel(const float* __restrict__ m1, const float* __restrict__ m2, const 
     fn_score[(size_t)b * M + n] = score;
   }
   __syncthreads();
-  // ordered compaction of the kept rows (keep_prev_dets)
-  if (threadIdx.x == 0) {
-    int c = 0;
-    for (int n = 0; n < np; ++n)
-      if (prev_state[(size_t)b * M + n] == 0) s_keep[c++] = n;
-    s_nkeep = c;
+  // ordered compaction of the kept rows (keep_prev_dets): ballot + warp-total scan, 256 rows per pass
+  {
+    __shared__ int s_wtot[kDecThreads / 32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int n0 = 0; n0 < np; n0 += kDecThreads) {
+      const int n = n0 + threadIdx.x;
+      const bool keep = n < np && prev_state[(size_t)b * M + n] == 0;   // written by this same thread above
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) s_wtot[warp] = __popc(bal);
+      __syncthreads();
+      int off = s_base;
+      for (int w = 0; w < warp; ++w) off += s_wtot[w];
+      if (keep) s_keep[off + __popc(bal & ((1u << lane) - 1u))] = n;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < kDecThreads / 32; ++w) tot += s_wtot[w];
+        s_base += tot;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) s_nkeep = s_base;
   }
   __syncthreads();
   const int nk = s_nkeep;

@@ -625,6 +625,26 @@ def test_decode_on_planted_matrices():
     _check_decode(m1, m2, n_prev, n_det)
 
 
+def test_decode_large_rows_compaction():
+    """More previous objects than one 256-row compaction pass; kept rows interleaved with dead / FN ones."""
+    rng = np.random.default_rng(9)
+    B, M = 3, 600
+    m1 = rng.uniform(0, 0.45, (B, M, M + 2)).astype(np.float32)
+    m2 = rng.uniform(0, 0.45, (B, M + 2, M)).astype(np.float32)
+    n_prev, n_det = [600, 257, 511], [600, 300, 64]
+    for b in range(B):
+        for n in range(n_prev[b]):
+            r = rng.integers(0, 4)
+            if r == 0:
+                m1[b, n, M] = 0.9
+            elif r == 1:
+                m1[b, n, M + 1] = 0.8
+        for k in range(n_det[b]):
+            if rng.integers(0, 3) == 0:
+                m2[b, rng.integers(0, n_prev[b]), k] = 0.99
+    _check_decode(m1, m2, n_prev, n_det)
+
+
 def test_decode_on_peaky_golden():
     c, pc_start, data, weights, g = load_golden("m20_32px_b3_peaky")
     _check_decode(g["matched1"], g["matched2"], [int(x) for x in data["n_prev"]], [int(x) for x in data["n_det"]])
