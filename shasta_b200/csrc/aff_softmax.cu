@@ -63,7 +63,11 @@ aff_row_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, con
   }
 }
 
-// matched2[b][t][d] = softmax over t of logits[b][t][d], d < M.  block (32 columns, 8 row slices)
+// matched2[b][t][d] = softmax over t of logits[b][t][d], d < M.  block (32 columns, 8 row slices).
+// A thread keeps its column slice (rows ty, ty+8, ...) in registers when T <= 8 * kColRegs, so the logits are read
+// once; longer columns fall back to re-reading them (L2-resident).
+constexpr int kColRegs = 32;
+
 __global__ void __launch_bounds__(256)
 col_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __restrict__ matched2) {
   __shared__ float red[8][33];
@@ -72,18 +76,39 @@ col_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __rest
   const int d = blockIdx.x * 32 + threadIdx.x;
   const int ty = threadIdx.y;
   const bool valid = d < M;
+  const bool in_regs = T <= 8 * kColRegs;
   const float* src = logits + (size_t)b * T * RS + d;
+  float v[kColRegs];
   float mx = -INFINITY;
-  if (valid)
-    for (int t = ty; t < T; t += 8) mx = fmaxf(mx, src[(size_t)t * RS]);
+  if (valid) {
+    if (in_regs) {
+#pragma unroll
+      for (int i = 0; i < kColRegs; ++i) {
+        const int t = ty + 8 * i;
+        v[i] = (t < T) ? src[(size_t)t * RS] : -INFINITY;
+        mx = fmaxf(mx, v[i]);
+      }
+    } else {
+      for (int t = ty; t < T; t += 8) mx = fmaxf(mx, src[(size_t)t * RS]);
+    }
+  }
   red[ty][threadIdx.x] = mx;
   __syncthreads();
 #pragma unroll
   for (int y = 0; y < 8; ++y) mx = fmaxf(mx, red[y][threadIdx.x]);
   __syncthreads();
   float sum = 0.f;
-  if (valid)
-    for (int t = ty; t < T; t += 8) sum += expf(src[(size_t)t * RS] - mx);
+  if (valid) {
+    if (in_regs) {
+#pragma unroll
+      for (int i = 0; i < kColRegs; ++i) {
+        v[i] = (ty + 8 * i < T) ? expf(v[i] - mx) : 0.f;
+        sum += v[i];
+      }
+    } else {
+      for (int t = ty; t < T; t += 8) sum += expf(src[(size_t)t * RS] - mx);
+    }
+  }
   red[ty][threadIdx.x] = sum;
   __syncthreads();
   sum = 0.f;
@@ -91,7 +116,15 @@ col_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __rest
   for (int y = 0; y < 8; ++y) sum += red[y][threadIdx.x];
   if (valid) {
     float* dst = matched2 + (size_t)b * T * M + d;
-    for (int t = ty; t < T; t += 8) dst[(size_t)t * M] = __fdiv_rn(expf(src[(size_t)t * RS] - mx), sum);
+    if (in_regs) {
+#pragma unroll
+      for (int i = 0; i < kColRegs; ++i) {
+        const int t = ty + 8 * i;
+        if (t < T) dst[(size_t)t * M] = __fdiv_rn(v[i], sum);
+      }
+    } else {
+      for (int t = ty; t < T; t += 8) dst[(size_t)t * M] = __fdiv_rn(expf(src[(size_t)t * RS] - mx), sum);
+    }
   }
 }
 
