@@ -21,7 +21,8 @@ namespace shasta {
 
 using namespace tc;
 
-constexpr int kAtThreads = 256;   // warps 0-3 workers (row owners), 4 MMA issuer, 5 loader, 6-7 only help in the tail
+constexpr int kAtThreads = 512;   // warps 0-3 workers (row owners), 4 MMA issuer, 5 loader, 6-15 only help in the
+                                  // softmax tail (latency bound: expf / division chains want many warps)
 constexpr int kAtSlots = 6;
 constexpr int kAtSlotBytes = kAffTcSlotFloats * 4;
 // barrier slots: [0,2) layer-0 A ring full, [2,7) a_ready of layers 1..5 (slot 1 + layer), then the ones below
@@ -240,8 +241,8 @@ aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPla
   }
 
   // ---- logits to global (coalesced along d) and the row softmax for rows t < M -> matched1 (B,M,M+2).
-  // A warp owns rows warp, warp+8, ... and works on kTR of them at a time (independent dependency chains: the tail is
-  // latency bound with 8 warps per SM); D <= 224 means at most 7 columns per lane.
+  // A warp owns rows warp, warp+16, ... and works on kTR of them at a time (independent dependency chains: the tail
+  // is latency bound); D <= 224 means at most 7 columns per lane.
   constexpr int kTR = 4, kTC = (kAffTcMaxD + 31) / 32;
   for (int rb = warp; rb < 128; rb += (kAtThreads / 32) * kTR) {
     float v[kTR][kTC], mx[kTR], sum[kTR];
