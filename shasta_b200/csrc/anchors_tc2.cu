@@ -13,6 +13,8 @@
 //     registers (round-to-nearest adds) while the MMAs continue into a second TMEM buffer. Long chains inside the
 //     tensor core lose ~2 decimal digits at K = 64 000 (measured 5e-5 vs 2e-7 for fp32 FMA);
 //   * the epilogue writes along the weight-row dimension, i.e. coalesced.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -28,25 +30,28 @@ constexpr int kT2WTile = kT2BM * kT2BK * 4;  // 16 KB
 
 template <int BN>
 struct T2Cfg {
-  static constexpr int kXTile = BN * kT2BK * 4;                    // 8 / 16 KB
-  static constexpr int kStageBytes = kT2WTile + 2 * kXTile;        // Whi | Xhi | Xlo
-  static constexpr int kStages = (BN == 64) ? 6 : 4;
+  static constexpr int kXTile = BN * kT2BK * 4;                    // fp32 activations (tf32 "high" operand, raw)
+  static constexpr int kXLoTile = BN * kT2BK * 2;                  // their low parts in bf16 (64-byte rows, SW64)
+  static constexpr int kStageBytes = kT2WTile + kXTile + kXLoTile; // W | Xhi | Xlo16
+  static constexpr int kStages = (BN == 64) ? 7 : 5;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
-  // BN = 64: the Xhi and Xlo tiles are adjacent in shared memory and are fed as ONE 128-row B operand, so that
-  // Whi*Xhi^T and Whi*Xlo^T come out of a single N = 128 MMA (columns [0,64) and [64,128) of the accumulator); the
-  // TMEM-A MMA adds Wlo*Xhi^T into columns [0,64). Two MMAs per K step instead of three: the single issuing thread,
-  // not the tensor pipe, was the limiter (ncu: 37 % tensor-active at 32-cycle MMAs).
-  static constexpr bool kFuseX = (BN == 64);
-  static constexpr int kDW = kFuseX ? 2 * BN : BN;                 // accumulator buffer width in TMEM columns
-  static constexpr int kColD = 0;                                  // two accumulator buffers of kDW columns
-  static constexpr int kColWl = 2 * kDW;                           // kStages x 32 columns of weight low parts
-  static_assert(2 * kDW + kStages * 32 <= 512, "TMEM budget");
+  // Three products per K step, all into the same BN accumulator columns:
+  //   W_raw (smem, tf32)      x X_raw  (kind::tf32: the tensor core ignores the low 13 mantissa bits of both)
+  //   W_lo  (TMEM, tf32)      x X_raw  (kind::tf32, TS mode)
+  //   W_hi  (TMEM, bf16)      x X_lo   (kind::f16 bf16, TS mode): X_lo is <= 2^-10 |X|, so 8-bit operands keep this
+  //                                     term to ~2^-18 relative - below the dropped lo x lo term's neighbourhood -
+  //                                     at a quarter of the tf32 cost (kind::tf32 runs at ~1024 MAC/clk/SM here)
+  static constexpr int kColD = 0;                                  // two accumulator buffers of BN columns
+  static constexpr int kColW = 2 * BN;                             // per stage: 32 columns W_lo (fp32) + 16 columns W_hi (bf16 pairs)
+  static constexpr int kColsPerStage = 48;
+  static_assert(2 * BN + kStages * kColsPerStage <= 512, "TMEM budget");
+  static_assert(kStageBytes % 1024 == 0, "stage tiles must stay 1024-byte aligned");
 };
 
 struct AnchorT2Maps {
   CUtensorMap w[4];  // aug_shape.i.0.weight (5M, 320M), box 32 x 128
   CUtensorMap x[4];    // activations of anchor i as (B, K): FEAT_CUR / FEAT_PREV rows (stride (M+2)*320) or HID
-  CUtensorMap xlo[4];  // the tf32 low parts of the same elements (FEATLO_* / HIDLO), compact
+  CUtensorMap xlo[4];  // the tf32 low parts of the same elements as bf16 (FEATLO_* / HIDLO), compact, SW64
 };
 
 // The same streaming GEMM serves both Linear layers of aug_shape.i:
@@ -72,7 +77,21 @@ __device__ __forceinline__ void t2_tmem_st8(uint32_t taddr, const uint32_t (&v)[
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+__device__ __forceinline__ void t2_tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3])
+               : "memory");
+}
 __device__ __forceinline__ void t2_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void t2_mma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void t2_mma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                                uint32_t accumulate) {
   asm volatile(
@@ -146,7 +165,7 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, const __grid
           if (++st == nst) st = 0, ph ^= 1;
           continue;
         }
-        mbar_expect_tx(full_bar(st), kT2WTile + 2 * C::kXTile);
+        mbar_expect_tx(full_bar(st), C::kStageBytes);
         const int k0 = (kb_beg + kb) * kT2BK;
         if (conv) {   // K block = (tap, 32 input channels): the pixel patch shifted by the tap, zero-filled outside
           const int kbg = kb_beg + kb, tap = kbg >> 4, cb = kbg & 15;
@@ -163,7 +182,7 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, const __grid
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc(kFmtTF32, kT2BM, BN);
-      constexpr uint32_t idesc2 = umma_idesc(kFmtTF32, kT2BM, 2 * BN > 256 ? 256 : 2 * BN);
+      constexpr uint32_t idesc16 = umma_idesc(kFmtBF16, kT2BM, BN);
       int st = 0;
       uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
@@ -177,21 +196,20 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, const __grid
         tc_fence_after();
         const uint32_t sb = base + st * C::kStageBytes;
         const uint64_t dwh = umma_desc_sw128(sb);
-        const uint64_t dxh = umma_desc_sw128(sb + kT2WTile), dxl = umma_desc_sw128(sb + kT2WTile + C::kXTile);
-        const uint32_t d = tmem + (uint32_t)(C::kColD + buf * C::kDW);
-        const uint32_t wl = tmem + (uint32_t)(C::kColWl + st * 32);
+        const uint64_t dxh = umma_desc_sw128(sb + kT2WTile);
+        const uint64_t dxl = umma_desc_sw64(sb + kT2WTile + C::kXTile);
+        const uint32_t d = tmem + (uint32_t)(C::kColD + buf * BN);
+        const uint32_t wl = tmem + (uint32_t)(C::kColW + st * C::kColsPerStage), wh16 = wl + 32u;
+        if (!(dbg & 1)) {   // (dbg bit 0: timing experiment without MMAs)
 #pragma unroll
-        for (int k = 0; k < kT2BK / 8; ++k) {
-          if (dbg & 1) break;  // timing experiment: no MMAs (results are garbage)
-          const uint64_t adv = (uint64_t)((k * 32) >> 4);
-          if (C::kFuseX) {
-            if (!(dbg & 0x10))
-            mma_tf32(d, dwh + adv, dxh + adv, idesc2, !(first && k == 0));   // [Xhi; Xlo] as one 128-row operand
-          } else {
+          for (int k = 0; k < kT2BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
             mma_tf32(d, dwh + adv, dxh + adv, idesc, !(first && k == 0));
-            mma_tf32(d, dwh + adv, dxl + adv, idesc, 1);
+            t2_mma_ts_tf32(d, wl + (uint32_t)(k * 8), dxh + adv, idesc, 1);
           }
-          if (!(dbg & 0x20)) t2_mma_ts_tf32((dbg & 8) ? tmem + 448u : d, wl + (uint32_t)(k * 8), dxh + adv, idesc, 1);
+#pragma unroll
+          for (int j = 0; j < kT2BK / 16; ++j)
+            t2_mma_ts_bf16(d, wh16 + (uint32_t)(j * 8), dxl + (uint64_t)((j * 32) >> 4), idesc16, 1);
         }
         mma_commit(empty_bar(st));
         if ((kb % kT2Flush) == kT2Flush - 1 || kb == nkb - 1) mma_commit(dfull_bar(buf));
@@ -215,18 +233,10 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, const __grid
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(lane_base + (uint32_t)(C::kColD + buf * C::kDW + c0), v);
-        if (C::kFuseX) {
-          uint32_t v2[16];
-          tmem_ld16(lane_base + (uint32_t)(C::kColD + buf * C::kDW + BN + c0), v2);
-          tmem_ld_wait();
+        tmem_ld16(lane_base + (uint32_t)(C::kColD + buf * BN + c0), v);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(v2[j]);
-        } else {
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(v[j]);
-        }
+        for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(v[j]);
       }
       tc_fence_before();
       mbar_arrive(dempty_bar(buf));
@@ -256,37 +266,22 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, const __grid
       for (int c = 0; c < 8; ++c) w[c] = *reinterpret_cast<const float4*>(sg + r * 128 + ((c ^ (r & 7)) << 4));
 #pragma unroll
       for (int c = 0; c < 8; c += 2) {
-        uint32_t lo[8];
+        uint32_t lo[8], hb[4];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const float4 v = w[c + h];
-          float4 wh;
-          wh.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          wh.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          wh.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          wh.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-          lo[h * 4 + 0] = __float_as_uint(v.x - wh.x);
-          lo[h * 4 + 1] = __float_as_uint(v.y - wh.y);
-          lo[h * 4 + 2] = __float_as_uint(v.z - wh.z);
-          lo[h * 4 + 3] = __float_as_uint(v.w - wh.w);
-          if (!raw_hi) *reinterpret_cast<float4*>(sg + r * 128 + (((c + h) ^ (r & 7)) << 4)) = wh;
+          lo[h * 4 + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+          lo[h * 4 + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+          lo[h * 4 + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+          lo[h * 4 + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+          const __nv_bfloat162 b01 = __floats2bfloat162_rn(v.x, v.y), b23 = __floats2bfloat162_rn(v.z, v.w);
+          hb[h * 2 + 0] = *reinterpret_cast<const uint32_t*>(&b01);   // low half = even k
+          hb[h * 2 + 1] = *reinterpret_cast<const uint32_t*>(&b23);
         }
-        t2_tmem_st8(lane_base + (uint32_t)(C::kColWl + st * 32 + c * 4), lo);
-      }
-      if (!raw_hi) {  // explicit tf32 truncation of the activation high parts too (the default feeds raw fp32)
-        float4* xh = reinterpret_cast<float4*>(sg + kT2WTile);
-#pragma unroll
-        for (int j = 0; j < C::kXTile / 16 / 128; ++j) {
-          float4 a = xh[j * 128 + t];
-          a.x = __uint_as_float(__float_as_uint(a.x) & 0xffffe000u);
-          a.y = __uint_as_float(__float_as_uint(a.y) & 0xffffe000u);
-          a.z = __uint_as_float(__float_as_uint(a.z) & 0xffffe000u);
-          a.w = __uint_as_float(__float_as_uint(a.w) & 0xffffe000u);
-          xh[j * 128 + t] = a;
-        }
+        t2_tmem_st8(lane_base + (uint32_t)(C::kColW + st * C::kColsPerStage + c * 4), lo);
+        t2_tmem_st4(lane_base + (uint32_t)(C::kColW + st * C::kColsPerStage + 32 + c * 2), hb);
       }
       t2_tmem_st_wait();
-      if (!raw_hi) fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(split_bar(st));
       if (++st == nst) st = 0, ph ^= 1;
@@ -404,6 +399,27 @@ static int make_map2(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t c
   return 0;
 }
 
+// bf16 (rows, cols) matrix, box 32 x box_rows, 64-byte rows in shared memory (SWIZZLE_64B)
+static int make_map2_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn2 fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return SHASTA_ERR_UNSUPPORTED;
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kT2BK, box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (bf16) failed with CUresult %d", (int)r);
+    return SHASTA_ERR_ARG;
+  }
+  return 0;
+}
+
 static int t2_bn(int B) { return B <= 64 ? 64 : 128; }
 
 int anchor_tc2_splits(int M, int B) {
@@ -432,12 +448,11 @@ __global__ void feat_lo_kernel(const float* __restrict__ feat0, const float* __r
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
     const size_t b = v / per, e = v % per;
     const float4 x = __ldg(reinterpret_cast<const float4*>(feat + b * (size_t)(M + 2) * kF) + e);
-    float4 r;
-    r.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-    r.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-    r.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-    r.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-    reinterpret_cast<float4*>(lo)[v] = r;
+    const __nv_bfloat162 a = __floats2bfloat162_rn(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u),
+                                                   x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u));
+    const __nv_bfloat162 c = __floats2bfloat162_rn(x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u),
+                                                   x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u));
+    reinterpret_cast<uint2*>(lo)[v] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&c));
   }
 }
 
@@ -471,7 +486,7 @@ int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, co
     if (rc) return rc;
     rc = make_map2(&maps.x[i], (i < 2) ? feat_cur : feat_prev, (uint64_t)B, K, ld, (uint32_t)bn);
     if (rc) return rc;
-    rc = make_map2(&maps.xlo[i], (i < 2) ? featlo_cur : featlo_prev, (uint64_t)B, K, K, (uint32_t)bn);
+    rc = make_map2_bf16(&maps.xlo[i], (i < 2) ? featlo_cur : featlo_prev, (uint64_t)B, K, K, (uint32_t)bn);
     if (rc) return rc;
   }
   if (!featlo_ready) {
@@ -489,7 +504,7 @@ int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, co
 struct AnchorBias4 {
   const float* b[4];
 };
-__global__ void anchor_reduce_kernel(const float* __restrict__ part, int S, int B, int N5, AnchorBias4 bias,
+__global__ void anchor_reduce_kernel(const float* __restrict__ part, int S, int B, int N5, int ldlo, AnchorBias4 bias,
                                      float* __restrict__ hid, float* __restrict__ hidlo) {
   const size_t total = (size_t)4 * B * N5;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -499,7 +514,9 @@ __global__ void anchor_reduce_kernel(const float* __restrict__ part, int S, int 
     for (int sp = 0; sp < S; ++sp) sum += part[(((size_t)sp * B + b) * 4 + i) * N5 + n];   // fixed order
     const float h = fmaxf(sum + __ldg(bias.b[i] + n), 0.f);
     hid[idx] = h;
-    hidlo[idx] = h - __uint_as_float(__float_as_uint(h) & 0xffffe000u);
+    // bf16 rows are padded to a multiple of 8 elements (TMA wants a 16-byte row pitch)
+    reinterpret_cast<__nv_bfloat16*>(hidlo)[((size_t)i * B + b) * ldlo + n] =
+        __float2bfloat16_rn(h - __uint_as_float(__float_as_uint(h) & 0xffffe000u));
   }
 }
 
@@ -509,7 +526,8 @@ int launch_anchor_out_tc(const shasta_params_t& p, const float* part, int S, int
   const int M = p.max_obj, N5 = 5 * M, T = M + 2;
   AnchorBias4 b0;
   for (int i = 0; i < 4; ++i) b0.b[i] = p.aug_shape_b0[i];
-  anchor_reduce_kernel<<<592, 256, 0, s>>>(part, S, B, N5, b0, hid, hidlo);
+  const int ldlo = (N5 + 7) / 8 * 8;
+  anchor_reduce_kernel<<<592, 256, 0, s>>>(part, S, B, N5, ldlo, b0, hid, hidlo);
   SHASTA_CHECK_LAUNCH("anchor_reduce_kernel");
   const int bn = t2_bn(B);
   AnchorT2Maps maps;
@@ -518,7 +536,8 @@ int launch_anchor_out_tc(const shasta_params_t& p, const float* part, int S, int
     if (rc) return rc;
     rc = make_map2(&maps.x[i], hid + (size_t)i * B * N5, (uint64_t)B, (uint64_t)N5, (uint64_t)N5, (uint32_t)bn);
     if (rc) return rc;
-    rc = make_map2(&maps.xlo[i], hidlo + (size_t)i * B * N5, (uint64_t)B, (uint64_t)N5, (uint64_t)N5, (uint32_t)bn);
+    rc = make_map2_bf16(&maps.xlo[i], reinterpret_cast<const __nv_bfloat16*>(hidlo) + (size_t)i * B * ldlo, (uint64_t)B,
+                        (uint64_t)N5, (uint64_t)ldlo, (uint32_t)bn);
     if (rc) return rc;
   }
   AnchorT2Job job = {};
@@ -540,7 +559,8 @@ int launch_anchor_out_tc(const shasta_params_t& p, const float* part, int S, int
 // ------------------------------------------------------------------------------------------------
 constexpr int kConvCin = 512, kConvCout = 64, kConvK = 9 * kConvCin;
 
-// packed = [W_hi (64 x 4608) ; W_lo (64 x 4608)] with k = (ky*3 + kx)*512 + c, then scale[64], shift[64]
+// packed = [W (64 x 4608) fp32 ; W_lo (64 x 4608) bf16 in the next 64 x 4608 float slots] with
+// k = (ky*3 + kx)*512 + c, then scale[64], shift[64]
 __global__ void conv_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ mean, const float* __restrict__ var, float eps,
@@ -550,7 +570,8 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, const float* __res
     const int o = idx / kConvK, k = idx % kConvK, tap = k / kConvCin, c = k % kConvCin;
     const float v = w[((size_t)o * kConvCin + c) * 9 + tap];
     packed[idx] = v;   // the tensor core ignores the low 13 mantissa bits of the "high" operand
-    packed[(size_t)kConvCout * kConvK + idx] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    reinterpret_cast<__nv_bfloat16*>(packed + (size_t)kConvCout * kConvK)[idx] =
+        __float2bfloat16_rn(v - __uint_as_float(__float_as_uint(v) & 0xffffe000u));   // low parts as bf16
   }
   if (idx < kConvCout) {
     const float sc = gamma[idx] / sqrtf(var[idx] + eps);
@@ -594,7 +615,7 @@ int launch_shared_conv(const float* packed, const float* x_nchw, int nmaps, int 
   if (rc) return rc;
   rc = make_map2(&maps.x[0], packed, kConvCout, kConvK, kConvK, 64);
   if (rc) return rc;
-  rc = make_map2(&maps.xlo[0], packed + (size_t)kConvCout * kConvK, kConvCout, kConvK, kConvK, 64);
+  rc = make_map2_bf16(&maps.xlo[0], packed + (size_t)kConvCout * kConvK, kConvCout, kConvK, kConvK, 64);
   if (rc) return rc;
   for (int i = 1; i < 4; ++i) maps.w[i] = maps.w[0], maps.x[i] = maps.x[0], maps.xlo[i] = maps.xlo[0];
   AnchorT2Job job = {};

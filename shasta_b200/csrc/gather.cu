@@ -7,6 +7,8 @@
 //   det3d/core/utils/center_utils.py:92-121            (clamped bilinear interpolation)
 // Two samplers: (0) half-warp per point, four 16-byte LDGs per lane (each tap is one 256-byte channel run);
 // (1) the same taps staged into shared memory by cp.async.bulk (TMA bulk copies, one mbarrier per CTA).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace shasta {
@@ -76,14 +78,17 @@ struct GatherJob {
   const float* bev[2];
   const float* boxes[2];
   float* feat[2];
-  float* featlo[2];  // optional (B, 320M): x - tf32_trunc(x), the low operand of the 3xTF32 anchors GEMM
+  float* featlo[2];  // optional (B, 320M) bf16: x - tf32_trunc(x), the low operand of the anchors GEMM
 };
 
 __device__ __forceinline__ float tf32_lo(float v) {
   return __fsub_rn(v, __uint_as_float(__float_as_uint(v) & 0xffffe000u));
 }
-__device__ __forceinline__ float4 tf32_lo4(float4 v) {
-  return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+// four low parts as bf16 (8 bytes)
+__device__ __forceinline__ uint2 tf32_lo4(float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(tf32_lo(v.x), tf32_lo(v.y));
+  const __nv_bfloat162 b = __floats2bfloat162_rn(tf32_lo(v.z), tf32_lo(v.w));
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
 }
 
 __device__ __forceinline__ void box_point_pixels(const float* __restrict__ bx, int p, const shasta_geom_t& g,
@@ -149,7 +154,8 @@ gather_ldg_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, 
   const float4 v = blend4(a, bb, c, d, t);
   dst[lane16] = v;
   if (job.featlo[f] != nullptr)
-    reinterpret_cast<float4*>(job.featlo[f] + ((size_t)b * M + m) * kF + p * kC)[lane16] = tf32_lo4(v);
+    reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(job.featlo[f]) + ((size_t)b * M + m) * kF + p * kC)[lane16] =
+        tf32_lo4(v);
   }
 }
 
@@ -235,7 +241,8 @@ gather_bulk_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g,
     const float4 d = reinterpret_cast<const float4*>(&s_taps[pt][3][0])[q];
     const float4 v = blend4(a, bb, c, d, t);
     reinterpret_cast<float4*>(feat + s_dst[pt])[q] = v;
-    if (job.featlo[f] != nullptr) reinterpret_cast<float4*>(job.featlo[f] + s_dstlo[pt])[q] = tf32_lo4(v);
+    if (job.featlo[f] != nullptr)
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(job.featlo[f]) + s_dstlo[pt])[q] = tf32_lo4(v);
   }
 }
 

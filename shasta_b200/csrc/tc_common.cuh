@@ -186,6 +186,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
   return d;
 }
+// K-major operand tile whose rows are exactly 64 bytes, written by TMA with CU_TENSOR_MAP_SWIZZLE_64B (tile base
+// 512-byte aligned): 8-row groups are 512 B apart, layout type 4 = SWIZZLE_64B.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
 // K-major operand tile in the un-swizzled canonical layout: 8-row x 16-byte core matrices (128 B contiguous);
 // core matrices adjacent in K are lbo bytes apart, adjacent 8-row groups sbo bytes apart.
 __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
