@@ -165,7 +165,8 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, const __grid
           if (++st == nst) st = 0, ph ^= 1;
           continue;
         }
-        mbar_expect_tx(full_bar(st), C::kStageBytes);
+        const bool skip_x = (dbg & 0x40) && (kb & 3) != 0;   // timing experiment: a quarter of the activation traffic
+        mbar_expect_tx(full_bar(st), skip_x ? kT2WTile : C::kStageBytes);
         const int k0 = (kb_beg + kb) * kT2BK;
         if (conv) {   // K block = (tap, 32 input channels): the pixel patch shifted by the tap, zero-filled outside
           const int kbg = kb_beg + kb, tap = kbg >> 4, cb = kbg & 15;
@@ -173,8 +174,10 @@ anchor_hidden_tc2_kernel(const __grid_constant__ AnchorT2Maps maps, const __grid
                       kEvictLast);
         } else
         tma_load_2d(sb, &maps.w[i], full_bar(st), k0, n0, kEvictFirst);                  // weights: streamed once
-        tma_load_2d(sb + kT2WTile, &maps.x[i], full_bar(st), k0, b0, kEvictLast);        // activations: reused
-        tma_load_2d(sb + kT2WTile + C::kXTile, &maps.xlo[i], full_bar(st), k0, b0, kEvictLast);
+        if (!skip_x) {
+          tma_load_2d(sb + kT2WTile, &maps.x[i], full_bar(st), k0, b0, kEvictLast);        // activations: reused
+          tma_load_2d(sb + kT2WTile + C::kXTile, &maps.xlo[i], full_bar(st), k0, b0, kEvictLast);
+        }
         if (++st == nst) st = 0, ph ^= 1;
       }
     }
