@@ -460,6 +460,8 @@ def main():
         # warm-up: at least W (>= 3) steps AND at least 0.6 s of sustained work - a freshly started process finds the
         # GPU in an idle power state and the first ~100 ms of kernels run several times slower (measured: 3.3 ms vs
         # 0.93 ms per step right after start-up, SM clock already reading 1965 MHz)
+        step()   # builds the step graph (eager runs + capture: host time with an idle GPU, kept out of the warm-up clock)
+        torch.cuda.synchronize()
         t_w = time.time()
         n_warm = 0
         while n_warm < max(a.warmup, 3) or time.time() - t_w < 0.6:
