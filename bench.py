@@ -325,13 +325,19 @@ def run_train(a):
         m1, m2 = model.affinity(bev, prev_bev, det, prev)
         loss = L.affinity_loss(m1, m2, gt)
         loss.backward()
-        if dist is not None:   # DDP-style gradient averaging: one flat all-reduce (0.6 MB)
-            torch.cat([p_.grad.reshape(-1) for p_ in params], out=flat)
-            dist.all_reduce(flat)
-            flat.div_(world)
+        if dist is not None:   # DDP-style gradient averaging (train.py:154-156): the four 257 MB aug_shape.i.0 gradients
+            # are averaged in place, everything else (1.6 MB in 60 tensors) through one flat bucket
+            big = [p_ for p_ in params if p_.numel() >= (1 << 22)]
+            small = [p_ for p_ in params if p_.numel() < (1 << 22)]
+            works = [dist.all_reduce(p_.grad, op=dist.ReduceOp.AVG, async_op=True) for p_ in big]
+            fl = flat[:sum(p_.numel() for p_ in small)]
+            torch.cat([p_.grad.reshape(-1) for p_ in small], out=fl)
+            works.append(dist.all_reduce(fl, op=dist.ReduceOp.AVG, async_op=True))
+            for w_ in works:
+                w_.wait()
             o = 0
-            for p_ in params:
-                p_.grad.copy_(flat[o:o + p_.numel()].view_as(p_))
+            for p_ in small:
+                p_.grad.copy_(fl[o:o + p_.numel()].view_as(p_))
                 o += p_.numel()
         opt.step()
         return loss
@@ -365,7 +371,7 @@ def run_train(a):
         line = {"metric": "affinity-head training frame-pairs/sec (200x200 pairs)", "value": world * B * a.steps / (ms / 1e3),
                 "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": n_warm, "ms_per_step": ms / a.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "impl": "b200", "mode": "train", "loss": float(loss),
+                "impl": "b200", "mode": "train", "loss": float(loss.detach()),
                 "config": config_dict(a, {"differentiated_parameters": training.differentiable_parameter_names(),
                                           "note": "BASELINE.json config 5: every head parameter trained (258 M), shared_conv / trunk frozen"}),
                 "clocks": clocks, "gpu_launches": (lib.shasta_last_launch_count() + 6) * a.steps}
