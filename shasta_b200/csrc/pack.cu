@@ -29,25 +29,17 @@ __global__ void umma_b_image_kernel(float* __restrict__ hi, float* __restrict__ 
   bf[(k / 8) * (n_pad * 8) + n * 8 + (k % 8)] = __float2bfloat16_rn(v);
 }
 
-// tf32 hi/lo image of the K slice [k0, k0 + kc) of a Linear weight (n_valid x k_valid, leading dimension src_ld):
-// hi[(k-k0)/4][n][(k-k0)%4], lo directly behind it; rows n >= n_valid and columns k >= k_valid are zero.
-__global__ void umma_b_slice_kernel(float* __restrict__ img, const float* __restrict__ src, int src_ld, int n_valid,
-                                    int k_valid, int n_pad, int k0, int kc) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_pad * kc) return;
-  const int n = idx / kc, kk = idx % kc, k = k0 + kk;
-  const float v = (n < n_valid && k < k_valid) ? src[(size_t)n * src_ld + k] : 0.f;
-  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-  const size_t o = (size_t)(kk / 4) * (n_pad * 4) + n * 4 + (kk % 4);
-  img[o] = h;
-  img[(size_t)n_pad * kc + o] = v - h;
-}
-
+// tf32 hi/lo images of K slices: hi[(k-k0)/4][n][(k-k0)%4], lo directly behind it; padding rows / columns are zero.
 // same image from a k-major source matrix src[k][n] (ld = n_src): piece [k0, k0 + kc) x n_pad
-__global__ void umma_b_slice_kmajor_kernel(float* __restrict__ img, const float* __restrict__ src, int n_src, int n_pad,
-                                           int k0, int kc) {
+// (one launch for all pieces of both sides: blockIdx.y = piece, blockIdx.z = side)
+__global__ void umma_b_slice_kmajor_kernel(float* __restrict__ img0, float* __restrict__ img1,
+                                           const float* __restrict__ src0, const float* __restrict__ src1, int n_src,
+                                           int n_pad, int kc) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_pad * kc) return;
+  float* img = (blockIdx.z ? img1 : img0) + (size_t)blockIdx.y * 2 * kc * n_pad;
+  const float* src = blockIdx.z ? src1 : src0;
+  const int k0 = blockIdx.y * kc;
   const int n = idx % n_pad, kk = idx / n_pad;
   const float v = (n < n_src) ? src[(size_t)(k0 + kk) * n_src + n] : 0.f;
   const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
@@ -56,11 +48,25 @@ __global__ void umma_b_slice_kmajor_kernel(float* __restrict__ img, const float*
   img[(size_t)n_pad * kc + o] = v - h;
 }
 
-static int bslice(float* img, const float* src, int src_ld, int n_valid, int k_valid, int n_pad, int k0, int kc,
-                  cudaStream_t s) {
-  umma_b_slice_kernel<<<(n_pad * kc + 255) / 256, 256, 0, s>>>(img, src, src_ld, n_valid, k_valid, n_pad, k0, kc);
-  SHASTA_CHECK_LAUNCH("umma_b_slice_kernel");
-  return 0;
+// all aff_tc weight pieces in one launch (blockIdx.y = piece of the plan)
+struct AffSrc {
+  const float* w[6];
+  int ld[6];
+};
+__global__ void aff_pieces_kernel(float* __restrict__ base, const __grid_constant__ AffTcPlan plan, AffSrc src) {
+  const AffTcPiece q = plan.p[blockIdx.y];
+  const int n_pad = q.n, kc = q.ks;
+  float* img = base + q.off;
+  const float* w = src.w[q.layer];
+  const int ld = src.ld[q.layer];
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_pad * kc; idx += gridDim.x * blockDim.x) {
+    const int n = idx / kc, kk = idx % kc, k = q.k0 + kk;
+    const float v = (n < q.src_n && k < q.src_k) ? w[(size_t)n * ld + k] : 0.f;
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    const size_t o = (size_t)(kk / 4) * (n_pad * 4) + n * 4 + (kk % 4);
+    img[o] = h;
+    img[(size_t)n_pad * kc + o] = v - h;
+  }
 }
 
 static int bimage(float* hi, float* lo, float* bf, const float* src, int src_ld, int n_valid, int n_pad, int K,
@@ -142,21 +148,16 @@ int launch_pack(const shasta_params_t& p, float* packed, cudaStream_t s) {
   if (P.aff_tc_floats > 0) {   // tensor-core aff: the weight pieces of AffTcPlan, hi | lo images
     const AffTcPlan A = aff_tc_plan(M);
     const int lds[6] = {(int)D, 128, 64, 32, 64, 128};
-    for (int i = 0; i < A.npieces; ++i) {
-      const AffTcPiece& q = A.p[i];
-      int rc2 = bslice(packed + P.aff_tc_begin + q.off, p.aff_w[q.layer], lds[q.layer], q.src_n, q.src_k, q.n, q.k0,
-                       q.ks, s);
-      if (rc2) return rc2;
-    }
+    AffSrc src;
+    for (int l = 0; l < 6; ++l) src.w[l] = p.aff_w[l], src.ld[l] = lds[l];
+    aff_pieces_kernel<<<dim3(16, A.npieces), 256, 0, s>>>(packed + P.aff_tc_begin, A, src);
+    SHASTA_CHECK_LAUNCH("aff_pieces_kernel");
   }
   // tensor-core images of the two [320][112] first-layer projection matrices (built from the k-major copies above)
-  for (int sd = 0; sd < 2; ++sd)
-    for (int pc = 0; pc < kProjTcPieces; ++pc) {
-      umma_b_slice_kmajor_kernel<<<(kProjShape * kProjTcKs + 255) / 256, 256, 0, s>>>(
-          packed + P.proj_tc[sd] + (size_t)pc * 2 * kProjTcKs * kProjShape, packed + (sd ? P.p1_cur : P.p1_prev),
-          kProjShape, kProjShape, pc * kProjTcKs, kProjTcKs);
-      SHASTA_CHECK_LAUNCH("umma_b_slice_kmajor_kernel");
-    }
+  umma_b_slice_kmajor_kernel<<<dim3((kProjShape * kProjTcKs + 255) / 256, kProjTcPieces, 2), 256, 0, s>>>(
+      packed + P.proj_tc[0], packed + P.proj_tc[1], packed + P.p1_prev, packed + P.p1_cur, kProjShape, kProjShape,
+      kProjTcKs);
+  SHASTA_CHECK_LAUNCH("umma_b_slice_kmajor_kernel");
   // tensor-core operand images of fuse_shape.2 (20x40), res_coeff.2 (18x72), fuse_det.2 (8x32)
   int rc = bimage(packed + P.tc32_w2a_hi, packed + P.tc32_w2a_lo, packed + P.tc16_w2a, p.fuse_shape_w[1], 40, 20, 32, 40, s);
   if (rc) return rc;
