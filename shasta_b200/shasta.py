@@ -367,6 +367,30 @@ class Shasta(nn.Module):
                 _cabi.check(rc, "shasta_shared_conv_f32")
         return out
 
+    def decode(self, matched1, matched2, n_prev, n_det):
+        """The thresholded argmax of the eval loop (tools/nusc_shasta/eval.py:126-181) for a whole batch on the device:
+        returns int32/float32 CUDA tensors of shape (B, M): ``prev_state`` (0 keep, 1 dead, 2 FN, -1 padding),
+        ``prev_argmax``, ``fn_score`` (1 - matched[n,-2] for FN rows), ``det_state`` (0 keep, 1 newborn, 2 dropped FP,
+        -1 padding), ``det_argmax``, ``det_score`` (ref_detection_score). ``n_prev`` / ``n_det``: real counts per
+        frame pair (sequence or int32 tensor)."""
+        if not matched1.is_cuda or not matched2.is_cuda:
+            raise _cabi.ShastaLibraryError("decode needs CUDA tensors: shasta_b200 has no CPU path")
+        dev = matched1.device
+        B, M = matched1.shape[0], matched1.shape[1]
+        m1, m2 = matched1.contiguous(), matched2.contiguous()
+        npv = torch.as_tensor(n_prev, dtype=torch.int32).to(dev)
+        ndv = torch.as_tensor(n_det, dtype=torch.int32).to(dev)
+        out = {k: torch.empty((B, M), dtype=(torch.float32 if k.endswith("score") else torch.int32), device=dev)
+               for k in ("prev_state", "prev_argmax", "fn_score", "det_state", "det_argmax", "det_score")}
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().shasta_decode_f32(
+                m1.data_ptr(), m2.data_ptr(), npv.data_ptr(), ndv.data_ptr(), B, M, out["prev_state"].data_ptr(),
+                out["prev_argmax"].data_ptr(), out["fn_score"].data_ptr(), out["det_state"].data_ptr(),
+                out["det_argmax"].data_ptr(), out["det_score"].data_ptr(),
+                ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _cabi.check(rc, "shasta_decode_f32")
+        return out
+
     def _launch_forward(self, bev, prev_bev, det_c, prev_c, ws):
         """Enqueues the five forward kernels on the current stream. Inputs are validated, contiguous, boxes on the
         device; ``ws`` is the workspace the activations are left in (the backward pass reads them)."""
