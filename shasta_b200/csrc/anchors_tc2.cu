@@ -1,18 +1,24 @@
-// aug_shape.i.0 on tcgen05, second generation ("weights on the M side").
+// The streaming fp32-equivalent GEMM on tcgen05 ("operand streamed from memory on the M side"). Three users:
+//   mode 0  aug_shape.i.0   HIDDEN_PART[s][b][i][n] = sum_{k in split s} W0_i[n][k] * X_src(i)[b][k]   (shasta.py:54, 241-244)
+//   mode 1  aug_shape.i.2   anchor row = | W2_i . hidden_i + b2_i |                                   (shasta.py:55, 241-247)
+//   mode 2  shared_conv     3x3 conv 512 -> 64 as an implicit GEMM over channels-last pixel patches     (shasta.py:42-47, 223-228)
 //
-//   HIDDEN_PART[s][b][i][n] = sum_{k in split s} W0_i[n][k] * X_src(i)[b][k]              (shasta.py:54, 241-244)
-//
-// What changed against anchors_tc.cu (kept as option 3 for comparison):
-//   * the weight tile is the UMMA A operand (M = 128 weight rows = 128 TMEM lanes), the batch is the N dimension
-//     (64 or 128 frame pairs). A stage then holds 16 KB of weights + 2 x BN x 128 B of activations, so 6 (BN = 64) or
-//     4 (BN = 128) stages fit in shared memory and ~96 KB of weight bytes are in flight per SM - the kernel is a weight
-//     streamer and needs that much to cover HBM latency;
-//   * the low part of the weight tile never goes back to shared memory: the splitter warps write it to TENSOR MEMORY
-//     (tcgen05.st) and the third MMA of each K step reads its A operand from TMEM (TS mode);
+// Design (what changed against anchors_tc.cu, kept as option 3 for comparison):
+//   * the streamed tile (weights / pixels) is the UMMA A operand (M = 128 rows = 128 TMEM lanes), the small reused
+//     operand (64 or 128 frame pairs / the 64 output channels) is the N dimension. A stage holds 16 KB of the stream +
+//     BN x 192 B of the reused operand, so 7 (BN = 64) or 5 (BN = 128) stages fit: ~112 KB of stream bytes in flight
+//     per SM - the kernel is a streamer and needs that much to cover HBM latency;
+//   * arithmetic per K step: A_raw x B_raw and A_lo x B_raw as kind::tf32 MMAs (the tensor core ignores the low 13
+//     mantissa bits, so the raw fp32 tiles serve as the tf32 "high" operands) plus A_hi x B_lo as a bf16 MMA. The
+//     splitter warps write A_lo (fp32) and a bf16 copy of A into TENSOR MEMORY (tcgen05.st), both are TS-mode A
+//     operands; the bf16 low parts of the reused operand are produced upstream (gather / reduce / pack kernels) and
+//     arrive by TMA (64-byte rows, SWIZZLE_64B);
 //   * accumulation chains are bounded: every kFlush K blocks (512 elements) the accumulator is drained into fp32
 //     registers (round-to-nearest adds) while the MMAs continue into a second TMEM buffer. Long chains inside the
 //     tensor core lose ~2 decimal digits at K = 64 000 (measured 5e-5 vs 2e-7 for fp32 FMA);
-//   * the epilogue writes along the weight-row dimension, i.e. coalesced.
+//   * the issuing threads are chosen with elect.sync (ptxas then emits back-to-back UTCHMMA; with `lane == 0` it wraps
+//     every MMA in a uniform-datapath waterfall loop);
+//   * the epilogue writes along the streamed-row dimension, i.e. coalesced.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -623,7 +629,7 @@ int launch_shared_conv(const float* packed, const float* x_nchw, int nmaps, int 
   for (int i = 1; i < 4; ++i) maps.w[i] = maps.w[0], maps.x[i] = maps.x[0], maps.xlo[i] = maps.xlo[0];
   AnchorT2Job job = {};
   job.B = kConvCout, job.nrows = 128, job.kblocks = kConvK / kT2BK, job.S = 1, job.ntiles_n = 1;
-  job.raw_hi = 1, job.dbg = 0, job.mode = 2, job.part = nullptr;
+  job.raw_hi = 1, job.dbg = g_options[2] & 0x43, job.mode = 2, job.part = nullptr;   // (0x40: traffic experiment)
   job.bias[0] = packed + (size_t)2 * kConvCout * kConvK, job.bias[1] = job.bias[0] + kConvCout;
   job.out[0] = out_nhwc;
   job.H = H, job.W = W, job.tiles_x = (W + kConvTX - 1) / kConvTX;

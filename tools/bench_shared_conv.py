@@ -40,6 +40,8 @@ def main():
     with torch.device(dev):
         model = build_track(cfg)
     model.eval()
+    from shasta_b200 import _cabi
+    _cabi.lib().shasta_set_option(2, int(os.environ.get("SHASTA_DBG", "0"), 0))
     x = torch.relu(torch.randn((a.maps, 512, a.hw, a.hw), device=dev))
     flop = 2.0 * a.maps * a.hw * a.hw * 64 * 512 * 9
     out = {}
