@@ -133,7 +133,8 @@ enum shasta_region {
   SHASTA_WS_COUNTERS = 23,   /* 64 ints: work-item counters of the persistent kernels */
   SHASTA_WS_HID = 24,        /* (4,B,5M) hidden activations of aug_shape.i (operand of the tcgen05 output GEMM) */
   SHASTA_WS_HIDLO = 25,      /* their tf32 low parts */
-  SHASTA_WS_NUM_REGIONS = 26
+  SHASTA_WS_OUT_PART = 26,   /* (4,B,4,320) split-K partial sums of the tcgen05 aug_shape.i.2 GEMM */
+  SHASTA_WS_NUM_REGIONS = 27
 };
 
 /* Runtime options (process-wide, not thread-safe; meant for tests and benchmarks).

@@ -58,7 +58,7 @@ class ShastaGeom(ctypes.Structure):
 # region ids (enum shasta_region)
 WS_FEAT_CUR, WS_FEAT_PREV, WS_BOX_CUR, WS_BOX_PREV, WS_HIDDEN_PART, WS_PROJ_PREV, WS_PROJ_CUR, WS_AUX_PREV, \
     WS_AUX_CUR, WS_COLNORM, WS_RESIDUAL, WS_LOGITS, WS_ANCHOR_BOX, WS_PROJ_CUR_T, WS_DPROJ_PREV, WS_DPROJ_CUR, WS_ANCH_H, \
-    WS_ANCH_DY, WS_ANCH_DZ, WS_RAW_XY, WS_BOX_BWD, WS_FEATLO_CUR, WS_FEATLO_PREV, WS_COUNTERS, WS_HID, WS_HIDLO = range(26)
+    WS_ANCH_DY, WS_ANCH_DZ, WS_RAW_XY, WS_BOX_BWD, WS_FEATLO_CUR, WS_FEATLO_PREV, WS_COUNTERS, WS_HID, WS_HIDLO, WS_OUT_PART = range(27)
 FLAG_TMA_GATHER, FLAG_NARROW_GATHER, FLAG_PROFILE, FLAG_SKIP_GATHER = 0x1, 0x2, 0x100, 0x200
 
 OPT_ANCHOR_PATH = 0

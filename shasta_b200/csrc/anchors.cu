@@ -305,7 +305,7 @@ int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, co
                              float* featlo_cur, float* featlo_prev, bool featlo_ready, int B, int S, float* part,
                              cudaStream_t s);
 int launch_anchor_out_tc(const shasta_params_t& p, const float* part, int S, int B, float* hid, float* hidlo,
-                         float* feat_cur, float* feat_prev, cudaStream_t s);
+                         float* out_part, float* feat_cur, float* feat_prev, cudaStream_t s);
 int anchor_tc_splits(int M, int B);  // anchors_tc.cu
 int launch_anchor_hidden_tc(const shasta_params_t& p, const float* feat_cur, const float* feat_prev, int B, int S,
                             float* part, cudaStream_t s);
@@ -376,8 +376,8 @@ int launch_anchor_shapes(const shasta_params_t& p, int B, float* ws, const WsLay
   }
   if (mid) cudaEventRecord(mid, s);
   if (out_tc) {
-    int rc = launch_anchor_out_tc(p, part, S, B, ws + L.off[SHASTA_WS_HID], ws + L.off[SHASTA_WS_HIDLO], feat_cur,
-                                  feat_prev, s);
+    int rc = launch_anchor_out_tc(p, part, S, B, ws + L.off[SHASTA_WS_HID], ws + L.off[SHASTA_WS_HIDLO],
+                                  ws + L.off[SHASTA_WS_OUT_PART], feat_cur, feat_prev, s);
     if (rc) return rc;
   }
   if (S_out) *S_out = S;

@@ -529,9 +529,23 @@ __global__ void anchor_reduce_kernel(const float* __restrict__ part, int S, int 
   }
 }
 
+struct AnchorOutArgs {
+  const float* bias[4];
+  float* out[4];
+};
+// anchor row = | sum over split-K partials + bias |   (partials in the mode-0 layout [s][b][i][320])
+__global__ void anchor_out_finish_kernel(const float* __restrict__ part, int S, int B, AnchorOutArgs a, size_t bstride) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 4 * B * kF) return;
+  const int n = idx % kF, i = (idx / kF) % 4, b = idx / (4 * kF);
+  float sum = 0.f;
+  for (int sp = 0; sp < S; ++sp) sum += part[(((size_t)sp * B + b) * 4 + i) * kF + n];   // fixed order
+  a.out[i][(size_t)b * bstride + n] = fabsf(sum + __ldg(a.bias[i] + n));
+}
+
 // aug_shape.i.2 + abs on tensor cores: the anchor rows of the augmented feature arrays
 int launch_anchor_out_tc(const shasta_params_t& p, const float* part, int S, int B, float* hid, float* hidlo,
-                         float* feat_cur, float* feat_prev, cudaStream_t s) {
+                         float* out_part, float* feat_cur, float* feat_prev, cudaStream_t s) {
   const int M = p.max_obj, N5 = 5 * M, T = M + 2;
   AnchorBias4 b0;
   for (int i = 0; i < 4; ++i) b0.b[i] = p.aug_shape_b0[i];
@@ -549,17 +563,27 @@ int launch_anchor_out_tc(const shasta_params_t& p, const float* part, int S, int
                         (uint64_t)N5, (uint64_t)ldlo, (uint32_t)bn);
     if (rc) return rc;
   }
+  // split-K over kOutSplits CTAs per (anchor, row tile): the 12-CTA single-pass launch was a 32-block latency chain.
+  // Partial sums go to OUT_PART, a small kernel adds them up, adds the bias and takes |.|
+  const int kblocks = (N5 + kT2BK - 1) / kT2BK;
+  const int S2 = kblocks >= 16 ? 4 : 1;
   AnchorT2Job job = {};
-  job.B = B, job.nrows = kF, job.kblocks = (N5 + kT2BK - 1) / kT2BK, job.S = 1;
+  job.B = B, job.nrows = kF, job.kblocks = kblocks, job.S = S2;
   job.ntiles_n = (kF + kT2BM - 1) / kT2BM;
-  job.raw_hi = g_options[SHASTA_OPT_TC_RAW_HI], job.dbg = 0, job.mode = 1, job.part = nullptr;
+  job.raw_hi = g_options[SHASTA_OPT_TC_RAW_HI], job.dbg = 0, job.mode = (S2 > 1) ? 0 : 1;
+  job.part = out_part;   // mode 0 layout: [s][b][i][320]
+  AnchorOutArgs oa;
   for (int i = 0; i < 4; ++i) {
-    job.bias[i] = p.aug_shape_b2[i];
+    job.bias[i] = oa.bias[i] = p.aug_shape_b2[i];
     // newborn/fp extend the T axis of the previous frame, dead/fn the D axis of the current frame
-    job.out[i] = ((i < 2) ? feat_prev : feat_cur) + (size_t)(M + (i & 1)) * kF;
+    job.out[i] = oa.out[i] = ((i < 2) ? feat_prev : feat_cur) + (size_t)(M + (i & 1)) * kF;
   }
   job.out_bstride = (size_t)T * kF;
-  return t2_launch(maps, job, bn, (B + bn - 1) / bn, s);
+  int rc = t2_launch(maps, job, bn, (B + bn - 1) / bn, s);
+  if (rc || S2 == 1) return rc;
+  anchor_out_finish_kernel<<<(4 * B * kF + 255) / 256, 256, 0, s>>>(out_part, S2, B, oa, (size_t)T * kF);
+  SHASTA_CHECK_LAUNCH("anchor_out_finish_kernel");
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

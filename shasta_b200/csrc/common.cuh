@@ -62,6 +62,7 @@ __host__ inline WsLayout ws_layout(int B, int M) {
   sz[SHASTA_WS_COUNTERS] = 64;
   sz[SHASTA_WS_HID] = (size_t)4 * B * 5 * M;
   sz[SHASTA_WS_HIDLO] = (size_t)4 * B * 5 * M;
+  sz[SHASTA_WS_OUT_PART] = (size_t)4 * B * 4 * kF;
   sz[SHASTA_WS_BOX_BWD] = (size_t)B * 4 * (16 + 2 * (size_t)((7 * M) / 32 + 1) + 7 * (size_t)M);
   size_t o = 0;
   for (int i = 0; i < SHASTA_WS_NUM_REGIONS; ++i) {

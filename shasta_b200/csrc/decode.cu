@@ -21,28 +21,42 @@ decode_kernel(const float* __restrict__ m1, const float* __restrict__ m2, const 
   const float* Bm = m2 + (size_t)b * T * M;  // (M+2, M)
 
   // ---- rows: each real previous object over {real detections, dead, FN}        eval.py:132-151
-  for (int n = threadIdx.x; n < M; n += kDecThreads) {
-    int state = -1, arg = -1;
-    float score = 0.f;
-    if (n < np) {
-      const float* row = A + (size_t)n * D;
-      float best = -INFINITY;
-      for (int k = 0; k < nd; ++k) {
-        const float v = row[k];
-        if (v > best) best = v, arg = k;  // first maximum, like torch.max / numpy argmax
+  // a warp per row, lanes stride over the columns (coalesced); first maximum like torch.max / numpy argmax
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int n = warp; n < M; n += kDecThreads / 32) {
+      int state = -1, arg = -1;
+      float score = 0.f;
+      if (n < np) {
+        const float* row = A + (size_t)n * D;
+        float best = -INFINITY;
+        int barg = 0x7fffffff;
+        for (int k = lane; k < nd; k += 32) {
+          const float v = row[k];
+          if (v > best) best = v, barg = k;   // ascending k per lane: keeps the lane's first maximum
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oa = __shfl_xor_sync(0xffffffffu, barg, o);
+          if (ob > best || (ob == best && oa < barg)) best = ob, barg = oa;
+        }
+        arg = (barg == 0x7fffffff) ? -1 : barg;
+        if (row[M] > best) best = row[M], arg = nd;
+        if (row[M + 1] > best) best = row[M + 1], arg = nd + 1;
+        state = 0;
+        if ((double)best > 0.5 && arg == nd) state = 1;
+        else if ((double)best > 0.5 && arg == nd + 1) {
+          state = 2;
+          score = 1.0f - row[M];  // 1 - matched_dets[n,-2]
+        }
       }
-      if (row[M] > best) best = row[M], arg = nd;
-      if (row[M + 1] > best) best = row[M + 1], arg = nd + 1;
-      state = 0;
-      if ((double)best > 0.5 && arg == nd) state = 1;
-      else if ((double)best > 0.5 && arg == nd + 1) {
-        state = 2;
-        score = 1.0f - row[M];  // 1 - matched_dets[n,-2]
+      if (lane == 0) {
+        prev_state[(size_t)b * M + n] = state;
+        prev_argmax[(size_t)b * M + n] = arg;
+        fn_score[(size_t)b * M + n] = score;
       }
     }
-    prev_state[(size_t)b * M + n] = state;
-    prev_argmax[(size_t)b * M + n] = arg;
-    fn_score[(size_t)b * M + n] = score;
   }
   __syncthreads();
   // ordered compaction of the kept rows (keep_prev_dets): ballot + warp-total scan, 256 rows per pass
@@ -54,7 +68,7 @@ decode_kernel(const float* __restrict__ m1, const float* __restrict__ m2, const 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int n0 = 0; n0 < np; n0 += kDecThreads) {
       const int n = n0 + threadIdx.x;
-      const bool keep = n < np && prev_state[(size_t)b * M + n] == 0;   // written by this same thread above
+      const bool keep = n < np && prev_state[(size_t)b * M + n] == 0;   // written above, visible after the barrier
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
       if (lane == 0) s_wtot[warp] = __popc(bal);
       __syncthreads();
