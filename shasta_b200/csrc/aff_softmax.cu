@@ -147,10 +147,9 @@ int launch_aff_softmax(const float* packed, int B, int M, float* ws, const WsLay
     return 0;
   }
   const size_t smem = sizeof(float) * (((size_t)T + 256) * kAffRows + 2 * kAffKC * kAffNT);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static MaxPerDevice configured;
+  if (smem > 48 * 1024 && configured.raise(smem)) {
     SHASTA_CUDA(cudaFuncSetAttribute(aff_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
   }
   const long long nrows = (long long)B * T;
   aff_row_kernel<<<(unsigned)((nrows + kAffRows - 1) / kAffRows), kAffThreads, smem, s>>>(

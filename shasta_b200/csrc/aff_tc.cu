@@ -306,10 +306,9 @@ int launch_aff_tc(const float* packed, int B, int M, const float* residual, floa
   }
   const size_t tile = 128 * (size_t)((plan.np5 + 1 > row_stride(M)) ? plan.np5 + 1 : row_stride(M)) * sizeof(float);
   const size_t smem = 128 + (size_t)kAtSlots * kAtSlotBytes + 256 + 6 * 256 * sizeof(float) + tile;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static MaxPerDevice configured;
+  if (configured.raise(smem)) {
     SHASTA_CUDA(cudaFuncSetAttribute(aff_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
   }
   const long long nrows = (long long)B * (M + 2);
   aff_tc_kernel<<<(unsigned)((nrows + 127) / 128), kAtThreads, smem, s>>>(

@@ -411,23 +411,21 @@ int launch_anchor_boxes(const shasta_params_t& p, const float* det_boxes, const 
   const size_t smem_shape = out_tc ? 0 : sizeof(float) * (size_t)BG * N5;
   const size_t smem_dets = sizeof(float) * (size_t)(7 * M + (H7 > 0 ? H7 : 1));
   const size_t smem = smem_shape > smem_dets ? smem_shape : smem_dets;
-  static size_t configured[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > configured[BG == 8]) {
+  static MaxPerDevice configured[2];
+  if (smem > 48 * 1024 && configured[BG == 8].raise(smem)) {
     if (BG == 8)
       SHASTA_CUDA(cudaFuncSetAttribute(anchor_finish_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else
       SHASTA_CUDA(cudaFuncSetAttribute(anchor_finish_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[BG == 8] = smem;
   }
-  static bool carveout_set = false;
-  if (!carveout_set) {
+  static OncePerDevice carveout_set;
+  if (carveout_set.first()) {
     // same shared-memory carve-out as the big-smem GEMM kernels: an SM only runs kernels of one carve-out at a time,
     // and the light launch is meant to co-reside with the anchors GEMM
     SHASTA_CUDA(cudaFuncSetAttribute(anchor_finish_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
     SHASTA_CUDA(cudaFuncSetAttribute(anchor_finish_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
-    carveout_set = true;
   }
   const int groups = (B + BG - 1) / BG;
   const int slices = (groups >= 16) ? 2 : (groups >= 6 ? 5 : 10);  // 320 outputs = 10 passes of 32 rows

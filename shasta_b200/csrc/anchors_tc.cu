@@ -239,11 +239,10 @@ int launch_anchor_hidden_tc(const shasta_params_t& p, const float* feat_cur, con
   if (rc) return rc;
   rc = make_map_f32(&maps.x[1], feat_prev, (uint64_t)B, K, ld);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice configured;
+  if (configured.first()) {
     SHASTA_CUDA(cudaFuncSetAttribute(anchor_hidden_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kTcSmemBytes));
-    configured = true;
   }
   const int ntn = (int)((N5 + kTcBN - 1) / kTcBN), ntb = (B + kTcBM - 1) / kTcBM;
   dim3 grid(ntn * ntb, 4, S);

@@ -466,13 +466,12 @@ __global__ void feat_lo_kernel(const float* __restrict__ feat0, const float* __r
 }
 
 static int t2_launch(const AnchorT2Maps& maps, const AnchorT2Job& job, int bn, int ntb, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice configured;
+  if (configured.first()) {
     SHASTA_CUDA(cudaFuncSetAttribute(anchor_hidden_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      T2Cfg<64>::kSmemBytes));
     SHASTA_CUDA(cudaFuncSetAttribute(anchor_hidden_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      T2Cfg<128>::kSmemBytes));
-    configured = true;
   }
   dim3 grid(job.ntiles_n * ntb, 4, job.S);
   if (bn == 64)
@@ -657,11 +656,10 @@ int launch_shared_conv(const float* packed, const float* x_nchw, int nmaps, int 
   job.bias[0] = packed + (size_t)2 * kConvCout * kConvK, job.bias[1] = job.bias[0] + kConvCout;
   job.out[0] = out_nhwc;
   job.H = H, job.W = W, job.tiles_x = (W + kConvTX - 1) / kConvTX;
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice configured;
+  if (configured.first()) {
     SHASTA_CUDA(cudaFuncSetAttribute(anchor_hidden_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      T2Cfg<64>::kSmemBytes));
-    configured = true;
   }
   dim3 grid(job.tiles_x * ((H + kConvTY - 1) / kConvTY), nmaps, 1);
   anchor_hidden_tc2_kernel<64><<<grid, kT2Threads, T2Cfg<64>::kSmemBytes, s>>>(maps, job);

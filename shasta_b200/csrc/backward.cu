@@ -202,10 +202,9 @@ int launch_backward(const shasta_params_t& p, const shasta_grads_t& g, const flo
   for (int i = 0; i < 6; ++i) ag.w[i] = g.aff_w[i], ag.b[i] = g.aff_b[i];
   const int DR = (T + 3) / 4 * 4;
   const size_t smem = sizeof(float) * ((size_t)(2 * DR + 128 + 64 + 32 + 64 + 128 + 128) * kAffRows + 2 * kAffKC * kAffNT);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static MaxPerDevice configured;
+  if (configured.raise(smem)) {
     SHASTA_CUDA(cudaFuncSetAttribute(aff_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
   }
   // d residual is written in place of the forward residual: a CTA reads its 32 rows before anything is written
   aff_bwd_kernel<<<(unsigned)((nrows + kAffRows - 1) / kAffRows), kAffThreads, smem, s>>>(packed, P, B, M, residual,

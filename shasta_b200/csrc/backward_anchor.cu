@@ -191,10 +191,9 @@ int launch_backward_anchor(const shasta_params_t& p, const shasta_grads_t& gr, i
   a.rc0_w = p.res_coeff_w[0];
   for (int i = 0; i < 4; ++i) a.b0[i] = p.aug_shape_b0[i], a.w2[i] = p.aug_shape_w2[i], a.b2[i] = p.aug_shape_b2[i];
   const size_t smem = sizeof(float) * ((size_t)N5 + kProjShape + 2 * kF);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static MaxPerDevice configured;
+  if (smem > 48 * 1024 && configured.raise(smem)) {
     SHASTA_CUDA(cudaFuncSetAttribute(anchor_prep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
   }
   anchor_prep_bwd_kernel<<<dim3(B, 4), 256, smem, s>>>(a, ws + L.off[SHASTA_WS_HIDDEN_PART], S, B, M,
                                                        ws + L.off[SHASTA_WS_DPROJ_PREV], ws + L.off[SHASTA_WS_DPROJ_CUR],

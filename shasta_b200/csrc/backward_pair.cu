@@ -595,10 +595,9 @@ int launch_backward_pair(const shasta_grads_t& gr, const float* packed, int B, i
   const int wcount = (int)(P.pair_end - P.l2a);
   const size_t smem = sizeof(float) * (8 * kProj + 16 * kPbQStride + 64 + 128 + 16 + (wcount + 3) / 4 * 4 +
                                        St::rows * 128 + 8 * kProj + 16 * kProj);
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice configured;
+  if (configured.first()) {
     SHASTA_CUDA(cudaFuncSetAttribute(pair_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   dim3 grid((T + 15) / 16, B);
   pair_bwd_kernel<<<grid, kPbThreads, smem, s>>>(packed, P, B, M, ws + L.off[SHASTA_WS_PROJ_PREV],

@@ -274,6 +274,28 @@ extern thread_local int g_launch_count;
     }                                                                           \
   } while (0)
 
+// ---- one-time kernel attribute set-up is per DEVICE (function attributes live in the device's context) --------------
+struct OncePerDevice {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+struct MaxPerDevice {   // raise(x): true when x exceeds what was configured on the current device so far
+  size_t v[64] = {};
+  bool raise(size_t x) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+    if (x <= v[d]) return false;
+    v[d] = x;
+    return true;
+  }
+};
+
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

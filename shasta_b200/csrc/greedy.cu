@@ -96,10 +96,9 @@ int launch_greedy_assign(const float* dets, const float* tracks, const float* ma
     set_error("greedy_assign: at most %d tracks per problem", (int)(200 * 1024 / 20));
     return SHASTA_ERR_SIZE;
   }
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static MaxPerDevice configured;
+  if (smem > 48 * 1024 && configured.raise(smem)) {
     SHASTA_CUDA(cudaFuncSetAttribute(greedy_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
   }
   greedy_assign_kernel<<<problems, kGrThreads, smem, s>>>(dets, tracks, max_diff, det_cat, track_cat, n_det, n_track,
                                                           nmax, mmax, match, det_near, track_near);

@@ -276,10 +276,9 @@ int launch_pairwise(const float* packed, int B, int M, float* ws, const WsLayout
   const PackLayout P = pack_layout(M);
   const int T = M + 2;
   const size_t smem = sizeof(float) * (PwSmem::w + (P.pair_end - P.l2a));
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice configured;
+  if (configured.first()) {
     SHASTA_CUDA(cudaFuncSetAttribute(pairwise_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   dim3 grid((T + kPwDT - 1) / kPwDT, (T + kPwTT - 1) / kPwTT, B);
   pairwise_ffma_kernel<<<grid, kPwThreads, smem, s>>>(

@@ -457,18 +457,16 @@ int launch_pairwise_tc(const float* packed, int B, int M, float* ws, const WsLay
   const bool bf16 = variant == 2;
   const size_t bimg = (bf16 ? (P.tc16_end - P.tc16_begin) : (P.tc32_end - P.tc32_begin)) * sizeof(float);
   const size_t smem = 128 + bimg + 128 + sizeof(float) * ((P.pair_end - P.l2a) + 256 + 2 * PtBuf::floats);
-  static bool configured[2] = {false, false};
-  static int sm_count = 0;
-  if (!configured[bf16]) {
+  static OncePerDevice configured[2];
+  if (configured[bf16].first()) {
     if (bf16)
       SHASTA_CUDA(cudaFuncSetAttribute(pairwise_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else
       SHASTA_CUDA(cudaFuncSetAttribute(pairwise_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    SHASTA_CUDA(cudaGetDevice(&dev));
-    SHASTA_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    configured[bf16] = true;
   }
+  int dev = 0, sm_count = 0;
+  SHASTA_CUDA(cudaGetDevice(&dev));
+  SHASTA_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   const long long nitems = (long long)B * ((T + kPtTT - 1) / kPtTT) * ((T + kPtDT - 1) / kPtDT);
   const int grid = (int)(nitems < 2LL * sm_count ? nitems : 2LL * sm_count);   // persistent: two CTAs per SM
   int* counter = reinterpret_cast<int*>(ws + L.off[SHASTA_WS_COUNTERS]);

@@ -225,11 +225,10 @@ bool project_uses_tc(int B, int M) {
 int launch_project_aux(int B, int M, float* ws, const WsLayout& L, float* det_boxes_inout, cudaStream_t s) {
   const int T = M + 2;
   const int naux = (int)((2LL * B * T + kProjThreads - 1) / kProjThreads);
-  static bool carveout_set = false;
-  if (!carveout_set) {   // co-resides with the anchors GEMM: same (maximum) shared-memory carve-out
+  static OncePerDevice carveout_set;
+  if (carveout_set.first()) {   // co-resides with the anchors GEMM: same (maximum) shared-memory carve-out
     SHASTA_CUDA(cudaFuncSetAttribute(project_aux_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
-    carveout_set = true;
   }
   project_aux_kernel<<<naux + B, kProjThreads, sizeof(float) * 3 * T, s>>>(
       B, M, naux, ws + L.off[SHASTA_WS_BOX_CUR], ws + L.off[SHASTA_WS_BOX_PREV], ws + L.off[SHASTA_WS_AUX_PREV],

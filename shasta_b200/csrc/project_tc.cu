@@ -193,10 +193,9 @@ project_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, 
 
 int launch_project_tc(const float* packed, int B, int M, float* ws, const WsLayout& L, cudaStream_t s) {
   const size_t smem = 128 + (size_t)kPjSlots * kPjPieceFloats * 4 + 128 + (size_t)128 * kPjRowStride * 4;
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice configured;
+  if (configured.first()) {
     SHASTA_CUDA(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   const long long nrows = (long long)B * (M + 2);
   dim3 grid((unsigned)((nrows + 127) / 128), 2);

@@ -435,6 +435,23 @@ def test_internal_side_stream_changes_nothing():
         assert torch.equal(a, b)
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_second_device_in_same_process():
+    """Kernel attributes (dynamic shared memory, carve-out) are per device: a model on cuda:1 after one on cuda:0."""
+    M, B, H, W = 20, 9, 32, 32
+    pc_start = (-W * 0.3, -H * 0.3)
+    w = synthetic.make_weights(M, seed=12)
+    d = synthetic.make_frame_pairs(B, M, H, W, 61, pc_start=pc_start)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        model = G.make_model(M, pc_start, w, device=dev)
+        args = [G.t(d[k], device=dev) for k in ("bev", "prev_bev", "det_boxes", "prev_det_boxes")]
+        with torch.no_grad(), torch.cuda.device(dev):
+            m1, m2 = model.affinity(*args)
+            outs.append((m1.cpu(), m2.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_pipelined_host_inputs_match_device_path():
     """Pinned host inputs run the gather on a side stream into alternating workspaces (two-stage pipeline over calls):
     every call must return what the plain device path returns, including the in-place back-projection."""
