@@ -52,6 +52,7 @@ def parse():
                          "+ Adam on the differentiated parameters) instead of inference")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--bf16", action="store_true", help="bf16 mode (shasta_forward_bf16): separate tolerance, dtype bf16")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -173,17 +174,18 @@ def build_model(a, pc_start, device):
         model = build_track(cfg)
     model.eval()
     model.kernel_flags = a.flags
+    model.bf16 = bool(getattr(a, "bf16", False))
     model.cuda_graphs = not getattr(a, "no_graph", False)
     return model
 
 
-def algorithmic_bytes_anchor_hidden(M, B):
+def algorithmic_bytes_anchor_hidden(M, B, bf16=False):
     """Dominant kernel (anchor_hidden_kernel): the four aug_shape.i.0 matrices are read once (4 x 5M x 320M fp32),
     the gathered features of both frames once; split-K partials are an implementation artefact and
     are not counted."""
     w = 4 * (5 * M) * (320 * M) * 4
     x = 2 * B * (320 * M) * 4
-    return w + x
+    return (w + x) // 2 if bf16 else w + x   # bf16 mode streams bf16 copies of both operands
 
 
 def path_bytes(M, B, hw):
@@ -530,18 +532,19 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     dom = max(stages, key=stages.get)
-    ab = algorithmic_bytes_anchor_hidden(M, B)
+    ab = algorithmic_bytes_anchor_hidden(M, B, a.bf16 and (a.anchor_path == 2 or (a.anchor_path == 0 and B > 4)))
     ah_ms = stages["anchor_hidden"]
     achieved = ab / (ah_ms / 1e3) / 1e9 if ah_ms > 0 else 0.0
     tc_path = a.anchor_path == 2 or (a.anchor_path == 0 and B > 4)
     traffic = None
-    if tc_path and M == 200 and B == 64:   # dram read+write of one launch from the committed ncu --set full capture
+    if tc_path and M == 200 and B == 64 and not a.bf16:   # dram bytes of one launch from the committed ncu capture
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[
                 "anchor_hidden_tc2_kernel<64>"]["traffic_bytes_per_launch"]
         except Exception:  # noqa: BLE001
             traffic = None
-    roofline = {"kernel": "anchor_hidden_tc2_kernel<64> (aug_shape.i.0, the 1.03 GB weight stream)" if tc_path
+    roofline = {"kernel": ("anchor_hidden_bf16_kernel (aug_shape.i.0, 0.51 GB of bf16 weights)" if a.bf16 else
+                           "anchor_hidden_tc2_kernel<64> (aug_shape.i.0, the 1.03 GB weight stream)") if tc_path
                 else "anchor_hidden_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab, "ms_per_launch": ah_ms, "dominant_stage_by_time": dom,
@@ -556,7 +559,7 @@ def main():
             cpu = cpu_reference_run(a, a.cpu_seconds, weights_state=state)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": n_warm, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "b200",
+                "vs_baseline": None, "dtype": "bf16" if a.bf16 else "f32", "data": "synthetic", "impl": "b200",
                 "config": config_dict(a, {"flags": a.flags, "anchor_path": a.anchor_path, "cuda_graph": not a.no_graph}), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * a.steps}
         print(json.dumps(line))

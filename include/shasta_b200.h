@@ -239,6 +239,21 @@ SHASTA_API int shasta_forward_f32(const shasta_params_t* host_params, const floa
                        const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes,
                        float* matched1, float* matched2, uint32_t flags, shasta_stream_t stream);
 
+/* bf16 mode of the same path (BASELINE configs[1] "fp32 and bf16"; its tolerance is stated separately from fp32:
+ * affinities within 2e-2 relative, association agreement reported, not required to be identical):
+ *   - aug_shape.i.0 runs on a bf16 copy of its weights (shasta_pack_anchor_bf16, shasta_anchor_bf16_bytes(M) bytes,
+ *     once per weight version) and bf16 copies of the gathered features: half the HBM bytes of the dominant kernel;
+ *   - the pairwise tiles run as bf16 UMMAs (pairwise variant 2) unless flags pick another variant;
+ *   - everything else (gather, box geometry, projections, aff, softmax) stays fp32 / fp32-equivalent.
+ * Batches of up to 4 frame pairs use the fp32 streaming kernel for aug_shape.i.0 in either mode. Inference only. */
+SHASTA_API size_t shasta_anchor_bf16_bytes(int max_obj);
+SHASTA_API int shasta_pack_anchor_bf16(const shasta_params_t* host_params, void* anchor_w_bf16, size_t bytes,
+                            shasta_stream_t stream);
+SHASTA_API int shasta_forward_bf16(const shasta_params_t* host_params, const float* packed, const void* anchor_w_bf16,
+                        const float* bev, const float* prev_bev, float* det_boxes, const float* prev_det_boxes,
+                        int batch, const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes,
+                        float* matched1, float* matched2, uint32_t flags, shasta_stream_t stream);
+
 /* First stage of shasta_forward_f32 on its own (a1-a2 for both frames, writing FEAT_* and, when the anchors path in
  * use for (max_obj, batch) wants them, FEATLO_*), so that a caller can run it on another stream: the gather of the
  * next batch (PCIe-bound when the BEV maps are host-resident and sampled in place) then overlaps the remaining stages

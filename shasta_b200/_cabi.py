@@ -90,6 +90,10 @@ SYMBOLS = {
     "shasta_aff_softmax_f32": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "shasta_forward_f32": (_i, [ctypes.POINTER(ShastaParams), _vp, _vp, _vp, _vp, _vp, _i,
                                 ctypes.POINTER(ShastaGeom), _vp, _sz, _vp, _vp, _u32, _vp]),
+    "shasta_anchor_bf16_bytes": (_sz, [_i]),
+    "shasta_pack_anchor_bf16": (_i, [ctypes.POINTER(ShastaParams), _vp, _sz, _vp]),
+    "shasta_forward_bf16": (_i, [ctypes.POINTER(ShastaParams), _vp, _vp, _vp, _vp, _vp, _vp, _i,
+                                 ctypes.POINTER(ShastaGeom), _vp, _sz, _vp, _vp, _u32, _vp]),
     "shasta_gather_pair_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, ctypes.POINTER(ShastaGeom), _vp, _sz, _u32, _vp]),
     "shasta_greedy_assign_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "shasta_shared_conv_packed_bytes": (_sz, []),

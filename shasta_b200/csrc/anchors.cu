@@ -339,8 +339,13 @@ bool anchor_boxes_independent(const shasta_params_t& p, int B) {
 }
 
 // aug_shape.i.0 (+ aug_shape.i.2 when it runs on tensor cores); returns the split-K count in *S_out
+int anchor_bf16_splits(int M, int B);   // anchors_bf16.cu
+int launch_anchor_hidden_bf16(const shasta_params_t& p, const void* w16, const void* feat16_cur, const void* feat16_prev,
+                              int B, int S, float* part, cudaStream_t s);
+
+// w16 != NULL (bf16 mode): bf16 copies of the four aug_shape.i.0 matrices; FEATLO_* then hold bf16 copies of the features
 int launch_anchor_shapes(const shasta_params_t& p, int B, float* ws, const WsLayout& L, cudaStream_t s, cudaEvent_t mid,
-                         bool featlo_ready, int* S_out) {
+                         bool featlo_ready, int* S_out, const void* w16) {
   const int M = p.max_obj;
   const int N5 = 5 * M;
   float* feat_cur = ws + L.off[SHASTA_WS_FEAT_CUR];
@@ -350,7 +355,12 @@ int launch_anchor_shapes(const shasta_params_t& p, int B, float* ws, const WsLay
   bool tc_hidden, out_tc;
   anchor_plan(p, B, tc_hidden, out_tc);
   int S;
-  if (tc_hidden) {                                // tcgen05, weights on the M side, TMEM-resident low parts
+  if (tc_hidden && w16 != nullptr) {              // bf16 mode: half the weight bytes, plain bf16 UMMA
+    S = anchor_bf16_splits(M, B);
+    int rc = launch_anchor_hidden_bf16(p, w16, ws + L.off[SHASTA_WS_FEATLO_CUR], ws + L.off[SHASTA_WS_FEATLO_PREV], B, S,
+                                       part, s);
+    if (rc) return rc;
+  } else if (tc_hidden) {                         // tcgen05, weights on the M side, TMEM-resident low parts
     S = anchor_tc2_splits(M, B);
     int rc = launch_anchor_hidden_tc2(p, feat_cur, feat_prev, ws + L.off[SHASTA_WS_FEATLO_CUR],
                                       ws + L.off[SHASTA_WS_FEATLO_PREV], featlo_ready, B, S, part, s);
@@ -446,9 +456,9 @@ int launch_anchor_boxes(const shasta_params_t& p, const float* det_boxes, const 
 }
 
 int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
-                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid, bool featlo_ready) {
+                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid, bool featlo_ready, const void* w16) {
   int S = 1;
-  int rc = launch_anchor_shapes(p, B, ws, L, s, mid, featlo_ready, &S);
+  int rc = launch_anchor_shapes(p, B, ws, L, s, mid, featlo_ready, &S, w16);
   if (rc) return rc;
   return launch_anchor_boxes(p, det_boxes, prev_boxes, B, ws, L, S, false, s);
 }

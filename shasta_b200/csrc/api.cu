@@ -262,10 +262,10 @@ int shasta_aff_softmax_f32(const float* packed, int batch, int max_obj, float* w
                             (cudaStream_t)stream, nullptr);
 }
 
-int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, const float* bev,
-                       const float* prev_bev, float* det_boxes, const float* prev_det_boxes, int batch,
-                       const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes, float* matched1,
-                       float* matched2, uint32_t flags, shasta_stream_t stream) {
+static int forward_impl(const shasta_params_t* host_params, const float* packed, const void* w16, const float* bev,
+                        const float* prev_bev, float* det_boxes, const float* prev_det_boxes, int batch,
+                        const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes, float* matched1,
+                        float* matched2, uint32_t flags, shasta_stream_t stream) {
   int rc = check_params(host_params);
   if (rc) return rc;
   const int M = host_params->max_obj;
@@ -302,11 +302,12 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
   // a1-a2: both frames in one launch (blockIdx.y selects the frame)
   // the tcgen05 anchors GEMM takes the tf32 low parts of the features as a second TMA operand: the gather writes them
   const bool featlo = anchor_uses_featlo(M, batch);
+  if (!featlo) w16 = nullptr;   // small batches stream the fp32 weights on CUDA cores in either mode
   if (!(flags & SHASTA_FLAG_SKIP_GATHER)) {
     rc = launch_gather(bev, det_boxes, workspace + L.off[SHASTA_WS_FEAT_CUR], prev_bev, prev_det_boxes,
                        workspace + L.off[SHASTA_WS_FEAT_PREV], 2, 11, batch, M, *host_geom, fstride, (int)(flags & 3u),
                        s, featlo ? workspace + L.off[SHASTA_WS_FEATLO_CUR] : nullptr,
-                       featlo ? workspace + L.off[SHASTA_WS_FEATLO_PREV] : nullptr);
+                       featlo ? workspace + L.off[SHASTA_WS_FEATLO_PREV] : nullptr, w16 != nullptr ? 1 : 0);
     if (rc) return rc;
   }
   STAGE_MARK(1);
@@ -320,7 +321,7 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
     SHASTA_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
     // the GEMM is submitted FIRST: its one-CTA-per-SM grid takes its shared memory and registers, the light box
     // kernels then fit into what is left of every SM (the other order parks them first and the GEMM CTAs wait)
-    rc = launch_anchor_shapes(*host_params, batch, workspace, L, s, nullptr, featlo, nullptr);  // a3
+    rc = launch_anchor_shapes(*host_params, batch, workspace, L, s, nullptr, featlo, nullptr, w16);  // a3
     if (rc) return rc;
     rc = launch_anchor_boxes(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, 1, true, side->stream);
     if (rc) return rc;
@@ -332,7 +333,7 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
     if (rc) return rc;
   } else {
     rc = launch_anchors(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, s, ev ? ev[2] : nullptr,
-                        featlo);  // a3-a4
+                        featlo, w16);  // a3-a4
     if (rc) return rc;
     STAGE_MARK(3);
     rc = launch_project(packed, batch, M, workspace, L, det_boxes, s);  // first layers, aux, colnorm, back-projection
@@ -348,6 +349,44 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
 #undef STAGE_MARK
   g_last_forward_launches = g_launch_count;
   return 0;
+}
+
+int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, const float* bev,
+                       const float* prev_bev, float* det_boxes, const float* prev_det_boxes, int batch,
+                       const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes, float* matched1,
+                       float* matched2, uint32_t flags, shasta_stream_t stream) {
+  return forward_impl(host_params, packed, nullptr, bev, prev_bev, det_boxes, prev_det_boxes, batch, host_geom,
+                      workspace, workspace_bytes, matched1, matched2, flags, stream);
+}
+
+int shasta_forward_bf16(const shasta_params_t* host_params, const float* packed, const void* anchor_w_bf16,
+                        const float* bev, const float* prev_bev, float* det_boxes, const float* prev_det_boxes,
+                        int batch, const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes,
+                        float* matched1, float* matched2, uint32_t flags, shasta_stream_t stream) {
+  NOT_NULL(anchor_w_bf16);
+  ALIGNED16(anchor_w_bf16);
+  if (flags & SHASTA_FLAG_SKIP_GATHER) {
+    set_error("shasta_forward_bf16: the split gather stage writes fp32-mode operands; run the whole path in one call");
+    return SHASTA_ERR_UNSUPPORTED;
+  }
+  if (((flags >> 4) & 15u) == 0) flags |= 0x20u;   // pairwise tiles in bf16 unless the caller picked a variant
+  return forward_impl(host_params, packed, anchor_w_bf16, bev, prev_bev, det_boxes, prev_det_boxes, batch, host_geom,
+                      workspace, workspace_bytes, matched1, matched2, flags, stream);
+}
+
+size_t shasta_anchor_bf16_bytes(int max_obj) { return max_obj < 1 ? 0 : anchor_bf16_elems(max_obj) * 2; }
+
+int shasta_pack_anchor_bf16(const shasta_params_t* host_params, void* anchor_w_bf16, size_t bytes,
+                            shasta_stream_t stream) {
+  int rc = check_params(host_params);
+  if (rc) return rc;
+  NOT_NULL(anchor_w_bf16);
+  ALIGNED16(anchor_w_bf16);
+  if (bytes < shasta_anchor_bf16_bytes(host_params->max_obj)) {
+    set_error("bf16 anchor weight buffer too small");
+    return SHASTA_ERR_SIZE;
+  }
+  return launch_pack_anchor_bf16(*host_params, anchor_w_bf16, (cudaStream_t)stream);
 }
 
 int shasta_gather_pair_f32(const float* bev, const float* prev_bev, const float* det_boxes,

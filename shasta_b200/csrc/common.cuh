@@ -315,11 +315,12 @@ int launch_bilinear(const float* im, int H, int W, int C, const float* xs, const
 int launch_gather(const float* bev0, const float* boxes0, float* feat0, const float* bev1, const float* boxes1,
                   float* feat1, int nframes, int box_stride, int B, int M, const shasta_geom_t& g,
                   size_t feat_batch_stride, int variant, cudaStream_t s, float* featlo0 = nullptr,
-                  float* featlo1 = nullptr);
+                  float* featlo1 = nullptr, int lo_mode = 0);
 // `mid` (optional) is recorded between the two kernels of a stage (per-kernel timing for bench.py)
 // `featlo_ready`: the FEATLO_* regions already hold the tf32 low parts of FEAT_* (written by the fused gather)
 int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
-                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid, bool featlo_ready = false);
+                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid, bool featlo_ready = false,
+                   const void* w16 = nullptr);
 int launch_project(const float* packed, int B, int M, float* ws, const WsLayout& L, float* det_boxes_inout,
                    cudaStream_t s);
 int launch_pairwise(const float* packed, int B, int M, float* ws, const WsLayout& L, int variant,
@@ -345,7 +346,9 @@ int launch_shared_conv(const float* packed, const float* x_nchw, int nmaps, int 
                        float* out_nhwc, cudaStream_t s);
 bool anchor_boxes_independent(const shasta_params_t& p, int B);   // the box part of the anchors stage needs no GEMM result
 int launch_anchor_shapes(const shasta_params_t& p, int B, float* ws, const WsLayout& L, cudaStream_t s, cudaEvent_t mid,
-                         bool featlo_ready, int* S_out);
+                         bool featlo_ready, int* S_out, const void* w16 = nullptr);
+size_t anchor_bf16_elems(int M);
+int launch_pack_anchor_bf16(const shasta_params_t& p, void* w16, cudaStream_t s);
 int launch_anchor_boxes(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
                         const WsLayout& L, int S, bool light, cudaStream_t s);
 bool project_uses_tc(int B, int M);

@@ -79,10 +79,16 @@ struct GatherJob {
   const float* boxes[2];
   float* feat[2];
   float* featlo[2];  // optional (B, 320M) bf16: x - tf32_trunc(x), the low operand of the anchors GEMM
+  int lo_mode;       // 0: low parts (fp32-equivalent anchors GEMM), 1: bf16(x) itself (bf16 anchors GEMM)
 };
 
 __device__ __forceinline__ float tf32_lo(float v) {
   return __fsub_rn(v, __uint_as_float(__float_as_uint(v) & 0xffffe000u));
+}
+// four values as bf16 (8 bytes)
+__device__ __forceinline__ uint2 bf16x4(float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
 }
 // four low parts as bf16 (8 bytes)
 __device__ __forceinline__ uint2 tf32_lo4(float4 v) {
@@ -155,7 +161,7 @@ gather_ldg_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, 
   dst[lane16] = v;
   if (job.featlo[f] != nullptr)
     reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(job.featlo[f]) + ((size_t)b * M + m) * kF + p * kC)[lane16] =
-        tf32_lo4(v);
+        job.lo_mode ? bf16x4(v) : tf32_lo4(v);
   }
 }
 
@@ -242,7 +248,8 @@ gather_bulk_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g,
     const float4 v = blend4(a, bb, c, d, t);
     reinterpret_cast<float4*>(feat + s_dst[pt])[q] = v;
     if (job.featlo[f] != nullptr)
-      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(job.featlo[f]) + s_dstlo[pt])[q] = tf32_lo4(v);
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(job.featlo[f]) + s_dstlo[pt])[q] =
+          job.lo_mode ? bf16x4(v) : tf32_lo4(v);
   }
 }
 
@@ -259,9 +266,9 @@ int launch_bilinear(const float* im, int H, int W, int C, const float* xs, const
 
 int launch_gather(const float* bev0, const float* boxes0, float* feat0, const float* bev1, const float* boxes1,
                   float* feat1, int nframes, int box_stride, int B, int M, const shasta_geom_t& g,
-                  size_t feat_batch_stride, int variant, cudaStream_t s, float* featlo0, float* featlo1) {
+                  size_t feat_batch_stride, int variant, cudaStream_t s, float* featlo0, float* featlo1, int lo_mode) {
   GatherJob job;
-  job.featlo[0] = featlo0, job.featlo[1] = featlo1;
+  job.featlo[0] = featlo0, job.featlo[1] = featlo1, job.lo_mode = lo_mode;
   job.bev[0] = bev0, job.boxes[0] = boxes0, job.feat[0] = feat0;
   job.bev[1] = bev1, job.boxes[1] = boxes1, job.feat[1] = feat1;
   const long long total = (long long)B * M * 5;

@@ -116,6 +116,11 @@ class Shasta(nn.Module):
         # (and the caller's device-to-host copies) of the previous call
         self.pipeline_host_inputs = True
         self._pipe = None
+        # bf16 = True: inference runs shasta_forward_bf16 (bf16 copy of the aug_shape.i.0 weights and of the gathered
+        # features for that GEMM, bf16 pairwise tiles; everything else fp32). Tolerance stated separately (2e-2).
+        self.bf16 = False
+        self._w16 = None
+        self._w16_key = None
         self._packed = None
         self._pack_key = None
         self._cparams = None
@@ -209,6 +214,22 @@ class Shasta(nn.Module):
         _cabi.check(rc, "shasta_pack_weights")
         self._packed, self._pack_key, self._cparams = packed, key, p
 
+    def _ensure_bf16_anchor_weights(self, device):
+        """bf16 copies of the four aug_shape.i.0 matrices (half of their 4*5M*320M*4 bytes), cached per weight version."""
+        ws0 = [self.aug_shape[i][0].weight for i in range(4)]
+        key = tuple((w.data_ptr(), w._version) for w in ws0)
+        if key == self._w16_key and self._w16 is not None and self._w16.device == device:
+            return
+        lib = _cabi.lib()
+        nbytes = lib.shasta_anchor_bf16_bytes(self.max_obj)
+        if self._w16 is None or self._w16.numel() * 2 != nbytes or self._w16.device != device:
+            self._w16 = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=device)
+        with torch.cuda.device(device):
+            rc = lib.shasta_pack_anchor_bf16(ctypes.byref(self._cparams), self._w16.data_ptr(), nbytes,
+                                             ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+        _cabi.check(rc, "shasta_pack_anchor_bf16")
+        self._w16_key = key
+
     def _workspace(self, batch, device):
         k = (batch, device)
         ws = self._ws.get(k)
@@ -248,7 +269,7 @@ class Shasta(nn.Module):
         prev_bev = prev_bev if prev_bev.is_contiguous() else prev_bev.contiguous()
         if (not bev.is_cuda or not prev_bev.is_cuda) and (self.kernel_flags & FLAG_TMA_GATHER):
             raise _cabi.ShastaLibraryError("host-resident BEV maps need the LDG sampler (kernel_flags bit 0 clear)")
-        if (self.pipeline_host_inputs and not bev.is_cuda and not prev_bev.is_cuda and not det_boxes.is_cuda
+        if (self.pipeline_host_inputs and not self.bf16 and not bev.is_cuda and not prev_bev.is_cuda and not det_boxes.is_cuda
                 and not prev_det_boxes.is_cuda and not (self.kernel_flags & 0x100)
                 and not (torch.is_grad_enabled() and self.training)):
             return self._affinity_pipelined(bev, prev_bev, det_boxes, prev_det_boxes, device)
@@ -401,21 +422,31 @@ class Shasta(nn.Module):
         self._ensure_packed(device)
         geom = self.bev_extractor.geom(H, W)
 
+        use_bf16 = self.bf16 and not (torch.is_grad_enabled() and self.training)
+        if use_bf16:
+            self._ensure_bf16_anchor_weights(device)
+
         def enqueue(m1, m2):
             with torch.cuda.device(device):
-                rc = lib.shasta_forward_f32(
-                    ctypes.byref(self._cparams), self._packed.data_ptr(), bev.data_ptr(), prev_bev.data_ptr(),
-                    det_c.data_ptr(), prev_c.data_ptr(), B, ctypes.byref(geom), ws.buf.data_ptr(), ws.nbytes,
-                    m1.data_ptr(), m2.data_ptr(), int(self.kernel_flags),
-                    ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
-            _cabi.check(rc, "shasta_forward_f32")
+                stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+                if use_bf16:
+                    rc = lib.shasta_forward_bf16(
+                        ctypes.byref(self._cparams), self._packed.data_ptr(), self._w16.data_ptr(), bev.data_ptr(),
+                        prev_bev.data_ptr(), det_c.data_ptr(), prev_c.data_ptr(), B, ctypes.byref(geom),
+                        ws.buf.data_ptr(), ws.nbytes, m1.data_ptr(), m2.data_ptr(), int(self.kernel_flags), stream)
+                else:
+                    rc = lib.shasta_forward_f32(
+                        ctypes.byref(self._cparams), self._packed.data_ptr(), bev.data_ptr(), prev_bev.data_ptr(),
+                        det_c.data_ptr(), prev_c.data_ptr(), B, ctypes.byref(geom), ws.buf.data_ptr(), ws.nbytes,
+                        m1.data_ptr(), m2.data_ptr(), int(self.kernel_flags), stream)
+            _cabi.check(rc, "shasta_forward_bf16" if use_bf16 else "shasta_forward_f32")
 
         # (not while training: the packed weights change every optimizer step, a capture would never be replayed)
         use_graph = (self.cuda_graphs and not (self.kernel_flags & 0x100) and bev.is_cuda and prev_bev.is_cuda
                      and not self.training and not torch.cuda.is_current_stream_capturing())
         if use_graph:
             key = (bev.data_ptr(), prev_bev.data_ptr(), det_c.data_ptr(), prev_c.data_ptr(), B, H, W,
-                   int(self.kernel_flags), ws.buf.data_ptr(), self._pack_key)
+                   int(self.kernel_flags), ws.buf.data_ptr(), self._pack_key, use_bf16)
             entry = self._graphs.get(key)
             if entry is None:
                 if len(self._graphs) >= 16:

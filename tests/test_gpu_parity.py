@@ -347,6 +347,31 @@ def test_forward_bf16_pairwise_tolerance(name):
     assert np.isfinite(m1).all() and np.isfinite(m2).all()
 
 
+@pytest.mark.parametrize("M,B", [(200, 12), (20, 70), (50, 130)])
+def test_forward_bf16_mode_tolerance(M, B):
+    """shasta_forward_bf16 (bf16 aug_shape.i.0 weights + features, bf16 pairwise tiles) against the fp32 path on the
+    same inputs: bf16 tolerance 2e-2 relative on the affinities (stated separately from the fp32 bar, north_star);
+    the agreement of the row-wise argmax is reported. B > 4 so that the tcgen05 bf16 GEMM is the one that runs;
+    B = 70 / 130 exercise two batch tiles of 64 / 128."""
+    H = W = 32
+    pc_start = (-W * 0.3, -H * 0.3)
+    model = G.make_model(M, pc_start, synthetic.make_weights(M, seed=21))
+    d = synthetic.make_frame_pairs(B, M, H, W, 71, pc_start=pc_start)
+    args = [G.t(d[k]) for k in ("bev", "prev_bev", "det_boxes", "prev_det_boxes")]
+    with torch.no_grad():
+        r1, r2 = model.affinity(args[0], args[1], args[2].clone(), args[3])
+        model.bf16 = True
+        det = args[2].clone()
+        b1, b2 = model.affinity(args[0], args[1], det, args[3])
+        assert model._w16 is not None
+        # the anchor rows / columns are what the bf16 GEMM feeds
+        e1, e2 = G.rel_err(b1.cpu().numpy(), r1.cpu().numpy()), G.rel_err(b2.cpu().numpy(), r2.cpu().numpy())
+        agree = float((b1.argmax(2) == r1.argmax(2)).float().mean())
+    print("bf16 mode M=%d B=%d: rel err m1 %.3g m2 %.3g, row-argmax agreement %.4f" % (M, B, e1, e2, agree))
+    assert e1 < 2e-2 and e2 < 2e-2
+    assert torch.isfinite(b1).all() and torch.isfinite(b2).all()
+
+
 @pytest.mark.parametrize("flags", [0, 1, 0x30])
 @pytest.mark.parametrize("name", golden_names())
 def test_forward_matches_reference_golden(name, flags):
