@@ -188,13 +188,13 @@ def algorithmic_bytes_anchor_hidden(M, B, bf16=False):
     return (w + x) // 2 if bf16 else w + x   # bf16 mode streams bf16 copies of both operands
 
 
-def path_bytes(M, B, hw):
-    """bytes(M,B) per step = W(M) + B*IO(M)."""
+def path_bytes(M, B, hw, bf16=False):
+    """bytes(M,B) per step = W(M) + B*IO(M); bf16 mode reads the aug_shape.i.0 weights as bf16."""
     params = 4 * ((5 * M) * (320 * M) + 5 * M + 320 * 5 * M + 320) + 4 * ((7 * M // 32) * 7 * M + 7 * M // 32 + 7 * (7 * M // 32) + 7)
     params += 640 * 40 + 40 + 800 + 20 + 200 + 10 + 10 + 1 + 6 * 32 + 32 + 256 + 8 + 8 + 1 + 646 * 72 + 72 + 72 * 18 + 18 + 54 + 3
     params += 2 * ((M + 2) * 128 + 128 * 64 + 64 * 32) + 128 + 64 + 32 + 64 + 128 + (M + 2)
     io = 2 * 5 * M * 4 * 64 * 4 + 2 * M * 11 * 4 + 2 * M * (M + 2) * 4
-    return 4 * params + B * io
+    return 4 * params + B * io - (2 * 4 * (5 * M) * (320 * M) if bf16 else 0)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -549,8 +549,8 @@ def main():
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab, "ms_per_launch": ah_ms, "dominant_stage_by_time": dom,
                 "stage_ms": stages, "step_share": ah_ms / max(sum(stages.values()), 1e-9),
-                "path_bytes_per_step": path_bytes(M, B, a.hw),
-                "path_hbm_frac": path_bytes(M, B, a.hw) / (ms / a.steps / 1e3) / 1e9 / hbm_peak}
+                "path_bytes_per_step": path_bytes(M, B, a.hw, a.bf16 and tc_path),
+                "path_hbm_frac": path_bytes(M, B, a.hw, a.bf16 and tc_path) / (ms / a.steps / 1e3) / 1e9 / hbm_peak}
 
     if rank == 0:
         cpu = None
