@@ -304,8 +304,8 @@ int anchor_tc2_splits(int M, int B);  // anchors_tc2.cu
 int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, const float* feat_prev,
                              float* featlo_cur, float* featlo_prev, bool featlo_ready, int B, int S, float* part,
                              cudaStream_t s);
-int launch_anchor_out_tc(const shasta_params_t& p, const float* part, int S, int B, float* hid, float* hidlo,
-                         float* out_part, float* feat_cur, float* feat_prev, cudaStream_t s);
+int launch_anchor_out_tc(const shasta_params_t& p, const float* const* w2, int w2_ld, const float* part, int S, int B,
+                         float* hid, float* hidlo, float* out_part, float* feat_cur, float* feat_prev, cudaStream_t s);
 int anchor_tc_splits(int M, int B);  // anchors_tc.cu
 int launch_anchor_hidden_tc(const shasta_params_t& p, const float* feat_cur, const float* feat_prev, int B, int S,
                             float* part, cudaStream_t s);
@@ -323,18 +323,21 @@ int anchor_splits_in_use(int M, int B) {
 }
 
 // which kernels serve (M, B): hidden layer on tcgen05? output layer on tcgen05 (then anchor_finish only does the boxes)?
-static void anchor_plan(const shasta_params_t& p, int B, bool& tc_hidden, bool& out_tc) {
+static void anchor_plan(const shasta_params_t& p, int B, const float* packed, bool& tc_hidden, bool& out_tc,
+                        bool& w2_direct) {
   const int M = p.max_obj, mode = g_options[SHASTA_OPT_ANCHOR_PATH];
   tc_hidden = mode == 2 || (mode == 0 && B > kAnchorTcMinBatch);
-  // aug_shape.i.2 on tensor cores whatever kernel computed the hidden layer (TMA needs a 16-byte row pitch: 5M
-  // floats, M % 4 == 0); option 1 (streaming kernels only) keeps the CUDA-core finish kernel
-  out_tc = (M % 4) == 0 && mode != 1;
-  for (int i = 0; i < 4; ++i) out_tc = out_tc && (((uintptr_t)p.aug_shape_w2[i] & 15) == 0);
+  // aug_shape.i.2 on tensor cores whatever kernel computed the hidden layer. TMA needs 16-byte aligned rows: the
+  // parameters qualify when M % 4 == 0, otherwise the padded copies of the packed buffer are used (fused forward;
+  // the stage API has no packed buffer). Option 1 (streaming kernels only) keeps the CUDA-core finish kernel.
+  w2_direct = (M % 4) == 0;
+  for (int i = 0; i < 4; ++i) w2_direct = w2_direct && (((uintptr_t)p.aug_shape_w2[i] & 15) == 0);
+  out_tc = mode != 1 && (w2_direct || packed != nullptr);
 }
 
-bool anchor_boxes_independent(const shasta_params_t& p, int B) {
-  bool a, b;
-  anchor_plan(p, B, a, b);
+bool anchor_boxes_independent(const shasta_params_t& p, int B, const float* packed) {
+  bool a, b, c;
+  anchor_plan(p, B, packed, a, b, c);
   return b;
 }
 
@@ -345,15 +348,15 @@ int launch_anchor_hidden_bf16(const shasta_params_t& p, const void* w16, const v
 
 // w16 != NULL (bf16 mode): bf16 copies of the four aug_shape.i.0 matrices; FEATLO_* then hold bf16 copies of the features
 int launch_anchor_shapes(const shasta_params_t& p, int B, float* ws, const WsLayout& L, cudaStream_t s, cudaEvent_t mid,
-                         bool featlo_ready, int* S_out, const void* w16) {
+                         bool featlo_ready, int* S_out, const void* w16, const float* packed) {
   const int M = p.max_obj;
   const int N5 = 5 * M;
   float* feat_cur = ws + L.off[SHASTA_WS_FEAT_CUR];
   float* feat_prev = ws + L.off[SHASTA_WS_FEAT_PREV];
   float* part = ws + L.off[SHASTA_WS_HIDDEN_PART];
   const int mode = g_options[SHASTA_OPT_ANCHOR_PATH];
-  bool tc_hidden, out_tc;
-  anchor_plan(p, B, tc_hidden, out_tc);
+  bool tc_hidden, out_tc, w2_direct;
+  anchor_plan(p, B, packed, tc_hidden, out_tc, w2_direct);
   int S;
   if (tc_hidden && w16 != nullptr) {              // bf16 mode: half the weight bytes, plain bf16 UMMA
     S = anchor_bf16_splits(M, B);
@@ -386,7 +389,16 @@ int launch_anchor_shapes(const shasta_params_t& p, int B, float* ws, const WsLay
   }
   if (mid) cudaEventRecord(mid, s);
   if (out_tc) {
-    int rc = launch_anchor_out_tc(p, part, S, B, ws + L.off[SHASTA_WS_HID], ws + L.off[SHASTA_WS_HIDLO],
+    const float* w2[4];
+    int w2_ld = N5;
+    if (w2_direct) {
+      for (int i = 0; i < 4; ++i) w2[i] = p.aug_shape_w2[i];
+    } else {
+      const PackLayout P = pack_layout(M);
+      for (int i = 0; i < 4; ++i) w2[i] = packed + P.w2pad[i];
+      w2_ld = P.w2pad_ld;
+    }
+    int rc = launch_anchor_out_tc(p, w2, w2_ld, part, S, B, ws + L.off[SHASTA_WS_HID], ws + L.off[SHASTA_WS_HIDLO],
                                   ws + L.off[SHASTA_WS_OUT_PART], feat_cur, feat_prev, s);
     if (rc) return rc;
   }
@@ -398,14 +410,14 @@ int launch_anchor_shapes(const shasta_params_t& p, int B, float* ws, const WsLay
 // tensor cores, the aug_shape.i.2 roles 0-3 (those need the split-K partials: S). `light` = 128-thread CTAs with
 // the small shared-memory footprint, so that the launch can share the SMs with the anchors GEMM of another stream.
 int launch_anchor_boxes(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
-                        const WsLayout& L, int S, bool light, cudaStream_t s) {
+                        const WsLayout& L, int S, bool light, cudaStream_t s, const float* packed) {
   const int M = p.max_obj;
   const int N5 = 5 * M;
   float* feat_cur = ws + L.off[SHASTA_WS_FEAT_CUR];
   float* feat_prev = ws + L.off[SHASTA_WS_FEAT_PREV];
   float* part = ws + L.off[SHASTA_WS_HIDDEN_PART];
-  bool tc_hidden, out_tc;
-  anchor_plan(p, B, tc_hidden, out_tc);
+  bool tc_hidden, out_tc, w2_direct;
+  anchor_plan(p, B, packed, tc_hidden, out_tc, w2_direct);
   AnchorFinishArgs a;
   for (int i = 0; i < 4; ++i) {
     a.b0[i] = p.aug_shape_b0[i];
@@ -456,11 +468,12 @@ int launch_anchor_boxes(const shasta_params_t& p, const float* det_boxes, const 
 }
 
 int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
-                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid, bool featlo_ready, const void* w16) {
+                   const WsLayout& L, cudaStream_t s, cudaEvent_t mid, bool featlo_ready, const void* w16,
+                   const float* packed) {
   int S = 1;
-  int rc = launch_anchor_shapes(p, B, ws, L, s, mid, featlo_ready, &S, w16);
+  int rc = launch_anchor_shapes(p, B, ws, L, s, mid, featlo_ready, &S, w16, packed);
   if (rc) return rc;
-  return launch_anchor_boxes(p, det_boxes, prev_boxes, B, ws, L, S, false, s);
+  return launch_anchor_boxes(p, det_boxes, prev_boxes, B, ws, L, S, false, s, packed);
 }
 
 }  // namespace shasta

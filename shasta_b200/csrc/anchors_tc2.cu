@@ -512,8 +512,8 @@ int launch_anchor_hidden_tc2(const shasta_params_t& p, const float* feat_cur, co
 struct AnchorBias4 {
   const float* b[4];
 };
-__global__ void anchor_reduce_kernel(const float* __restrict__ part, int S, int B, int N5, int ldlo, AnchorBias4 bias,
-                                     float* __restrict__ hid, float* __restrict__ hidlo) {
+__global__ void anchor_reduce_kernel(const float* __restrict__ part, int S, int B, int N5, int ldh, int ldlo,
+                                     AnchorBias4 bias, float* __restrict__ hid, float* __restrict__ hidlo) {
   const size_t total = (size_t)4 * B * N5;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int n = (int)(idx % N5);
@@ -521,7 +521,7 @@ __global__ void anchor_reduce_kernel(const float* __restrict__ part, int S, int 
     float sum = 0.f;
     for (int sp = 0; sp < S; ++sp) sum += part[(((size_t)sp * B + b) * 4 + i) * N5 + n];   // fixed order
     const float h = fmaxf(sum + __ldg(bias.b[i] + n), 0.f);
-    hid[idx] = h;
+    hid[((size_t)i * B + b) * ldh + n] = h;   // fp32 rows padded to a multiple of 4 elements
     // bf16 rows are padded to a multiple of 8 elements (TMA wants a 16-byte row pitch)
     reinterpret_cast<__nv_bfloat16*>(hidlo)[((size_t)i * B + b) * ldlo + n] =
         __float2bfloat16_rn(h - __uint_as_float(__float_as_uint(h) & 0xffffe000u));
@@ -543,20 +543,23 @@ __global__ void anchor_out_finish_kernel(const float* __restrict__ part, int S, 
 }
 
 // aug_shape.i.2 + abs on tensor cores: the anchor rows of the augmented feature arrays
-int launch_anchor_out_tc(const shasta_params_t& p, const float* part, int S, int B, float* hid, float* hidlo,
-                         float* out_part, float* feat_cur, float* feat_prev, cudaStream_t s) {
+// w2 / w2_ld: the four (320, 5M) output-layer matrices and their row pitch (the parameters themselves when the pitch
+// is a multiple of 16 bytes, else the padded copies of the packed buffer)
+int launch_anchor_out_tc(const shasta_params_t& p, const float* const* w2, int w2_ld, const float* part, int S, int B,
+                         float* hid, float* hidlo, float* out_part, float* feat_cur, float* feat_prev, cudaStream_t s) {
   const int M = p.max_obj, N5 = 5 * M, T = M + 2;
+  const int ldh = (N5 + 3) / 4 * 4;
   AnchorBias4 b0;
   for (int i = 0; i < 4; ++i) b0.b[i] = p.aug_shape_b0[i];
   const int ldlo = (N5 + 7) / 8 * 8;
-  anchor_reduce_kernel<<<592, 256, 0, s>>>(part, S, B, N5, ldlo, b0, hid, hidlo);
+  anchor_reduce_kernel<<<592, 256, 0, s>>>(part, S, B, N5, ldh, ldlo, b0, hid, hidlo);
   SHASTA_CHECK_LAUNCH("anchor_reduce_kernel");
   const int bn = t2_bn(B);
   AnchorT2Maps maps;
   for (int i = 0; i < 4; ++i) {
-    int rc = make_map2(&maps.w[i], p.aug_shape_w2[i], (uint64_t)kF, (uint64_t)N5, (uint64_t)N5, 128);
+    int rc = make_map2(&maps.w[i], w2[i], (uint64_t)kF, (uint64_t)N5, (uint64_t)w2_ld, 128);
     if (rc) return rc;
-    rc = make_map2(&maps.x[i], hid + (size_t)i * B * N5, (uint64_t)B, (uint64_t)N5, (uint64_t)N5, (uint32_t)bn);
+    rc = make_map2(&maps.x[i], hid + (size_t)i * B * ldh, (uint64_t)B, (uint64_t)N5, (uint64_t)ldh, (uint32_t)bn);
     if (rc) return rc;
     rc = make_map2_bf16(&maps.xlo[i], reinterpret_cast<const __nv_bfloat16*>(hidlo) + (size_t)i * B * ldlo, (uint64_t)B,
                         (uint64_t)N5, (uint64_t)ldlo, (uint32_t)bn);

@@ -311,7 +311,7 @@ static int forward_impl(const shasta_params_t* host_params, const float* packed,
     if (rc) return rc;
   }
   STAGE_MARK(1);
-  SideStream* side = (ev == nullptr && !(flags & SHASTA_FLAG_NO_OVERLAP) && anchor_boxes_independent(*host_params, batch) &&
+  SideStream* side = (ev == nullptr && !(flags & SHASTA_FLAG_NO_OVERLAP) && anchor_boxes_independent(*host_params, batch, packed) &&
                       project_uses_tc(batch, M))
                          ? side_stream()
                          : nullptr;
@@ -321,9 +321,9 @@ static int forward_impl(const shasta_params_t* host_params, const float* packed,
     SHASTA_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
     // the GEMM is submitted FIRST: its one-CTA-per-SM grid takes its shared memory and registers, the light box
     // kernels then fit into what is left of every SM (the other order parks them first and the GEMM CTAs wait)
-    rc = launch_anchor_shapes(*host_params, batch, workspace, L, s, nullptr, featlo, nullptr, w16);  // a3
+    rc = launch_anchor_shapes(*host_params, batch, workspace, L, s, nullptr, featlo, nullptr, w16, packed);  // a3
     if (rc) return rc;
-    rc = launch_anchor_boxes(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, 1, true, side->stream);
+    rc = launch_anchor_boxes(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, 1, true, side->stream, packed);
     if (rc) return rc;
     rc = launch_project_aux(batch, M, workspace, L, det_boxes, side->stream);
     if (rc) return rc;
@@ -333,7 +333,7 @@ static int forward_impl(const shasta_params_t* host_params, const float* packed,
     if (rc) return rc;
   } else {
     rc = launch_anchors(*host_params, det_boxes, prev_det_boxes, batch, workspace, L, s, ev ? ev[2] : nullptr,
-                        featlo, w16);  // a3-a4
+                        featlo, w16, packed);  // a3-a4
     if (rc) return rc;
     STAGE_MARK(3);
     rc = launch_project(packed, batch, M, workspace, L, det_boxes, s);  // first layers, aux, colnorm, back-projection

@@ -60,7 +60,7 @@ __host__ inline WsLayout ws_layout(int B, int M) {
   sz[SHASTA_WS_FEATLO_CUR] = (size_t)B * M * kF;
   sz[SHASTA_WS_FEATLO_PREV] = (size_t)B * M * kF;
   sz[SHASTA_WS_COUNTERS] = 64;
-  sz[SHASTA_WS_HID] = (size_t)4 * B * 5 * M;
+  sz[SHASTA_WS_HID] = (size_t)4 * B * round_up(5 * M, 4);
   sz[SHASTA_WS_HIDLO] = (size_t)4 * B * 5 * M;
   sz[SHASTA_WS_OUT_PART] = (size_t)4 * B * 4 * kF;
   sz[SHASTA_WS_BOX_BWD] = (size_t)B * 4 * (16 + 2 * (size_t)((7 * M) / 32 + 1) + 7 * (size_t)M);
@@ -188,6 +188,10 @@ struct PackLayout {
   // first-layer projections on tensor cores (project_tc.cu): per side (0 prev, 1 cur) kProjTcPieces pieces of
   // kProjTcKs K rows, each [hi image | lo image] of the [320][112] projection matrix in the canonical layout
   size_t proj_tc[2];
+  // aug_shape.i.2.weight (320, 5M) copied to a row pitch of w2pad_ld = 5M rounded up to 4 floats: TMA wants a 16-byte
+  // pitch, the PyTorch parameter only has one when M % 4 == 0 (the shipped configs use M = 90, 50, 60, 20)
+  size_t w2pad[4];
+  int w2pad_ld;
   size_t total;       // floats
 };
 
@@ -244,6 +248,8 @@ __host__ inline PackLayout pack_layout(int M) {
   P.aff_tc_floats = aff_tc_plan(M).floats;
   P.aff_tc_begin = take(P.aff_tc_floats);
   for (int sd = 0; sd < 2; ++sd) P.proj_tc[sd] = take((size_t)2 * kF * kProjShape);
+  P.w2pad_ld = round_up(5 * M, 4);
+  for (int i = 0; i < 4; ++i) P.w2pad[i] = take((size_t)kF * P.w2pad_ld);
   P.total = o;
   return P;
 }
@@ -320,7 +326,7 @@ int launch_gather(const float* bev0, const float* boxes0, float* feat0, const fl
 // `featlo_ready`: the FEATLO_* regions already hold the tf32 low parts of FEAT_* (written by the fused gather)
 int launch_anchors(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
                    const WsLayout& L, cudaStream_t s, cudaEvent_t mid, bool featlo_ready = false,
-                   const void* w16 = nullptr);
+                   const void* w16 = nullptr, const float* packed = nullptr);
 int launch_project(const float* packed, int B, int M, float* ws, const WsLayout& L, float* det_boxes_inout,
                    cudaStream_t s);
 int launch_pairwise(const float* packed, int B, int M, float* ws, const WsLayout& L, int variant,
@@ -344,13 +350,14 @@ int launch_shared_conv_pack(const float* w, const float* bias, const float* gamm
                             const float* var, float eps, float* packed, cudaStream_t s);
 int launch_shared_conv(const float* packed, const float* x_nchw, int nmaps, int H, int W, float* scratch,
                        float* out_nhwc, cudaStream_t s);
-bool anchor_boxes_independent(const shasta_params_t& p, int B);   // the box part of the anchors stage needs no GEMM result
+// `packed` (optional): the packed-weight buffer; with it the tcgen05 output layer also serves M % 4 != 0 (padded copy)
+bool anchor_boxes_independent(const shasta_params_t& p, int B, const float* packed);   // box part needs no GEMM result
 int launch_anchor_shapes(const shasta_params_t& p, int B, float* ws, const WsLayout& L, cudaStream_t s, cudaEvent_t mid,
-                         bool featlo_ready, int* S_out, const void* w16 = nullptr);
+                         bool featlo_ready, int* S_out, const void* w16 = nullptr, const float* packed = nullptr);
 size_t anchor_bf16_elems(int M);
 int launch_pack_anchor_bf16(const shasta_params_t& p, void* w16, cudaStream_t s);
 int launch_anchor_boxes(const shasta_params_t& p, const float* det_boxes, const float* prev_boxes, int B, float* ws,
-                        const WsLayout& L, int S, bool light, cudaStream_t s);
+                        const WsLayout& L, int S, bool light, cudaStream_t s, const float* packed = nullptr);
 bool project_uses_tc(int B, int M);
 int launch_project_aux(int B, int M, float* ws, const WsLayout& L, float* det_boxes_inout, cudaStream_t s);
 int launch_project_gemm_tc(const float* packed, int B, int M, float* ws, const WsLayout& L, cudaStream_t s);

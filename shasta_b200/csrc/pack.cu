@@ -153,6 +153,12 @@ int launch_pack(const shasta_params_t& p, float* packed, cudaStream_t s) {
     aff_pieces_kernel<<<dim3(16, A.npieces), 256, 0, s>>>(packed + P.aff_tc_begin, A, src);
     SHASTA_CHECK_LAUNCH("aff_pieces_kernel");
   }
+  for (int i = 0; i < 4; ++i) {   // aug_shape.i.2.weight with a 16-byte row pitch
+    const long long n = (long long)kF * 5 * M;
+    copy_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(packed + P.w2pad[i], P.w2pad_ld, p.aug_shape_w2[i], 5 * M,
+                                                                 kF, 5 * M);
+    SHASTA_CHECK_LAUNCH("copy_rows_kernel");
+  }
   // tensor-core images of the two [320][112] first-layer projection matrices (built from the k-major copies above)
   umma_b_slice_kmajor_kernel<<<dim3((kProjShape * kProjTcKs + 255) / 256, kProjTcPieces, 2), 256, 0, s>>>(
       packed + P.proj_tc[0], packed + P.proj_tc[1], packed + P.p1_prev, packed + P.p1_cur, kProjShape, kProjShape,
