@@ -52,6 +52,8 @@ def parse():
                          "+ Adam on the differentiated parameters) instead of inference")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="independent batches in flight: N step graphs replayed round-robin on N streams (experiment)")
     ap.add_argument("--bf16", action="store_true", help="bf16 mode (shasta_forward_bf16): separate tolerance, dtype bf16")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -428,32 +430,56 @@ def main():
     inner = bool(os.environ.get("BENCH_INNER_GRAPH"))   # A/B knob: the model's per-call graph instead of the step graph
     model.cuda_graphs = inner and not a.no_graph
 
-    def step_body():
-        det.copy_(det0)  # fresh boxes every step (the forward back-projects det_boxes in place)
-        m1, m2 = model.affinity(bev, prev_bev, det, prev)
+    # lanes: independent batches in flight (--streams N): each lane has its own model instance (workspace), box buffer,
+    # step graph and stream; steps go to the lanes round-robin. The default is one lane on the current stream.
+    nl = max(1, a.streams) if not (a.no_graph or inner) else 1
+    lanes = []
+    for k in range(nl):
+        mk = model if k == 0 else build_model(a, pc_start, device)
+        mk.cuda_graphs = model.cuda_graphs
+        lanes.append({"model": mk, "det": det if k == 0 else det0.clone(),
+                      "dec": dec_one if k == 0 else (torch.empty_like(dec_one) if dec_one is not None else None),
+                      "stream": torch.cuda.current_stream() if k == 0 else torch.cuda.Stream(), "g": None, "out": None})
+
+    def lane_body(ln):
+        ln["det"].copy_(det0)  # fresh boxes every step (the forward back-projects det_boxes in place)
+        m1, m2 = ln["model"].affinity(bev, prev_bev, ln["det"], prev)
         if world > 1:
-            o = [dec_one[i].data_ptr() for i in range(6)]  # prev_state, prev_argmax, fn_score, det_state, ...
+            o = [ln["dec"][i].data_ptr() for i in range(6)]  # prev_state, prev_argmax, fn_score, det_state, ...
             rc = lib.shasta_decode_f32(m1.data_ptr(), m2.data_ptr(), n_prev.data_ptr(), n_det.data_ptr(), B, M,
                                        o[0], o[1], o[2], o[3], o[4], o[5],
                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
             _cabi.check(rc, "decode")
         return m1, m2
 
-    step_graph = {"g": None, "out": None}
+    def step_body():
+        return lane_body(lanes[0])
 
-    def step():
+    counter = [0]
+
+    def step(store=None):
+        ln = lanes[counter[0] % nl]
+        counter[0] += 1
         if a.no_graph or inner:
-            return step_body()
-        if step_graph["g"] is None:
-            for _ in range(2):   # eager runs first: one-time kernel attribute set-up must not happen inside a capture
-                step_body()
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                step_graph["out"] = step_body()
-            step_graph["g"] = g
-        step_graph["g"].replay()
-        return step_graph["out"]
+            out = lane_body(ln)
+        else:
+            if ln["g"] is None:
+                with torch.cuda.stream(ln["stream"]):
+                    for _ in range(2):   # eager runs first: one-time kernel attribute set-up must not be captured
+                        lane_body(ln)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ln["out"] = lane_body(ln)
+                ln["g"] = g
+            with torch.cuda.stream(ln["stream"]):
+                ln["g"].replay()
+                if store is not None:
+                    store.copy_(ln["dec"])   # this step's compact decode output
+            return ln["out"]
+        if store is not None:
+            store.copy_(ln["dec"])
+        return out
 
     def barrier():
         if dist is not None:
@@ -482,10 +508,12 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_begin = time.time()
         e0.record()
+        for ln in lanes[1:]:
+            ln["stream"].wait_event(e0)
         for it in range(a.steps):
-            m1, m2 = step()
-            if world > 1:
-                dec_pack[it].copy_(dec_one)   # this step's compact decode output
+            m1, m2 = step(dec_pack[it] if world > 1 else None)
+        for ln in lanes[1:]:
+            torch.cuda.current_stream().wait_stream(ln["stream"])
         if world > 1:  # NCCL only gathers the per-rank results
             gathered = sharding.gather_rank_blocks(dec_pack)  # (world, steps, 6, B, M) on every rank
             assert gathered.shape[0] == world
@@ -560,7 +588,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": n_warm, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16" if a.bf16 else "f32", "data": "synthetic", "impl": "b200",
-                "config": config_dict(a, {"flags": a.flags, "anchor_path": a.anchor_path, "cuda_graph": not a.no_graph}), "clocks": clocks, "roofline": roofline,
+                "config": config_dict(a, {"flags": a.flags, "anchor_path": a.anchor_path, "cuda_graph": not a.no_graph, "batches_in_flight": nl}), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * a.steps}
         print(json.dumps(line))
     if dist is not None:

@@ -34,22 +34,39 @@ cudaEvent_t* profile_slot() {
 // ---- side stream of the fused forward: the box half of the anchors stage and the AUX / column-norm kernel only
 // need the input boxes, so they run next to the (HBM-bound, one CTA per SM) anchors GEMM instead of after it -------
 struct SideStream {
+  cudaStream_t main = nullptr;   // the caller's stream this helper stream belongs to
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  bool used = false;
 };
-static SideStream g_side[64];
-static SideStream* side_stream() {
+// one helper stream (+ its two events) per (device, caller stream): forwards enqueued on different caller streams
+// must not share fork / join events
+constexpr int kSidePerDevice = 8;
+static SideStream g_side[64][kSidePerDevice];
+static SideStream* side_stream(cudaStream_t main) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  SideStream& ss = g_side[dev];
-  if (ss.stream == nullptr) {
-    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) {
-      ss = SideStream();
-      return nullptr;
-    }
+  SideStream* free_slot = nullptr;
+  for (int i = 0; i < kSidePerDevice; ++i) {
+    SideStream& ss = g_side[dev][i];
+    if (ss.used && ss.main == main) return &ss;
+    if (!ss.used && free_slot == nullptr) free_slot = &ss;
   }
+  if (free_slot == nullptr) {   // more caller streams than slots: hand the oldest slot over (round robin)
+    static int next[64] = {};
+    SideStream& ss = g_side[dev][next[dev]];
+    next[dev] = (next[dev] + 1) % kSidePerDevice;
+    ss.main = main;
+    return &ss;
+  }
+  SideStream& ss = *free_slot;
+  if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) {
+    ss = SideStream();
+    return nullptr;
+  }
+  ss.main = main, ss.used = true;
   return &ss;
 }
 
@@ -313,7 +330,7 @@ static int forward_impl(const shasta_params_t* host_params, const float* packed,
   STAGE_MARK(1);
   SideStream* side = (ev == nullptr && !(flags & SHASTA_FLAG_NO_OVERLAP) && anchor_boxes_independent(*host_params, batch, packed) &&
                       project_uses_tc(batch, M))
-                         ? side_stream()
+                         ? side_stream(s)
                          : nullptr;
   if (side != nullptr) {
     // fork: [box copy, aug_dets, AUX, column norms, back-projection] || [aug_shape GEMMs]; join before the projections
