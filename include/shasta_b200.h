@@ -145,7 +145,7 @@ enum shasta_region {
  *                           kind::tf32 ignores the low 13 mantissa bits (measured on B200: identical accuracy),
  *                           0 = write tf32-exact high parts back to shared memory first.
  *   (2, 3: kernel experiment knobs of bench.py: debug bits, forced split-K count.)
- *   SHASTA_OPT_AFF_PATH:    0 = auto (tcgen05 3xTF32 row tiles when max_obj + 2 <= 224, CUDA-core tiles otherwise),
+ *   SHASTA_OPT_AFF_PATH:    0 = auto (tcgen05 3xTF32 row tiles when max_obj + 2 <= 1024, CUDA-core tiles otherwise),
  *                           1 = always the CUDA-core kernel, 2 = always the tcgen05 kernel (error if unavailable).
  *   SHASTA_OPT_PROJECT_PATH: same values for the first-layer projection GEMM.
  *   SHASTA_OPT_HOST_GATHER_CTAS: CTAs per frame of the narrow gather used for host-resident maps (0 = default). */

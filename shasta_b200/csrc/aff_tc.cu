@@ -14,6 +14,12 @@
 //
 // TMEM columns: [0,256) A operand (layer 0: two 64-K chunks of hi|lo in flight; layers 1-5: hi [0,K) lo [K,2K)),
 // [256,512) accumulators (aff_tc_dcol).
+//
+// Two variants. STAGED (D <= kAffTcStagedD = 224): as above, row softmax fused into the tail. STREAMED (D up to 1024,
+// the 500 x 500 and 1000 x 1000 shapes): a 128-row tile no longer fits shared memory, so the workers read their rows
+// straight from global memory (L2: the pairwise kernel has just written them), the last layer runs in halves of <= 256
+// outputs whose accumulator the workers drain directly into the global logits, and the row softmax is a separate
+// warp-per-row kernel over the L2-resident logits.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -31,7 +37,10 @@ constexpr int kAtBarD = 9;                   // 6 accumulator-complete
 constexpr int kAtBarFull = 15;               // kAtSlots
 constexpr int kAtBarEmpty = 15 + kAtSlots;   // kAtSlots
 constexpr int kAtBarInput = 15 + 2 * kAtSlots;   // residual tile landed
-constexpr int kAtNumBars = 16 + 2 * kAtSlots;
+constexpr int kAtBarD5Empty = 16 + 2 * kAtSlots; // streamed variant: a last-layer half has been drained (128 arrivals)
+constexpr int kAtNumBars = 17 + 2 * kAtSlots;
+static_assert(kAtBarD5Empty == kAffTcBarD5Empty, "AffTcPlan refers to this barrier slot by number");
+static_assert(8 * kAtNumBars + 4 <= 256, "barrier block");
 
 __device__ __forceinline__ void at_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
@@ -68,6 +77,7 @@ __device__ __forceinline__ void at_split_store(uint32_t lane_base, int col_hi, i
   at_st16(lane_base + (uint32_t)col_lo, lo);
 }
 
+template <bool kStream>
 __global__ void __launch_bounds__(kAtThreads, 1)
 aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPlan plan, size_t tc_begin,
               size_t bias_off0, size_t bias_off1, size_t bias_off2, size_t bias_off3, size_t bias_off4,
@@ -81,13 +91,15 @@ aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPla
 
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  // [ring: kAtSlots x 16 KB][barriers + tmem slot: 256 B][bias: 6 x 256 floats][row tile: input rows, later logits]
+  // [ring: kAtSlots x 16 KB][barriers + tmem slot: 256 B][bias: 5 x 256 + kBias5 floats][staged: row tile: input rows,
+  // later logits]
+  constexpr int kBias5 = kStream ? kAffTcMaxD : 256;
   const uint32_t bars = base + kAtSlots * kAtSlotBytes;
   auto bar = [&](int i) { return bars + 8u * i; };
   const uint32_t tmem_slot = bars + 8u * kAtNumBars;
   float* bias_s = reinterpret_cast<float*>(gbase + kAtSlots * kAtSlotBytes + 256);
-  float* stage = bias_s + 6 * 256;                  // input rows [128][RS], later the logits [128][SS]
-  const uint32_t stage_u32 = base + kAtSlots * kAtSlotBytes + 256 + 6 * 256 * 4;
+  float* stage = bias_s + 5 * 256 + kBias5;         // input rows [128][RS], later the logits [128][SS]
+  const uint32_t stage_u32 = base + kAtSlots * kAtSlotBytes + 256 + (5 * 256 + kBias5) * 4;
   const int SS = plan.np5 + 1;                      // staging row stride (odd: conflict-free column writes)
 
   if (threadIdx.x == 0) {
@@ -97,6 +109,7 @@ aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPla
     for (int l = 0; l < 6; ++l) mbar_init(bar(kAtBarD + l), 1);
     for (int i = 0; i < kAtSlots; ++i) mbar_init(bar(kAtBarFull + i), 1), mbar_init(bar(kAtBarEmpty + i), 1);
     mbar_init(bar(kAtBarInput), 1);
+    mbar_init(bar(kAtBarD5Empty), 128);
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc(tmem_slot, 512);
@@ -104,7 +117,8 @@ aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPla
     const size_t boff[6] = {bias_off0, bias_off1, bias_off2, bias_off3, bias_off4, bias_off5};
     const int bn[6] = {128, 64, 32, 64, 128, D};
     for (int l = 0; l < 6; ++l)
-      for (int j = threadIdx.x; j < 256; j += kAtThreads) bias_s[l * 256 + j] = (j < bn[l]) ? __ldg(packed + boff[l] + j) : 0.f;
+      for (int j = threadIdx.x; j < (l == 5 ? kBias5 : 256); j += kAtThreads)
+        bias_s[l * 256 + j] = (j < bn[l]) ? __ldg(packed + boff[l] + j) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -114,7 +128,7 @@ aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPla
   if (warp == 5) {
     // ===================== weight loader =====================
     if (elect_one()) {
-      {  // the tile's residual rows are one contiguous block of (rows in tile) x RS floats
+      if (!kStream) {  // the tile's residual rows are one contiguous block of (rows in tile) x RS floats
         const uint32_t rows = (uint32_t)min((long long)128, nrows - row0);
         const uint32_t bytes = rows * (uint32_t)RS * 4u;
         mbar_expect_tx(bar(kAtBarInput), bytes);
@@ -167,24 +181,42 @@ aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPla
     const long long row = row0 + r;
     const bool live = row < nrows;
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    const float* src = stage + (size_t)r * RS;
-    mbar_wait(bar(kAtBarInput), 0);
+    const float* src = kStream ? residual + (size_t)(live ? row : 0) * RS : stage + (size_t)r * RS;
+    if (!kStream) mbar_wait(bar(kAtBarInput), 0);
 
     // ---- layer 0 operand: the residual row in chunks of 64 K through the two-slot TMEM ring
     for (int c = 0; c < plan.nchunk0; ++c) {
       const int slot = c & 1;
+      const int kbeg = c * 64, kend = min(kbeg + 64, plan.kp0);
+      // streamed: the chunk's 16 global loads are in flight while the thread waits for the TMEM slot; staged: the rows
+      // sit in shared memory and are read 16 values at a time.
+      // rows are RS floats long (RS = D rounded up to 4, pad columns are never written: treat them as 0)
+      float4 xs[kStream ? 16 : 1];
+      if constexpr (kStream) {
+#pragma unroll
+        for (int v = 0; v < 16; ++v) {
+          const int k = kbeg + 4 * v;
+          xs[v] = (live && k < RS && k < kend) ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       if (c >= 2) {
         mbar_wait(bar(kAtBarA0Empty + slot), (uint32_t)((c >> 1) - 1) & 1u);
         tc_fence_after();
       }
-      const int kbeg = c * 64, kend = min(kbeg + 64, plan.kp0);
-      for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+      for (int kk = 0; kk < 64; kk += 16) {
+        const int k0 = kbeg + kk;
+        if (k0 >= kend) break;
         float h[16];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const int k = k0 + 4 * v;
-          // rows are RS floats long (RS = D rounded up to 4, pad columns are never written: treat them as 0)
-          const float4 x = (live && k < RS) ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 x;
+          if constexpr (kStream) {
+            x = xs[kk / 4 + v];
+          } else {
+            x = (live && k < RS) ? *reinterpret_cast<const float4*>(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           h[4 * v + 0] = (k + 0 < D) ? x.x : 0.f;
           h[4 * v + 1] = (k + 1 < D) ? x.y : 0.f;
           h[4 * v + 2] = (k + 2 < D) ? x.z : 0.f;
@@ -219,10 +251,44 @@ aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPla
       mbar_arrive(bar(2 + l));   // a_ready of layer l + 1
     }
 
-    // ---- layer 5: logits -> shared-memory staging (the weight ring is idle: every MMA has retired)
-    mbar_wait(bar(kAtBarD + 5), 0);
-    tc_fence_after();
-    {
+    if (kStream) {
+      // ---- layer 5, streamed: every half's accumulator goes straight to the global logits (64-byte runs per thread)
+      float* dst = logits + (size_t)(live ? row : 0) * RS;
+      for (int hf = 0; hf < plan.nhalf5; ++hf) {
+        mbar_wait(bar(kAtBarD + 5), (uint32_t)hf & 1u);
+        tc_fence_after();
+        const int n0 = hf * 256, nn = min(256, plan.np5 - n0);
+        const float* bl = bias_s + 5 * 256 + n0;
+        for (int c0 = 0; c0 < nn; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(lane_base + (uint32_t)(aff_tc_dcol(5) + c0), v);
+          tmem_ld_wait();
+          if (live) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int c = n0 + c0 + 4 * q4;
+              float4 o;
+              o.x = __uint_as_float(v[4 * q4 + 0]) + bl[c0 + 4 * q4 + 0];
+              o.y = __uint_as_float(v[4 * q4 + 1]) + bl[c0 + 4 * q4 + 1];
+              o.z = __uint_as_float(v[4 * q4 + 2]) + bl[c0 + 4 * q4 + 2];
+              o.w = __uint_as_float(v[4 * q4 + 3]) + bl[c0 + 4 * q4 + 3];
+              if (c + 3 < D) {
+                *reinterpret_cast<float4*>(dst + c) = o;
+              } else {
+                if (c + 0 < D) dst[c + 0] = o.x;
+                if (c + 1 < D) dst[c + 1] = o.y;
+                if (c + 2 < D) dst[c + 2] = o.z;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar(kAtBarD5Empty));
+      }
+    } else {
+      // ---- layer 5: logits -> shared-memory staging (the weight ring is idle: every MMA has retired)
+      mbar_wait(bar(kAtBarD + 5), 0);
+      tc_fence_after();
       const float* bl = bias_s + 5 * 256;
       for (int c0 = 0; c0 < plan.np5; c0 += 16) {
         uint32_t v[16];
@@ -239,11 +305,12 @@ aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPla
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+  if (kStream) return;   // row softmax: row_softmax_kernel
 
   // ---- logits to global (coalesced along d) and the row softmax for rows t < M -> matched1 (B,M,M+2).
   // A warp owns rows warp, warp+16, ... and works on kTR of them at a time (independent dependency chains: the tail
   // is latency bound); D <= 224 means at most 7 columns per lane.
-  constexpr int kTR = 4, kTC = (kAffTcMaxD + 31) / 32;
+  constexpr int kTR = 4, kTC = (kAffTcStagedD + 31) / 32;
   for (int rb = warp; rb < 128; rb += (kAtThreads / 32) * kTR) {
     float v[kTR][kTC], mx[kTR], sum[kTR];
 #pragma unroll
@@ -294,6 +361,39 @@ aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPla
   }
 }
 
+// matched1[b][t][:] = softmax over d of logits[b][t][:], t < M: one warp per row, the row stays in registers (D <= 1024).
+__global__ void __launch_bounds__(256)
+row_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __restrict__ matched1) {
+  constexpr int kC = kAffTcMaxD / 32;
+  const int T = M + 2, D = M + 2, RS = row_stride(M);
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);   // over B * M
+  if (r >= (long long)B * M) return;
+  const int b = (int)(r / M), t = (int)(r % M);
+  const float* src = logits + ((size_t)b * T + t) * RS;
+  float v[kC], mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < kC; ++c) {
+    const int d = lane + 32 * c;
+    v[c] = (d < D) ? src[d] : -INFINITY;
+    mx = fmaxf(mx, v[c]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < kC; ++c) {
+    v[c] = (lane + 32 * c < D) ? expf(v[c] - mx) : 0.f;
+    sum += v[c];
+  }
+  sum = warp_sum(sum);
+  float* dst = matched1 + (size_t)r * D;
+#pragma unroll
+  for (int c = 0; c < kC; ++c) {
+    const int d = lane + 32 * c;
+    if (d < D) dst[d] = __fdiv_rn(v[c], sum);
+  }
+}
+
 bool aff_tc_available(int M) { return M + 2 <= kAffTcMaxD; }
 
 int launch_aff_tc(const float* packed, int B, int M, const float* residual, float* logits, float* matched1,
@@ -304,16 +404,31 @@ int launch_aff_tc(const float* packed, int B, int M, const float* residual, floa
     set_error("tensor-core aff kernel needs max_obj + 2 <= %d (got max_obj %d)", kAffTcMaxD, M);
     return SHASTA_ERR_UNSUPPORTED;
   }
+  const long long nrows = (long long)B * (M + 2);
+  const unsigned grid = (unsigned)((nrows + 127) / 128);
+  if (M + 2 > kAffTcStagedD) {
+    const size_t smem = 128 + (size_t)kAtSlots * kAtSlotBytes + 256 + (5 * 256 + kAffTcMaxD) * sizeof(float);
+    static OncePerDevice configured;
+    if (configured.first()) {
+      SHASTA_CUDA(cudaFuncSetAttribute(aff_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    aff_tc_kernel<true><<<grid, kAtThreads, smem, s>>>(packed, plan, P.aff_tc_begin, P.aff_b[0], P.aff_b[1], P.aff_b[2],
+                                                      P.aff_b[3], P.aff_b[4], P.aff_b[5], B, M, residual, logits,
+                                                      matched1);
+    SHASTA_CHECK_LAUNCH("aff_tc_kernel<streamed>");
+    row_softmax_kernel<<<(unsigned)(((long long)B * M + 7) / 8), 256, 0, s>>>(B, M, logits, matched1);
+    SHASTA_CHECK_LAUNCH("row_softmax_kernel");
+    return 0;
+  }
   const size_t tile = 128 * (size_t)((plan.np5 + 1 > row_stride(M)) ? plan.np5 + 1 : row_stride(M)) * sizeof(float);
   const size_t smem = 128 + (size_t)kAtSlots * kAtSlotBytes + 256 + 6 * 256 * sizeof(float) + tile;
   static MaxPerDevice configured;
   if (configured.raise(smem)) {
-    SHASTA_CUDA(cudaFuncSetAttribute(aff_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SHASTA_CUDA(cudaFuncSetAttribute(aff_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  const long long nrows = (long long)B * (M + 2);
-  aff_tc_kernel<<<(unsigned)((nrows + 127) / 128), kAtThreads, smem, s>>>(
-      packed, plan, P.aff_tc_begin, P.aff_b[0], P.aff_b[1], P.aff_b[2], P.aff_b[3], P.aff_b[4], P.aff_b[5], B, M,
-      residual, logits, matched1);
+  aff_tc_kernel<false><<<grid, kAtThreads, smem, s>>>(packed, plan, P.aff_tc_begin, P.aff_b[0], P.aff_b[1], P.aff_b[2],
+                                                     P.aff_b[3], P.aff_b[4], P.aff_b[5], B, M, residual, logits,
+                                                     matched1);
   SHASTA_CHECK_LAUNCH("aff_tc_kernel");
   return 0;
 }

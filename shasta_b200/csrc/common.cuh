@@ -78,9 +78,11 @@ __host__ inline WsLayout ws_layout(int B, int M) {
 // tf32 hi/lo parts), weights stream through a shared-memory ring as "pieces": a K slice [k0, k0+ks) of one layer in
 // the canonical K-major UMMA layout [ks/4][N][4] (hi image, then the lo image). Layer 0 (K = D) is cut into chunks
 // of 64 K so that its A operand fits a 2 x 128-column TMEM ring.
-constexpr int kAffTcMaxPieces = 64;
+constexpr int kAffTcMaxPieces = 160;
 constexpr int kAffTcSlotFloats = 4096;   // 16 KB ring slot
-constexpr int kAffTcMaxD = 224;          // row tile + weight ring must fit 227 KB of shared memory
+constexpr int kAffTcStagedD = 224;       // up to here the row tile + weight ring fit 227 KB of shared memory (staged variant)
+constexpr int kAffTcMaxD = 1024;         // streamed variant: rows read from global, last layer in halves of <= 256 outputs
+constexpr int kAffTcBarD5Empty = 28;     // barrier slot (aff_tc.cu): accumulator of a last-layer half drained
 struct AffTcPiece {
   uint32_t off;       // float offset from PackLayout::aff_tc_begin
   uint16_t n;         // UMMA N (outputs padded to a multiple of 16)
@@ -89,15 +91,16 @@ struct AffTcPiece {
   uint16_t a_lo;      // column distance from the hi to the lo part
   uint16_t d_col;     // accumulator column
   uint8_t layer;
-  uint8_t first;      // first piece of its layer: the first MMA overwrites the accumulator
+  uint8_t first;      // first piece of its layer (or last-layer half): the first MMA overwrites the accumulator
   int8_t wait_a;      // barrier slot (AffTcBars) to wait on before this piece, -1 = none
   uint8_t wait_parity;
   int8_t commit_a;    // layer-0 A ring slot (0/1) released after this piece, -1 = none
-  uint8_t commit_d;   // 1: the layer's accumulator is complete after this piece
+  uint8_t commit_d;   // 1: the layer's (half's) accumulator is complete after this piece
   uint16_t k0, src_k, src_n;  // packing: K offset in the layer, valid K and N of the layer's weight (n_valid x k_valid)
+  uint16_t n0;        // packing: first output of the piece (last-layer halves)
 };
 struct AffTcPlan {
-  int npieces, nchunk0, kp0, np5;
+  int npieces, nchunk0, kp0, np5, nhalf5;
   size_t floats;
   AffTcPiece p[kAffTcMaxPieces];
 };
@@ -107,6 +110,7 @@ __host__ inline AffTcPlan aff_tc_plan(int M) {
   A.npieces = 0, A.floats = 0;
   const int D = M + 2;
   A.kp0 = round_up(D, 8), A.np5 = round_up(D, 16), A.nchunk0 = (A.kp0 + 63) / 64;
+  A.nhalf5 = (D > kAffTcStagedD) ? (A.np5 + 255) / 256 : 1;
   if (D > kAffTcMaxD) {
     A.nchunk0 = 0;
     return A;
@@ -117,15 +121,18 @@ __host__ inline AffTcPlan aff_tc_plan(int M) {
   const int nv[6] = {128, 64, 32, 64, 128, D};
   size_t off = 0;
   for (int l = 0; l < 6; ++l) {
-    int ks_max = (kAffTcSlotFloats / 2 / N[l]) / 8 * 8;
-    const int nseg = (l == 0) ? A.nchunk0 : 1;
+    // segments: layer 0 = K chunks of 64 (A operand ring), layer 5 = halves of <= 256 outputs, else one
+    const int nseg = (l == 0) ? A.nchunk0 : (l == 5) ? A.nhalf5 : 1;
     for (int sg = 0; sg < nseg; ++sg) {
+      const int n0 = (l == 5) ? sg * 256 : 0;
+      const int nn = (l == 5 && A.nhalf5 > 1) ? ((N[5] - n0 < 256) ? N[5] - n0 : 256) : N[l];
+      const int ks_max = (kAffTcSlotFloats / 2 / nn) / 8 * 8;
       const int kbeg = (l == 0) ? sg * 64 : 0;
       const int kend = (l == 0) ? ((kbeg + 64 < K[0]) ? kbeg + 64 : K[0]) : K[l];
       for (int k0 = kbeg; k0 < kend; k0 += ks_max) {
         AffTcPiece& q = A.p[A.npieces++];
         q.off = (uint32_t)off;
-        q.n = (uint16_t)N[l];
+        q.n = (uint16_t)nn;
         q.ks = (uint16_t)((kend - k0 < ks_max) ? kend - k0 : ks_max);
         q.layer = (uint8_t)l;
         q.first = (k0 == 0);
@@ -136,6 +143,8 @@ __host__ inline AffTcPlan aff_tc_plan(int M) {
         if (k0 == kbeg) {   // first piece of a segment: its A operand must have been written
           if (l == 0)
             q.wait_a = (int8_t)(sg & 1), q.wait_parity = (uint8_t)((sg >> 1) & 1);
+          else if (l == 5 && sg > 0)   // the workers must have drained the previous half's accumulator
+            q.wait_a = (int8_t)kAffTcBarD5Empty, q.wait_parity = (uint8_t)((sg - 1) & 1);
           else
             q.wait_a = (int8_t)(1 + l);   // a_ready[l] lives in slot 1 + l (slots 0,1 = layer-0 ring)
         }
@@ -143,8 +152,8 @@ __host__ inline AffTcPlan aff_tc_plan(int M) {
           if (l == 0) q.commit_a = (int8_t)(sg & 1);
           if (kend == K[l]) q.commit_d = 1;
         }
-        q.k0 = (uint16_t)k0, q.src_k = (uint16_t)kv[l], q.src_n = (uint16_t)nv[l];
-        off += 2 * (size_t)q.ks * N[l];
+        q.k0 = (uint16_t)k0, q.src_k = (uint16_t)kv[l], q.src_n = (uint16_t)nv[l], q.n0 = (uint16_t)n0;
+        off += 2 * (size_t)q.ks * nn;
       }
     }
   }
@@ -183,7 +192,7 @@ struct PackLayout {
   size_t tc16_begin;  // bf16 block (counted in floats): w2a (6x32x8 bf16), w2b (10x32x8), w2c (4x16x8)
   size_t tc16_w2a, tc16_w2b, tc16_w2c;
   size_t tc16_end;
-  // aff on tensor cores (aff_tc.cu; only when D = M+2 <= kAffTcMaxD): weight pieces of AffTcPlan, each [hi image | lo image]
+  // aff on tensor cores (aff_tc.cu; when D = M+2 <= kAffTcMaxD): weight pieces of AffTcPlan, each [hi image | lo image]
   size_t aff_tc_begin, aff_tc_floats;   // aff_tc_floats == 0 when the tensor-core aff kernel is unavailable for this M
   // first-layer projections on tensor cores (project_tc.cu): per side (0 prev, 1 cur) kProjTcPieces pieces of
   // kProjTcKs K rows, each [hi image | lo image] of the [320][112] projection matrix in the canonical layout

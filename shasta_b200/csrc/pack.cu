@@ -61,7 +61,7 @@ __global__ void aff_pieces_kernel(float* __restrict__ base, const __grid_constan
   const int ld = src.ld[q.layer];
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_pad * kc; idx += gridDim.x * blockDim.x) {
     const int n = idx / kc, kk = idx % kc, k = q.k0 + kk;
-    const float v = (n < q.src_n && k < q.src_k) ? w[(size_t)n * ld + k] : 0.f;
+    const float v = (q.n0 + n < q.src_n && k < q.src_k) ? w[(size_t)(q.n0 + n) * ld + k] : 0.f;
     const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     const size_t o = (size_t)(kk / 4) * (n_pad * 4) + n * 4 + (kk % 4);
     img[o] = h;

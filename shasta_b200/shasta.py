@@ -388,12 +388,13 @@ class Shasta(nn.Module):
                 _cabi.check(rc, "shasta_shared_conv_f32")
         return out
 
-    def decode(self, matched1, matched2, n_prev, n_det):
+    def decode(self, matched1, matched2, n_prev, n_det, out=None):
         """The thresholded argmax of the eval loop (tools/nusc_shasta/eval.py:126-181) for a whole batch on the device:
         returns int32/float32 CUDA tensors of shape (B, M): ``prev_state`` (0 keep, 1 dead, 2 FN, -1 padding),
         ``prev_argmax``, ``fn_score`` (1 - matched[n,-2] for FN rows), ``det_state`` (0 keep, 1 newborn, 2 dropped FP,
         -1 padding), ``det_argmax``, ``det_score`` (ref_detection_score). ``n_prev`` / ``n_det``: real counts per
-        frame pair (sequence or int32 tensor)."""
+        frame pair (sequence or int32 tensor). ``out``: optional contiguous (6, B, M) int32 CUDA tensor the six fields
+        are written into in the order above (float fields bit-cast); the returned dict then holds views of it."""
         if not matched1.is_cuda or not matched2.is_cuda:
             raise _cabi.ShastaLibraryError("decode needs CUDA tensors: shasta_b200 has no CPU path")
         dev = matched1.device
@@ -401,8 +402,15 @@ class Shasta(nn.Module):
         m1, m2 = matched1.contiguous(), matched2.contiguous()
         npv = torch.as_tensor(n_prev, dtype=torch.int32).to(dev)
         ndv = torch.as_tensor(n_det, dtype=torch.int32).to(dev)
-        out = {k: torch.empty((B, M), dtype=(torch.float32 if k.endswith("score") else torch.int32), device=dev)
-               for k in ("prev_state", "prev_argmax", "fn_score", "det_state", "det_argmax", "det_score")}
+        fields = ("prev_state", "prev_argmax", "fn_score", "det_state", "det_argmax", "det_score")
+        if out is None:
+            out = {k: torch.empty((B, M), dtype=(torch.float32 if k.endswith("score") else torch.int32), device=dev)
+                   for k in fields}
+        else:
+            if (tuple(out.shape) != (6, B, M) or out.dtype != torch.int32 or out.device != dev
+                    or not out.is_contiguous()):
+                raise ValueError("decode: out must be a contiguous (6, %d, %d) int32 tensor on %s" % (B, M, dev))
+            out = {k: (out[i].view(torch.float32) if k.endswith("score") else out[i]) for i, k in enumerate(fields)}
         with torch.cuda.device(dev):
             rc = _cabi.lib().shasta_decode_f32(
                 m1.data_ptr(), m2.data_ptr(), npv.data_ptr(), ndv.data_ptr(), B, M, out["prev_state"].data_ptr(),

@@ -1,0 +1,103 @@
+"""BASELINE.json configs[2] as a parity case: several class models (different max_obj, own weights) over a batch of
+scenes, ragged batches, decode blocks gathered into scene order - every frame pair of every class against the CPU
+oracle (O.forward + O.decode): the discrete decisions must be identical, the scores within 1e-4. The same workload
+served from a resident ring with step graphs must reproduce the eager result bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import shasta_oracle as O
+from shasta_b200 import multiclass, synthetic
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+CLASSES = (("bus", 20), ("tiny", 6), ("bicycle", 50))
+HW = 24
+
+
+def _lanes(step_graphs):
+    pc_start = (-HW * 0.3, -HW * 0.3)
+    lanes, weights = [], {}
+    for i, (name, M) in enumerate(CLASSES):
+        weights[name] = synthetic.make_weights(M, seed=10 + i, peaky=600.0)
+        lanes.append(multiclass.ClassLane(name, G.make_model(M, pc_start, weights[name]), step_graphs=step_graphs))
+    return lanes, weights, pc_start
+
+
+def _oracle_states(m1, m2, n_prev, n_det, M):
+    d = O.decode(m1, m2, n_prev, n_det)
+    prev_state = np.full(M, -1, np.int32)
+    prev_state[:n_prev] = [1 if n in d["dead"] else 2 if n in d["fn"] else 0 for n in range(n_prev)]
+    fn_score = np.zeros(M, np.float32)
+    for n, s in zip(d["fn"], d["fn_score"]):
+        fn_score[n] = s
+    det_state = np.full(M, -1, np.int32)
+    det_state[:n_det] = 2
+    det_score = np.zeros(M, np.float32)
+    for k, nb, s in zip(d["keep_dets"], d["newborn"], d["det_score"]):
+        det_state[k] = 1 if nb else 0
+        det_score[k] = s
+    return prev_state, fn_score, det_state, det_score
+
+
+def test_three_class_sequence_batch_matches_oracle():
+    lengths = [3, 2, 4]
+    lanes, weights, pc_start = _lanes(step_graphs=False)
+    prov = multiclass.SyntheticProvider(CLASSES, lengths, HW, G.DEV, seed=5)
+    res = multiclass.run_sequence_batch(lanes, lengths, prov, {"bus": 4, "tiny": 9, "bicycle": 2})
+    decisions = 0
+    for name, M in CLASSES:
+        wt = O.weights_to_torch(weights[name])
+        bx = prov.boxes[name]
+        assert len(res[name]) == len(lengths)
+        for s, n in enumerate(lengths):
+            got = multiclass.decode_fields(res[name][s].cpu())
+            assert tuple(res[name][s].shape) == (n, 6, M)
+            for f in range(n):
+                i = prov.pair_index(s, f)
+                maps = prov.maps[name]
+                m1, m2 = O.forward(wt, maps[i + s + 1:i + s + 2].cpu(), maps[i + s:i + s + 1].cpu(),
+                                   bx["det_boxes"][i:i + 1].cpu().clone(), bx["prev_det_boxes"][i:i + 1].cpu(),
+                                   pc_start=pc_start)
+                n_prev, n_det = int(bx["n_prev"][i]), int(bx["n_det"][i])
+                ps, fs, ds, sc = _oracle_states(m1[0], m2[0], n_prev, n_det, M)
+                assert np.array_equal(got["prev_state"][f].numpy()[:n_prev], ps[:n_prev]), (name, s, f)
+                assert np.array_equal(got["det_state"][f].numpy()[:n_det], ds[:n_det]), (name, s, f)
+                fn_rows = ps[:n_prev] == 2
+                assert np.allclose(got["fn_score"][f].numpy()[:n_prev][fn_rows], fs[:n_prev][fn_rows], atol=1e-4)
+                kept = ds[:n_det] != 2
+                assert np.allclose(got["det_score"][f].numpy()[:n_det][kept], sc[:n_det][kept], atol=1e-4)
+                decisions += int((ps[:n_prev] > 0).sum() + (ds[:n_det] > 0).sum())
+    assert decisions > 0, "weights not peaky enough: no dead / FN / newborn / FP decision was exercised"
+
+
+def test_ring_with_step_graphs_equals_eager():
+    lengths = [5, 3, 6]          # 14 frame pairs: batches of 4 -> 4, 4, 4, 2; ring of 2 -> slots reused, graphs replayed
+    out = []
+    for graphs in (False, True):
+        lanes, _, _ = _lanes(step_graphs=graphs)
+        prov = multiclass.SyntheticProvider(CLASSES, lengths, HW, G.DEV, seed=7, ring=2, batch_pairs=4)
+        out.append(multiclass.run_sequence_batch(lanes, lengths, prov, 4))
+        if graphs:
+            assert all(len(l._graphs) == 3 for l in lanes)      # (slot 0, B=4), (slot 1, B=4), (slot 1, B=2)
+    for name, _ in CLASSES:
+        for a, b in zip(out[0][name], out[1][name]):
+            assert torch.equal(a, b)
+    # the ring serves the same batch again: rows 0-3 and 8-11 of the rank's stream are identical
+    flat = torch.cat(out[1]["bus"], dim=0)
+    assert torch.equal(flat[0:4], flat[8:12]) and not torch.equal(flat[0:4], flat[4:8])
+
+
+def test_decode_out_argument_checks_shape():
+    lanes, _, _ = _lanes(step_graphs=False)
+    model = lanes[0].model
+    m1 = torch.rand((2, 20, 22), device=G.DEV)
+    m2 = torch.rand((2, 22, 20), device=G.DEV)
+    with pytest.raises(ValueError):
+        model.decode(m1, m2, [3, 4], [5, 6], out=torch.empty((6, 2, 21), dtype=torch.int32, device=G.DEV))
+    blk = torch.empty((6, 2, 20), dtype=torch.int32, device=G.DEV)
+    a = model.decode(m1, m2, [3, 4], [5, 6], out=blk)
+    b = model.decode(m1, m2, [3, 4], [5, 6])
+    assert all(torch.equal(a[k], b[k]) for k in b)
+    assert a["prev_state"].data_ptr() == blk.data_ptr()

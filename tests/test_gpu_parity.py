@@ -275,13 +275,20 @@ def aff_path(request):
     lib.shasta_set_option(_cabi.OPT_AFF_PATH, 0)
 
 
-@pytest.mark.parametrize("M,B", [(200, 7), (222, 2), (90, 3), (20, 9), (6, 1)])
+@pytest.mark.parametrize("M,B", [(200, 7), (222, 2), (90, 3), (20, 9), (6, 1), (223, 2), (300, 3), (500, 1), (1000, 1)])
 def test_aff_paths_agree(M, B):
     """tcgen05 3xTF32 row tiles vs the CUDA-core kernel on random residuals: partial last tile, K and N padding at
-    D = 202 / 224 / 92 / 22 / 8."""
+    D = 202 / 224 / 92 / 22 / 8 (staged variant) and D = 225 (one last-layer half of 240), 302 (halves 256 + 48),
+    502 (256 + 256), 1002 (256 x 3 + 240; 16 K chunks) for the streamed variant."""
     lib = _cabi.lib()
     T = M + 2
-    model = G.make_model(M, (-4.8, -4.8), synthetic.make_weights(M, seed=3, peaky=50.0))
+    if M <= 222:
+        model = G.make_model(M, (-4.8, -4.8), synthetic.make_weights(M, seed=3, peaky=50.0))
+    else:   # the big aug_shape matrices make numpy-generated weights impractical: default init on the device
+        torch.manual_seed(3)
+        model = G.make_model(M, (-4.8, -4.8))
+        with torch.no_grad():
+            model.aff[10].weight.mul_(50.0)
     st = G.Stages(model, B)
     gen = torch.Generator(device="cpu").manual_seed(5)
     res = (torch.randn((B, T, T), generator=gen) * 4.0).to(G.DEV)
@@ -299,9 +306,14 @@ def test_aff_paths_agree(M, B):
     scale = np.abs(out[1][0]).max()
     err = np.abs(out[1][0] - out[2][0]).max() / scale
     print("aff tcgen05 vs CUDA cores: logits max err / scale = %.3g" % err)
-    assert err < 1e-5
+    # two fp32 evaluations with different summation orders: the gap grows with the K = D of the first layer
+    # (1.2e-5 measured at D = 1002)
+    assert err < (1e-5 if M <= 222 else 3e-5)
     assert G.rel_err(out[2][1], out[1][1]) < FP32_REL_TOL
     assert G.rel_err(out[2][2], out[1][2]) < FP32_REL_TOL
+    if M > 222:
+        del st, model
+        torch.cuda.empty_cache()
 
 
 @pytest.mark.parametrize("name", golden_names())
