@@ -185,3 +185,62 @@ class SyntheticProvider:
         return {"bev": self.maps[1:B + 1], "prev_bev": self.maps[0:B], "det_boxes": bx["det_boxes"][lo:lo + B],
                 "prev_det_boxes": bx["prev_det_boxes"][lo:lo + B], "n_prev": bx["n_prev"][lo:lo + B],
                 "n_det": bx["n_det"][lo:lo + B]}
+
+
+class DetectionFileProvider:
+    """Serves ``run_sequence_batch`` from a binary detection file (detfile.py): scene s / frame pair f = frame
+    ``scenes[s].first + f`` of the file, packed per class with that class's ``det_type`` filter and ``max_obj``.
+    ``maps_for(name, frame_indices)`` returns the two (B,H,W,64) CUDA maps (current, previous) of those frames - in the
+    reference they come from the frozen trunk + that class model's shared_conv."""
+
+    def __init__(self, det_file, class_det_type, class_max_obj, maps_for, device, seed=0):
+        self.df, self.det_type, self.max_obj = det_file, dict(class_det_type), dict(class_max_obj)
+        self.maps_for, self.device, self.seed = maps_for, device, seed
+        self.scenes = det_file.scenes()
+        self.scene_lengths = [n for _, n in self.scenes]
+
+    def frame_of(self, scene, frame):
+        return self.scenes[scene][0] + frame
+
+    def rng_for(self, i):
+        import random
+        return random.Random(self.seed * 1000003 + i)
+
+    def pack(self, name, frame_indices):
+        return self.df.frame_pair_batch(frame_indices, self.max_obj[name], self.det_type[name], rng_for=self.rng_for)
+
+    def __call__(self, name, items):
+        idx = [self.frame_of(s, f) for s, f in items]
+        b = self.pack(name, idx)
+        bev, prev_bev = self.maps_for(name, idx)
+        t = lambda a: torch.from_numpy(a).to(self.device, non_blocking=True)  # noqa: E731
+        return {"bev": bev, "prev_bev": prev_bev, "det_boxes": t(b["det_boxes"]), "prev_det_boxes": t(b["prev_det_boxes"]),
+                "n_prev": t(b["n_prev"]), "n_det": t(b["n_det"])}
+
+    def annotations(self, name, per_scene_blocks):
+        """Gathered decode blocks of one class (``run_sequence_batch(...)[name]``) -> ``{token: annos}`` like the
+        reference's eval loop emits (tools/nusc_shasta/eval.py:126-181, incl. the ``dead`` post-pass)."""
+        from . import formats
+        df = self.df
+        results, dead_tracker = {}, {}
+        for s, (first, n) in enumerate(self.scenes):
+            fields = decode_fields(per_scene_blocks[s].cpu())
+            packed = self.pack(name, list(range(first, first + n)))
+            for f in range(n):
+                i = first + f
+                token = df.tokens[i]
+                p = int(df.prev_index[i])
+                prev_token = "" if p < 0 else df.tokens[p]
+                dead_tracker.setdefault(token, {"dead_idx": [], "keep_idx": []})
+                prev_cls = df.cls_info(packed["prev_rows"][f], prev_token)
+                cur_cls = df.cls_info(packed["rows"][f], token)
+                time_lag = float(packed["prev_det_boxes"][f, 0, 9])
+                annos, dead_idx, keep = formats.annos_from_decode(
+                    prev_cls, cur_cls, fields["prev_state"][f].numpy(), fields["fn_score"][f].numpy(),
+                    fields["det_state"][f].numpy(), fields["det_score"][f].numpy(), token, time_lag)
+                if len(prev_cls) > 0:
+                    dead_tracker.setdefault(prev_token, {"dead_idx": [], "keep_idx": []})["dead_idx"].extend(dead_idx)
+                if len(cur_cls) > 0:
+                    dead_tracker[token]["keep_idx"] = keep
+                results[token] = annos
+        return formats.mark_dead(results, dead_tracker)

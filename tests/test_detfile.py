@@ -1,0 +1,96 @@
+"""The binary detection batch file (shasta_b200/detfile.py) against the JSON path it replaces:
+``formats.frame_pair_example`` on the per-frame detection lists (itself pinned to the reference's dataset code by
+tests/test_formats.py). Packed arrays, counts and keep indices must be identical bit for bit, incl. the class filter,
+empty frames, scene starts and the seeded sub-sampling of over-full frames."""
+import copy
+import random
+
+import numpy as np
+import pytest
+
+from shasta_b200 import detfile, formats
+
+CLASSES = ["car", "truck", "pedestrian"]
+
+
+def _frames(seed, n_scenes=3, n_frames=5, max_dets=14):
+    rng = np.random.default_rng(seed)
+    frames = []
+    for s in range(n_scenes):
+        for f in range(n_frames):
+            n = 0 if (s == 1 and f == 2) else int(rng.integers(1, max_dets))
+            dets, cls = [], []
+            for _ in range(n):
+                q = rng.normal(size=4)
+                if rng.random() < 0.5:
+                    q /= np.linalg.norm(q)          # both normalised and raw quaternions
+                box = (list(rng.uniform(-50, 50, 3)) + list(rng.uniform(0.5, 5, 3)) + list(q) + list(rng.normal(0, 3, 2)))
+                dets.append([float(x) for x in box])
+                info = {"sample_token": "s%d_f%d" % (s, f), "translation": dets[-1][0:3], "size": dets[-1][3:6],
+                        "rotation": dets[-1][6:10], "velocity": dets[-1][10:12],
+                        "detection_name": CLASSES[int(rng.integers(0, 3))], "detection_score": float(rng.uniform(0.05, 1))}
+                if rng.random() < 0.6:
+                    info["attribute_name"] = ["vehicle.moving", "vehicle.parked", "pedestrian.standing"][int(rng.integers(0, 3))]
+                cls.append(info)
+            ts = 1_600_000_000_000_000 + (s * 100 + f) * 500_000 + int(rng.integers(0, 2000))
+            frames.append({"token": "s%d_f%d" % (s, f), "prev_token": "" if f == 0 else "s%d_f%d" % (s, f - 1),
+                           "timestamp": ts, "prev_timestamp": ts if f == 0 else frames[-1]["timestamp"],
+                           "dets": dets, "cls": cls})
+    return frames
+
+
+@pytest.mark.parametrize("det_type,M", [(None, 20), (["car"], 20), (["car", "pedestrian"], 4), (["bus"], 6), (None, 3)])
+def test_batch_equals_json_path(tmp_path, det_type, M):
+    frames = _frames(11)
+    path = str(tmp_path / "dets.shdb")
+    detfile.write_detection_file(path, frames)
+    df = detfile.DetectionFile(path)
+    assert df.n_frames == len(frames) and df.tokens == [f["token"] for f in frames]
+    by_token = {f["token"]: f for f in frames}
+    order = list(range(len(frames)))
+    batch = df.frame_pair_batch(order, M, det_type, rng=random.Random(5))
+    ref_rng = random.Random(5)
+    sampled = 0
+    for j, i in enumerate(order):
+        f = frames[i]
+        prev = by_token.get(f["prev_token"]) if f["prev_token"] else None
+        dt = 1e-6 * f["timestamp"] - 1e-6 * f["prev_timestamp"]
+        ex = formats.frame_pair_example(None if prev is None else copy.deepcopy(prev["dets"]),
+                                        None if prev is None else copy.deepcopy(prev["cls"]), copy.deepcopy(f["dets"]),
+                                        copy.deepcopy(f["cls"]), M, dt, det_type, rng=ref_rng)
+        assert np.array_equal(batch["det_boxes"][j].view(np.uint32), ex["det_boxes"][0].view(np.uint32)), f["token"]
+        assert np.array_equal(batch["prev_det_boxes"][j].view(np.uint32), ex["prev_det_boxes"][0].view(np.uint32))
+        assert int(batch["n_det"][j]) == ex["num_det_boxes"] and int(batch["n_prev"][j]) == ex["num_prev_det_boxes"]
+        assert batch["keep"][j] == ex["keep"] and batch["prev_keep"][j] == ex["prev_keep"]
+        got = df.cls_info(batch["rows"][j], f["token"])
+        assert got == ex["cls_det_boxes"]
+        sampled += len(f["dets"]) > M
+    if M <= 4:
+        assert sampled > 0, "the case was meant to exercise the seeded sub-sampling"
+
+
+def test_round_trip_and_errors(tmp_path):
+    frames = _frames(3, n_scenes=2, n_frames=3)
+    path = str(tmp_path / "a.shdb")
+    detfile.write_detection_file(path, frames)
+    df = detfile.DetectionFile(path)
+    assert df.frames() == frames
+    assert df.frame_index("s1_f2") == 5 and int(df.prev_index[3]) == -1 and int(df.prev_index[4]) == 3
+    bad = tmp_path / "bad.shdb"
+    bad.write_bytes(b"NOTSHDB0" + b"\0" * 64)
+    with pytest.raises(ValueError):
+        detfile.DetectionFile(str(bad))
+    data = open(path, "rb").read()
+    cut = tmp_path / "cut.shdb"
+    cut.write_bytes(data[:len(data) // 2])
+    with pytest.raises(ValueError):
+        detfile.DetectionFile(str(cut))
+
+
+def test_empty_file(tmp_path):
+    path = str(tmp_path / "e.shdb")
+    detfile.write_detection_file(path, [])
+    df = detfile.DetectionFile(path)
+    assert df.n_frames == 0 and df.rows.shape == (0, 14)
+    b = df.frame_pair_batch([], 5)
+    assert b["det_boxes"].shape == (0, 5, 11)

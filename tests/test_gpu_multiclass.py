@@ -101,3 +101,68 @@ def test_decode_out_argument_checks_shape():
     b = model.decode(m1, m2, [3, 4], [5, 6])
     assert all(torch.equal(a[k], b[k]) for k in b)
     assert a["prev_state"].data_ptr() == blk.data_ptr()
+
+
+def test_detection_file_provider_matches_json_loop(tmp_path):
+    """Binary detection file -> DetectionFileProvider -> batched, per-class lanes -> annotations, against the
+    reference-shaped JSON loop (pipeline.run_class_sequence, batch size 1, itself checked against the CPU oracle in
+    tests/test_gpu_pipeline.py): same surviving detections, flags and scores for every token of every class."""
+    import copy
+
+    from shasta_b200 import detfile, pipeline
+    from tests.test_gpu_pipeline import _scene
+
+    M, H, W = 20, 32, 32
+    pc_start = (-W * 0.3, -H * 0.3)
+    rng = np.random.default_rng(2)
+    frames = []
+    for s, nfr in enumerate((5, 3, 6)):
+        for f in _scene(20 + s, nfr, M, extent=8.0):
+            f["token"] = "s%d_%s" % (s, f["token"])
+            f["prev_token"] = "" if f["prev_token"] == "" else "s%d_%s" % (s, f["prev_token"])
+            f["timestamp"] += s * 10_000_000
+            f["prev_timestamp"] += s * 10_000_000
+            for c in f["cls"]:
+                c["sample_token"] = f["token"]
+                if rng.random() < 0.35:
+                    c["detection_name"] = "truck"
+            frames.append(f)
+    path = str(tmp_path / "dets.shdb")
+    detfile.write_detection_file(path, frames)
+    df = detfile.DetectionFile(path)
+
+    g = torch.Generator().manual_seed(9)
+    cur_maps = torch.relu(torch.randn((len(frames), H, W, 64), generator=g)).to(G.DEV)
+    first_prev = torch.relu(torch.randn((H, W, 64), generator=g)).to(G.DEV)
+
+    def prev_map(i):
+        p = int(df.prev_index[i])
+        return first_prev if p < 0 else cur_maps[p]
+
+    def maps_for(name, idx):
+        return cur_maps[idx].contiguous(), torch.stack([prev_map(i) for i in idx])
+
+    classes = {"car": ["car"], "truck": ["truck"]}
+    lanes, models = [], {}
+    for k, name in enumerate(classes):
+        models[name] = G.make_model(M, pc_start, synthetic.make_weights(M, seed=30 + k, peaky=500.0))
+        lanes.append(multiclass.ClassLane(name, models[name]))
+    prov = multiclass.DetectionFileProvider(df, classes, {n: M for n in classes}, maps_for, G.DEV)
+    assert prov.scene_lengths == [5, 3, 6]
+    blocks = multiclass.run_sequence_batch(lanes, prov.scene_lengths, prov, 4)
+
+    flags = 0
+    for name, det_type in classes.items():
+        got = prov.annotations(name, blocks[name])
+        want = pipeline.run_class_sequence(
+            models[name], copy.deepcopy(frames),
+            lambda tok: (cur_maps[df.frame_index(tok)][None], prev_map(df.frame_index(tok))[None]), det_type=det_type)
+        assert set(got) == set(want)
+        for tok in want:
+            assert len(got[tok]) == len(want[tok]), (name, tok)
+            for x, y in zip(got[tok], want[tok]):
+                assert x["translation"] == y["translation"] and x["detection_name"] == y["detection_name"]
+                assert x.get("newborn") == y.get("newborn") and x.get("dead") == y.get("dead") and x.get("FN") == y.get("FN")
+                assert abs(x["ref_detection_score"] - y["ref_detection_score"]) < 1e-6
+                flags += bool(x.get("newborn")) + bool(x.get("dead")) + bool(x.get("FN"))
+    assert flags > 0
