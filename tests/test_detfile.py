@@ -94,3 +94,33 @@ def test_empty_file(tmp_path):
     assert df.n_frames == 0 and df.rows.shape == (0, 14)
     b = df.frame_pair_batch([], 5)
     assert b["det_boxes"].shape == (0, 5, 11)
+
+
+def test_provider_packing_is_independent_of_batching(tmp_path):
+    """Over-full frames are sub-sampled with a per-frame-pair generator: the choice must not depend on which other
+    frame pairs share the batch (ranks and batch sizes differ between runs of the same job)."""
+    from shasta_b200 import multiclass
+    frames = _frames(17, n_scenes=2, n_frames=4)
+    path = str(tmp_path / "d.shdb")
+    detfile.write_detection_file(path, frames)
+    df = detfile.DetectionFile(path)
+    prov = multiclass.DetectionFileProvider(df, {"all": None}, {"all": 3}, maps_for=None, device="cpu", seed=4)
+    assert prov.scene_lengths == [4, 4] and prov.frame_of(1, 2) == 6
+    whole = prov.pack("all", list(range(8)))
+    assert (whole["n_det"] == 3).any()
+    for i in range(8):
+        one = prov.pack("all", [i])
+        assert np.array_equal(one["det_boxes"][0], whole["det_boxes"][i])
+        assert np.array_equal(one["prev_det_boxes"][0], whole["prev_det_boxes"][i])
+        assert one["keep"][0] == whole["keep"][i] and one["prev_keep"][0] == whole["prev_keep"][i]
+    other = multiclass.DetectionFileProvider(df, {"all": None}, {"all": 3}, maps_for=None, device="cpu", seed=5)
+    assert any(other.pack("all", [i])["keep"][0] != whole["keep"][i] for i in range(8))
+
+
+def test_scenes_rejects_out_of_order_frames(tmp_path):
+    frames = _frames(2, n_scenes=1, n_frames=3)
+    frames[1], frames[2] = frames[2], frames[1]
+    path = str(tmp_path / "o.shdb")
+    detfile.write_detection_file(path, frames)
+    with pytest.raises(ValueError):
+        detfile.DetectionFile(path).scenes()
