@@ -77,8 +77,9 @@ __device__ __forceinline__ void at_split_store(uint32_t lane_base, int col_hi, i
   at_st16(lane_base + (uint32_t)col_lo, lo);
 }
 
+constexpr int kAtStreamThreads = 192;   // streamed variant: no softmax tail, so only the workers, the issuer and the loader
 template <bool kStream>
-__global__ void __launch_bounds__(kAtThreads, 1)
+__global__ void __launch_bounds__(kStream ? kAtStreamThreads : kAtThreads, 1)
 aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPlan plan, size_t tc_begin,
               size_t bias_off0, size_t bias_off1, size_t bias_off2, size_t bias_off3, size_t bias_off4,
               size_t bias_off5, int B, int M, const float* __restrict__ residual, float* __restrict__ logits,
@@ -117,7 +118,7 @@ aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPla
     const size_t boff[6] = {bias_off0, bias_off1, bias_off2, bias_off3, bias_off4, bias_off5};
     const int bn[6] = {128, 64, 32, 64, 128, D};
     for (int l = 0; l < 6; ++l)
-      for (int j = threadIdx.x; j < (l == 5 ? kBias5 : 256); j += kAtThreads)
+      for (int j = threadIdx.x; j < (l == 5 ? kBias5 : 256); j += blockDim.x)
         bias_s[l * 256 + j] = (j < bn[l]) ? __ldg(packed + boff[l] + j) : 0.f;
   }
   tc_fence_before();
@@ -412,7 +413,7 @@ int launch_aff_tc(const float* packed, int B, int M, const float* residual, floa
     if (configured.first()) {
       SHASTA_CUDA(cudaFuncSetAttribute(aff_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    aff_tc_kernel<true><<<grid, kAtThreads, smem, s>>>(packed, plan, P.aff_tc_begin, P.aff_b[0], P.aff_b[1], P.aff_b[2],
+    aff_tc_kernel<true><<<grid, kAtStreamThreads, smem, s>>>(packed, plan, P.aff_tc_begin, P.aff_b[0], P.aff_b[1], P.aff_b[2],
                                                       P.aff_b[3], P.aff_b[4], P.aff_b[5], B, M, residual, logits,
                                                       matched1);
     SHASTA_CHECK_LAUNCH("aff_tc_kernel<streamed>");
