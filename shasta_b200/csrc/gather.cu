@@ -128,7 +128,8 @@ __device__ __forceinline__ void box_point_pixels(const float* __restrict__ bx, i
 }
 
 // ------------------------------------------------------------------------------------------------
-// Variant 0: half-warp per point, direct vector loads.
+// Variant 2 (host-resident maps, narrow persistent grid) and the first generation of variant 0: half-warp per point,
+// direct vector loads, every lane recomputes the point.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
 constexpr int kPointsPerCta0 = kGatherThreads / 16;
@@ -162,6 +163,56 @@ gather_ldg_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, 
   if (job.featlo[f] != nullptr)
     reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(job.featlo[f]) + ((size_t)b * M + m) * kF + p * kC)[lane16] =
         job.lo_mode ? bf16x4(v) : tf32_lo4(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Variant 0 (default, device-resident maps): the same half-warp-per-point loads, but the per-point arithmetic
+// (sin / cos of the yaw, corner mid-points, the two divisions, tap indices and weights) is done ONCE per point by one
+// thread and shared through shared memory. The ncu capture of the kernel above showed the 16-fold redundant point
+// arithmetic, not memory, as its limiter (issue slots 66 % active at 2.6 TB/s of DRAM traffic); here a half-warp
+// walks 8 points with the loads of 4 of them in flight.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPointsPerCta3 = 128;
+
+__global__ void __launch_bounds__(kGatherThreads)
+gather_pts_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, size_t feat_batch_stride) {
+  __shared__ Taps s_t[kPointsPerCta3];
+  __shared__ long long s_src[kPointsPerCta3];   // float4 offset of the point's map in the batch of maps
+  __shared__ long long s_dst[kPointsPerCta3];   // float offset of the point's 64 output channels
+  const int f = blockIdx.y;
+  const float* __restrict__ bev = job.bev[f];
+  const float* __restrict__ boxes = job.boxes[f];
+  float* __restrict__ feat = job.feat[f];
+  const long long total = (long long)B * M * 5;
+  const long long gp0 = (long long)blockIdx.x * kPointsPerCta3;
+  const int npts = (int)min((long long)kPointsPerCta3, total - gp0);
+  if (threadIdx.x < npts) {
+    const long long gp = gp0 + threadIdx.x;
+    const int bm = (int)(gp / 5), p = (int)(gp % 5);
+    const int b = bm / M, m = bm % M;
+    float xs, ys;
+    box_point_pixels(boxes + (size_t)bm * box_stride, p, g, xs, ys);
+    s_t[threadIdx.x] = make_taps(xs, ys, g.height, g.width);
+    s_src[threadIdx.x] = (long long)b * g.height * g.width * (kC / 4);
+    s_dst[threadIdx.x] = (long long)((size_t)b * feat_batch_stride + (size_t)m * kF + p * kC);
+  }
+  __syncthreads();
+  const int lane16 = threadIdx.x & 15;
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(job.featlo[f]);
+  const int lo_mode = job.lo_mode;
+#pragma unroll 4
+  for (int i = threadIdx.x >> 4; i < npts; i += kGatherThreads / 16) {
+    const Taps t = s_t[i];
+    const float4* base = reinterpret_cast<const float4*>(bev) + s_src[i] + lane16;
+    const float4 a = __ldg(base + (t.y0 * g.width + t.x0) * (kC / 4));
+    const float4 bb = __ldg(base + (t.y1 * g.width + t.x0) * (kC / 4));
+    const float4 c = __ldg(base + (t.y0 * g.width + t.x1) * (kC / 4));
+    const float4 d = __ldg(base + (t.y1 * g.width + t.x1) * (kC / 4));
+    const float4 v = blend4(a, bb, c, d, t);
+    reinterpret_cast<float4*>(feat + s_dst[i])[lane16] = v;
+    // (B, M, 320) bf16 companion: row-major over (b, m, p) = the point index itself
+    if (lo != nullptr) reinterpret_cast<uint2*>(lo + (size_t)(gp0 + i) * kC)[lane16] = lo_mode ? bf16x4(v) : tf32_lo4(v);
   }
 }
 
@@ -288,9 +339,9 @@ int launch_gather(const float* bev0, const float* boxes0, float* feat0, const fl
     gather_bulk_kernel<<<grid, kGatherThreads, 0, s>>>(job, box_stride, B, M, g, feat_batch_stride);
     SHASTA_CHECK_LAUNCH("gather_bulk_kernel");
   } else {
-    dim3 grid((unsigned)((total + kPointsPerCta0 - 1) / kPointsPerCta0), nframes);
-    gather_ldg_kernel<<<grid, kGatherThreads, 0, s>>>(job, box_stride, B, M, g, feat_batch_stride);
-    SHASTA_CHECK_LAUNCH("gather_ldg_kernel");
+    dim3 grid((unsigned)((total + kPointsPerCta3 - 1) / kPointsPerCta3), nframes);
+    gather_pts_kernel<<<grid, kGatherThreads, 0, s>>>(job, box_stride, B, M, g, feat_batch_stride);
+    SHASTA_CHECK_LAUNCH("gather_pts_kernel");
   }
   return 0;
 }
