@@ -227,3 +227,25 @@ class DetectionFile:
                         "dets": [self.rows[r, 0:12].tolist() for r in range(b, b + n)],
                         "cls": self.cls_info(range(b, b + n), token)})
         return res
+
+
+def frames_from_json_dirs(det_path, cls_info_path, frame_info, tokens):
+    """The reference's on-disk layout (nuscenes.py:198-217, 255-262): ``<det_path>/<token>.json`` = list of 12-float
+    boxes, ``<cls_info_path>/<token>.json`` = list of detection dicts, ``frame_info[token] = {prev, timestamp,
+    prev_timestamp}``. ``tokens``: the frames to convert, scene by scene in time order; a ``prev`` outside ``tokens``
+    counts as a scene start (the reference's ``get_frame_idx(prev_token) is None`` case). Returns the frame list
+    ``write_detection_file`` takes."""
+    import json
+    import os
+    known = set(tokens)
+    frames = []
+    for token in tokens:
+        with open(os.path.join(det_path, token + ".json")) as fh:
+            dets = json.load(fh)
+        with open(os.path.join(cls_info_path, token + ".json")) as fh:
+            cls = json.load(fh)
+        info = frame_info[token]
+        prev = info["prev"] if info["prev"] in known else ""
+        frames.append({"token": token, "prev_token": prev, "timestamp": info["timestamp"],
+                       "prev_timestamp": info["prev_timestamp"], "dets": dets, "cls": cls})
+    return frames

@@ -196,3 +196,15 @@ def mark_dead(results, dead_tracker):
             if i in keep_idx:
                 results[token][keep_idx.index(i)]['dead'] = True
     return results
+
+
+def write_results(path, results):
+    """tools/nusc_shasta/eval.py:184-193: the ``cp_<split>.json`` the downstream tracker reads - ``results`` is
+    ``{token: annos}`` (``annos_from_decode`` + ``mark_dead``), ``meta`` the fixed lidar-only modality block."""
+    import json
+    nusc_annos = {"results": results,
+                  "meta": {"use_camera": False, "use_lidar": True, "use_radar": False, "use_map": False,
+                           "use_external": False}}
+    with open(path, "w") as f:
+        json.dump(nusc_annos, f)
+    return nusc_annos

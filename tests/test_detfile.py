@@ -124,3 +124,31 @@ def test_scenes_rejects_out_of_order_frames(tmp_path):
     detfile.write_detection_file(path, frames)
     with pytest.raises(ValueError):
         detfile.DetectionFile(path).scenes()
+
+
+def test_json_dirs_to_file_and_results_json(tmp_path):
+    """The reference's on-disk layout (per-token detection + cls_info JSON, frame_info dict) -> one detection file;
+    and the cp_<split>.json writer."""
+    import json
+    frames = _frames(23, n_scenes=2, n_frames=3)
+    det_dir, cls_dir = tmp_path / "det", tmp_path / "cls"
+    det_dir.mkdir(), cls_dir.mkdir()
+    frame_info = {}
+    for f in frames:
+        (det_dir / (f["token"] + ".json")).write_text(json.dumps(f["dets"]))
+        (cls_dir / (f["token"] + ".json")).write_text(json.dumps(f["cls"]))
+        frame_info[f["token"]] = {"prev": f["prev_token"] or "outside_the_split", "timestamp": f["timestamp"],
+                                  "prev_timestamp": f["prev_timestamp"]}
+    got = detfile.frames_from_json_dirs(str(det_dir), str(cls_dir), frame_info, [f["token"] for f in frames])
+    assert got == frames                       # JSON floats round-trip exactly; an unknown prev = scene start
+    path = str(tmp_path / "all.shdb")
+    detfile.write_detection_file(path, got)
+    assert detfile.DetectionFile(path).frames() == frames
+
+    results = {f["token"]: f["cls"] for f in frames}
+    out = tmp_path / "cp_val.json"
+    formats.write_results(str(out), results)
+    back = json.loads(out.read_text())
+    assert back["results"] == results
+    assert back["meta"] == {"use_camera": False, "use_lidar": True, "use_radar": False, "use_map": False,
+                            "use_external": False}
