@@ -90,3 +90,12 @@ def test_class_table_matches_the_shipped_configs():
                                                    "bicycle": 50, "motorcycle": 50}
     assert len(multiclass.NUSC_CLASS_MAX_OBJ) + len(multiclass.SYNTHETIC_CLASS_MAX_OBJ) == 10
     assert max(m for _, m in multiclass.SYNTHETIC_CLASS_MAX_OBJ) == 500
+
+
+def test_rank_without_scenes_contributes_an_empty_block():
+    """More ranks than scenes: the idle rank runs no batch and hands back a zero-row block (gather=False view)."""
+    lanes = [_StubLane("car", 5, 1)]
+    res = multiclass.run_sequence_batch(lanes, [2, 3], _provider, 4, world_size=3, rank=2, gather=False)
+    assert lanes[0].batch_sizes == [] and tuple(res["car"].shape) == (6, 0, 5)
+    res = multiclass.run_sequence_batch(lanes, [2, 3], _provider, 4, world_size=3, rank=1, gather=False)
+    assert lanes[0].batch_sizes == [3] and tuple(res["car"].shape) == (6, 3, 5)
