@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--streams", type=int, default=1,
                     help="independent batches in flight: N step graphs replayed round-robin on N streams (experiment)")
     ap.add_argument("--bf16", action="store_true", help="bf16 mode (shasta_forward_bf16): separate tolerance, dtype bf16")
+    ap.add_argument("--opt", action="append", default=[], metavar="ID=VALUE",
+                    help="shasta_set_option(ID, VALUE) before the run (experiment knob, repeatable)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -413,6 +415,9 @@ def main():
     lib.shasta_set_option(_cabi.OPT_TC_RAW_HI, a.raw_hi)
     lib.shasta_set_option(2, a.dbg)
     lib.shasta_set_option(3, a.splits)
+    for kv in a.opt:
+        k, v = kv.split("=")
+        _cabi.check(lib.shasta_set_option(int(k, 0), int(v, 0)), "shasta_set_option")
     pc_start, d, bev, prev_bev = make_inputs(a, device, seed=1000 + rank)
     model = build_model(a, pc_start, device)
     det0 = torch.from_numpy(d["det_boxes"]).to(device)

@@ -134,7 +134,9 @@ enum shasta_region {
   SHASTA_WS_HID = 24,        /* (4,B,5M) hidden activations of aug_shape.i (operand of the tcgen05 output GEMM) */
   SHASTA_WS_HIDLO = 25,      /* their tf32 low parts */
   SHASTA_WS_OUT_PART = 26,   /* (4,B,4,320) split-K partial sums of the tcgen05 aug_shape.i.2 GEMM */
-  SHASTA_WS_NUM_REGIONS = 27
+  SHASTA_WS_CURX = 27,       /* (B*T + 16, 68) per current object: second-layer accumulator seeds W2.q + b2 (52), AUX (8),
+                                column norm (1) - the per-column operands of the tcgen05 pairwise kernel */
+  SHASTA_WS_NUM_REGIONS = 28
 };
 
 /* Runtime options (process-wide, not thread-safe; meant for tests and benchmarks).
@@ -148,14 +150,17 @@ enum shasta_region {
  *   SHASTA_OPT_AFF_PATH:    0 = auto (tcgen05 3xTF32 row tiles when max_obj + 2 <= 1024, CUDA-core tiles otherwise),
  *                           1 = always the CUDA-core kernel, 2 = always the tcgen05 kernel (error if unavailable).
  *   SHASTA_OPT_PROJECT_PATH: same values for the first-layer projection GEMM.
- *   SHASTA_OPT_HOST_GATHER_CTAS: CTAs per frame of the narrow gather used for host-resident maps (0 = default). */
+ *   SHASTA_OPT_HOST_GATHER_CTAS: CTAs per frame of the narrow gather used for host-resident maps (0 = default).
+ *   SHASTA_OPT_PAIR_FFMA2:  0 / 1 = packed FFMA2 in the third-layer epilogue of the pipelined pairwise kernel (default),
+ *                           2 = scalar FFMA (comparison). */
 enum shasta_option {
   SHASTA_OPT_ANCHOR_PATH = 0,
   SHASTA_OPT_TC_RAW_HI = 1,
   SHASTA_OPT_AFF_PATH = 4,
   SHASTA_OPT_PROJECT_PATH = 5,
   SHASTA_OPT_HOST_GATHER_CTAS = 6,
-  SHASTA_OPT_COUNT = 7
+  SHASTA_OPT_PAIR_FFMA2 = 7,
+  SHASTA_OPT_COUNT = 8
 };
 SHASTA_API int shasta_set_option(int option, int value);
 SHASTA_API int shasta_get_option(int option);

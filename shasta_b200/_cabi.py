@@ -65,6 +65,8 @@ OPT_ANCHOR_PATH = 0
 OPT_TC_RAW_HI = 1
 OPT_AFF_PATH = 4      # 0 auto, 1 CUDA cores, 2 tcgen05
 OPT_PROJECT_PATH = 5  # same values
+OPT_HOST_GATHER_CTAS = 6
+OPT_PAIR_FFMA2 = 7    # 2 = scalar FFMA in the pairwise epilogue (comparison)
 ANCHOR_AUTO, ANCHOR_STREAM, ANCHOR_TC, ANCHOR_TC_GEN1 = 0, 1, 2, 3
 
 # every symbol include/shasta_b200.h declares: name -> (restype, argtypes)

@@ -9,7 +9,7 @@ namespace shasta {
 static thread_local char g_error[512] = "";
 thread_local int g_launch_count = 0;
 static thread_local int g_last_forward_launches = 0;
-int g_options[SHASTA_OPT_COUNT] = {0, 1, 0, 0, 0, 0, 0};  // anchor path auto, raw-hi on
+int g_options[SHASTA_OPT_COUNT] = {0, 1, 0, 0, 0, 0, 0, 0};  // anchor path auto, raw-hi on
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -14,6 +14,15 @@ constexpr int kProj = SHASTA_PROJ;  // 144
 constexpr int kProjShape = 112;     // first-layer outputs that read the 320-wide shape feature (40 + 72)
 constexpr int kNF = 3;
 
+// ---- third / fourth pairwise layers as the FFMA2 epilogue of pairwise_tc3.cu reads them (float offsets in the block)
+//   w3a  [10 jp][10 m][2]  fuse_shape.4.W[m][2jp + i]        b3a [12]   w4a [12]   b4a [4]
+//   w3b  [9 jp][4 n][2]    res_coeff.4.W[n][2jp + i] (n < 3) b3b [4]
+//   w3c  [8]               fuse_det.4.W[0][j]                b3c [4]
+constexpr int kEp3W3a = 0, kEp3B3a = 200, kEp3W4a = 212, kEp3B4a = 224, kEp3W3b = 228, kEp3B3b = 300, kEp3W3c = 304,
+              kEp3B3c = 312, kPairEp3Floats = 316;
+constexpr int kPairCxStride = 68;   // floats per current object of the CURX region: [0,52) cinit, [52,60) aux, [60] colnorm
+
+
 // ---- anchors split-K geometry ------------------------------------------------------------------
 constexpr int kAnchorKRange = 2048;   // floats of K one CTA of the hidden kernel covers
 constexpr int kAnchorKChunk = 1024;   // floats of K staged in shared memory at a time
@@ -64,6 +73,7 @@ __host__ inline WsLayout ws_layout(int B, int M) {
   sz[SHASTA_WS_HIDLO] = (size_t)4 * B * 5 * M;
   sz[SHASTA_WS_OUT_PART] = (size_t)4 * B * 4 * kF;
   sz[SHASTA_WS_BOX_BWD] = (size_t)B * 4 * (16 + 2 * (size_t)((7 * M) / 32 + 1) + 7 * (size_t)M);
+  sz[SHASTA_WS_CURX] = ((size_t)B * T + 16) * kPairCxStride;
   size_t o = 0;
   for (int i = 0; i < SHASTA_WS_NUM_REGIONS; ++i) {
     L.off[i] = o;
@@ -201,6 +211,12 @@ struct PackLayout {
   // pitch, the PyTorch parameter only has one when M % 4 == 0 (the shipped configs use M = 90, 50, 60, 20)
   size_t w2pad[4];
   int w2pad_ld;
+  // pairwise_tc3.cu: block-diagonal second layers as two [72 x 32] UMMA B images (hi | lo each, layout [k/4][32][4]):
+  //   X: k 0..31 = fuse_det hidden (PROJ cols 112..143) -> n 0..7,  k 32..71 = fuse_shape hidden (cols 0..39) -> n 8..27
+  //   Y: k 0..71 = res_coeff hidden (cols 40..111) -> n 0..17
+  // and the third/fourth layers in the pair-interleaved layout of the FFMA2 epilogue (see PairEp3 in pairwise_tc3.cu)
+  size_t tc3_begin, tc3_x_hi, tc3_x_lo, tc3_y_hi, tc3_y_lo, tc3_end;
+  size_t ep3, ep3_end;
   size_t total;       // floats
 };
 
@@ -259,6 +275,15 @@ __host__ inline PackLayout pack_layout(int M) {
   for (int sd = 0; sd < 2; ++sd) P.proj_tc[sd] = take((size_t)2 * kF * kProjShape);
   P.w2pad_ld = round_up(5 * M, 4);
   for (int i = 0; i < 4; ++i) P.w2pad[i] = take((size_t)kF * P.w2pad_ld);
+  o = (o + 31) / 32 * 32;   // 128-byte alignment of the images that are bulk-copied into shared memory
+  P.tc3_begin = o;
+  P.tc3_x_hi = take(72 * 32);
+  P.tc3_x_lo = take(72 * 32);
+  P.tc3_y_hi = take(72 * 32);
+  P.tc3_y_lo = take(72 * 32);
+  P.tc3_end = o;
+  P.ep3 = take(kPairEp3Floats);
+  P.ep3_end = o;
   P.total = o;
   return P;
 }

@@ -69,6 +69,56 @@ __global__ void aff_pieces_kernel(float* __restrict__ base, const __grid_constan
   }
 }
 
+// pairwise_tc3.cu operands: the two block-diagonal [72 x 32] second-layer images (hi | lo, layout [k/4][32][4]) and
+// the pair-interleaved third / fourth layers of its FFMA2 epilogue (shasta.py:59-92: fuse_shape.2/.4/.6,
+// res_coeff.2/.4, fuse_det.2/.4)
+struct Tc3Src {
+  const float *det2, *shape2, *coeff2;                       // (8,32) (20,40) (18,72)
+  const float *shape4, *shape4_b, *shape6, *shape6_b;        // (10,20) (10) (1,10) (1)
+  const float *coeff4, *coeff4_b, *det4, *det4_b;            // (3,18) (3) (1,8) (1)
+};
+__global__ void tc3_pack_kernel(float* __restrict__ xhi, float* __restrict__ xlo, float* __restrict__ yhi,
+                                float* __restrict__ ylo, float* __restrict__ ep, Tc3Src w) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < 2 * 72 * 32) {
+    const int img = idx / (72 * 32), e = idx % (72 * 32), n = e / 72, k = e % 72;
+    float v = 0.f;
+    if (img == 0) {
+      if (k < 32 && n < 8) v = w.det2[n * 32 + k];
+      if (k >= 32 && n >= 8 && n < 28) v = w.shape2[(n - 8) * 40 + (k - 32)];
+    } else if (n < 18) {
+      v = w.coeff2[n * 72 + k];
+    }
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    const int o = (k / 4) * (32 * 4) + n * 4 + (k % 4);
+    (img ? yhi : xhi)[o] = h;
+    (img ? ylo : xlo)[o] = v - h;
+  }
+  if (idx < kPairEp3Floats) {
+    float v = 0.f;
+    if (idx < kEp3B3a) {                       // w3a [10 jp][10 m][2]
+      const int jp = idx / 20, m = (idx % 20) / 2, i = idx & 1;
+      v = w.shape4[m * 20 + 2 * jp + i];
+    } else if (idx < kEp3W4a) {
+      if (idx - kEp3B3a < 10) v = w.shape4_b[idx - kEp3B3a];
+    } else if (idx < kEp3B4a) {
+      if (idx - kEp3W4a < 10) v = w.shape6[idx - kEp3W4a];
+    } else if (idx < kEp3W3b) {
+      if (idx == kEp3B4a) v = w.shape6_b[0];
+    } else if (idx < kEp3B3b) {                // w3b [9 jp][4 n][2]
+      const int e = idx - kEp3W3b, jp = e / 8, n = (e % 8) / 2, i = e & 1;
+      if (n < 3) v = w.coeff4[n * 18 + 2 * jp + i];
+    } else if (idx < kEp3W3c) {
+      if (idx - kEp3B3b < 3) v = w.coeff4_b[idx - kEp3B3b];
+    } else if (idx < kEp3B3c) {
+      v = w.det4[idx - kEp3W3c];
+    } else if (idx == kEp3B3c) {
+      v = w.det4_b[0];
+    }
+    ep[idx] = v;
+  }
+}
+
 static int bimage(float* hi, float* lo, float* bf, const float* src, int src_ld, int n_valid, int n_pad, int K,
                   cudaStream_t s) {
   umma_b_image_kernel<<<(n_pad * K + 255) / 256, 256, 0, s>>>(hi, lo, reinterpret_cast<__nv_bfloat16*>(bf), src,
@@ -171,6 +221,11 @@ int launch_pack(const shasta_params_t& p, float* packed, cudaStream_t s) {
   if (rc) return rc;
   rc = bimage(packed + P.tc32_w2c_hi, packed + P.tc32_w2c_lo, packed + P.tc16_w2c, p.fuse_det_w[1], 32, 8, 16, 32, s);
   if (rc) return rc;
+  Tc3Src t3 = {p.fuse_det_w[1],    p.fuse_shape_w[1], p.res_coeff_w[1], p.fuse_shape_w[2], p.fuse_shape_b[2], p.fuse_shape_w[3],
+               p.fuse_shape_b[3], p.res_coeff_w[2],  p.res_coeff_b[2], p.fuse_det_w[2],   p.fuse_det_b[2]};
+  tc3_pack_kernel<<<(2 * 72 * 32 + 255) / 256, 256, 0, s>>>(packed + P.tc3_x_hi, packed + P.tc3_x_lo, packed + P.tc3_y_hi,
+                                                            packed + P.tc3_y_lo, packed + P.ep3, t3);
+  SHASTA_CHECK_LAUNCH("tc3_pack_kernel");
   return 0;
 }
 

@@ -269,9 +269,19 @@ pairwise_ffma_kernel(const float* __restrict__ packed, PackLayout P, int B, int 
 int launch_pairwise_tc(const float* packed, int B, int M, float* ws, const WsLayout& L, int variant,
                        cudaStream_t s);  // pairwise_tc.cu
 
+bool pairwise_tc3_supported(int M);                                                                      // pairwise_tc3.cu
+int launch_pairwise_tc3(const float* packed, int B, int M, float* ws, const WsLayout& L, cudaStream_t s);
+
 int launch_pairwise(const float* packed, int B, int M, float* ws, const WsLayout& L, int variant,
                     cudaStream_t s) {
-  // 0 = default (tcgen05 3xTF32, fp32-equivalent), 1 = tcgen05 3xTF32, 2 = tcgen05 bf16, 3 = CUDA-core fp32
+  // 0 = default = 1 = persistent tcgen05 3xTF32 kernel (pairwise_tc.cu), 2 = tcgen05 bf16, 3 = CUDA-core fp32,
+  // 4 = the warp-specialised pipelined tcgen05 kernel of pairwise_tc3.cu (experiment: correct, measured slower - see
+  //     profiles/README.md "pairwise_tc3")
+  if (variant == 4 && !pairwise_tc3_supported(M)) {
+    set_error("pairwise variant 4 needs max_obj >= 15");
+    return SHASTA_ERR_UNSUPPORTED;
+  }
+  if (variant == 4) return launch_pairwise_tc3(packed, B, M, ws, L, s);
   if (variant != 3) return launch_pairwise_tc(packed, B, M, ws, L, variant == 0 ? 1 : variant, s);
   const PackLayout P = pack_layout(M);
   const int T = M + 2;

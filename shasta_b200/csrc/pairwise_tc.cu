@@ -449,7 +449,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
 int launch_pairwise_tc(const float* packed, int B, int M, float* ws, const WsLayout& L, int variant,
                        cudaStream_t s) {
   if (variant != 1 && variant != 2) {
-    set_error("pairwise variant %d unknown (0 = default, 1 = tcgen05 3xTF32, 2 = tcgen05 bf16, 3 = CUDA cores)", variant);
+    set_error("pairwise variant %d unknown (0 = default, 1 = tcgen05 3xTF32 v2, 2 = tcgen05 bf16, 3 = CUDA cores, 4 = tcgen05 3xTF32 v3)", variant);
     return SHASTA_ERR_ARG;
   }
   const PackLayout P = pack_layout(M);

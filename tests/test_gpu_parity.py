@@ -257,13 +257,22 @@ def test_project_and_pairwise_stage(name, project_path):
     assert np.array_equal(got_pct, got_pc)
     # pairwise -> residual: CUDA-core fp32, tcgen05 3xTF32 (fp32-equivalent), tcgen05 bf16 (separate tolerance)
     want = g["residual"]
-    for variant, tol in ((3, 1e-5), (1, 2e-5), (0, 2e-5), (2, 2e-2)):
+    # (variant 4 = the warp-specialised pipelined tcgen05 kernel of pairwise_tc3.cu - max-form outer sum, seeded
+    # accumulators - with the FFMA2 and the scalar-FFMA epilogue)
+    variants = [(3, 1e-5, 0), (1, 2e-5, 0), (0, 2e-5, 0), (2, 2e-2, 0)]
+    if M >= 15:
+        variants += [(4, 2e-5, 0), (4, 2e-5, 2)]
+    for variant, tol, ffma2 in variants:
         st.region(_cabi.WS_RESIDUAL, (B, T, st.RS)).zero_()
-        st.pairwise(variant)
+        _cabi.lib().shasta_set_option(_cabi.OPT_PAIR_FFMA2, ffma2)
+        try:
+            st.pairwise(variant)
+        finally:
+            _cabi.lib().shasta_set_option(_cabi.OPT_PAIR_FFMA2, 0)
         res = st.region(_cabi.WS_RESIDUAL, (B, T, st.RS)).cpu().numpy()[:, :, :T]
         err = np.abs(res - want).max() / np.abs(want).max()
-        print("pairwise variant %d (0 default, 1 tf32x3, 2 bf16, 3 ffma): residual max err / scale = %.3g"
-              % (variant, err))
+        print("pairwise variant %d (0 default, 1 tf32x3 v2, 2 bf16, 3 ffma, 4 tf32x3 v3; ffma2 opt %d): residual max err / "
+              "scale = %.3g" % (variant, ffma2, err))
         assert err < tol, "variant %d residual max err / scale = %g" % (variant, err)
 
 
@@ -552,10 +561,11 @@ def test_all_zero_boxes_and_out_of_range_boxes():
 # ------------------------------------------------------------------------------------------------
 # headline size: M = 200 (BASELINE.json configs[0]/[1]) against the oracle, plus size-independent properties
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("H,W,B,flags,anchor", [(180, 180, 3, 0, 0), (512, 512, 1, 0x30, 0), (180, 180, 2, 0x10, 2)])
+@pytest.mark.parametrize("H,W,B,flags,anchor", [(180, 180, 3, 0, 0), (512, 512, 1, 0x30, 0), (180, 180, 2, 0x10, 2),
+                                                (512, 512, 5, 0x40, 2)])
 def test_headline_size_against_oracle(H, W, B, flags, anchor):
-    """anchor = 2 forces the tcgen05 anchors GEMM; flags 0 / 0x10 = tcgen05 3xTF32 pairwise tiles (the default),
-    0x30 = CUDA-core pairwise tiles: every fp32-mode combination must reproduce the oracle's association exactly."""
+    """anchor = 2 forces the tcgen05 anchors GEMM; flags 0 / 0x10 = persistent tcgen05 3xTF32 pairwise tiles (the
+    default), 0x40 = the warp-specialised pipelined tcgen05 kernel, 0x30 = CUDA-core pairwise tiles: every fp32-mode combination must reproduce the oracle's association exactly."""
     M = 200
     _cabi.lib().shasta_set_option(_cabi.OPT_ANCHOR_PATH, anchor)
     try:
