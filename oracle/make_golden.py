@@ -30,6 +30,13 @@ CASES = {
 }
 
 
+# headline-size fixtures (BASELINE.json configs[0]/[1] shape, M = 200): outputs only - the intermediates of a 200 x 200
+# case would be tens of MB. File names start with "h" so that the per-stage tests (which need intermediates) skip them.
+HEADLINE_CASES = {
+    "h200_180px_b1_peaky": dict(M=200, H=180, W=180, B=1, seed=16, wseed=6, peaky=400.0),
+}
+
+
 def case_inputs(c):
     pc_start = (-c["W"] * 0.6 / 2.0, -c["H"] * 0.6 / 2.0)
     data = synthetic.make_frame_pairs(c["B"], c["M"], c["H"], c["W"], c["seed"], pc_start=pc_start)
@@ -76,5 +83,30 @@ def main():
               "bytes", os.path.getsize(path))
 
 
+def main_headline():
+    torch.set_num_threads(1)
+    for name, c in HEADLINE_CASES.items():
+        pc_start, data, weights = case_inputs(c)
+        model = ref_loader.build_reference_head(c["M"], 3, pc_start=pc_start)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()}, strict=False)
+        det = torch.from_numpy(data["det_boxes"].copy())
+        prev = torch.from_numpy(data["prev_det_boxes"].copy())
+        m1, m2, ex = ref_loader.run_reference(
+            model, torch.from_numpy(data["bev"]), torch.from_numpy(data["prev_bev"]), det, prev, capture=False)
+        out = dict(matched1=m1.numpy(), matched2=m2.numpy(), det_boxes_after=ex["det_boxes"].numpy(),
+                   n_det=data["n_det"], n_prev=data["n_prev"],
+                   input_checksum=np.array([synthetic.checksum(data["det_boxes"], data["prev_det_boxes"],
+                                                               data["bev"], data["prev_bev"])], dtype=np.uint64),
+                   weight_checksum=np.array([synthetic.checksum(*[weights[k] for k in sorted(weights)])],
+                                            dtype=np.uint64),
+                   case=np.array(json.dumps(c)))
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(name, "m1", m1.shape, "max", float(m1.max()), "m2 max", float(m2.max()), "bytes", os.path.getsize(path))
+
+
 if __name__ == "__main__":
-    main()
+    if "--headline" in sys.argv:
+        main_headline()
+    else:
+        main()

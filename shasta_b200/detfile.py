@@ -5,18 +5,25 @@ The reference reads one ``<token>.json`` per frame and per class model, and buil
 row by row in Python (det3d/datasets/nuscenes/nuscenes.py:207-293). A detection file holds the same information for
 many frames in flat arrays, so that a BATCH of frame pairs is packed with a handful of numpy slice copies:
 
-    header   magic "SHDB0001", little-endian u32 counts (frames, classes, attributes), u64 rows
+    header   magic "SHDB0002", little-endian u32 counts (frames, classes, attributes), u64 rows
     tables   class names, attribute names (u16 length + utf-8 each)
     frames   token[frames] (u16 length + utf-8), then int32 prev_index (-1 = first frame of a scene), int64 timestamp,
              int64 prev_timestamp (microseconds, nuScenes frame info), int64 row_begin, int32 row_count
-    rows     float64 [rows][14]: translation(3) size(3) rotation(4: w,x,y,z) velocity(2) detection_score yaw
+    rows     float64 [rows][14]: the ``det_path`` box in the SENSOR frame of its own sweep - translation(3) size(3)
+             rotation(4: w,x,y,z) velocity(2) - then detection_score and yaw: what the head's (M, 11) boxes are packed from
+             float64 [rows][12]: the ``cls_info`` entry of the same detection in the GLOBAL frame - translation(3)
+             size(3) rotation(4) velocity(2): what the eval loop emits and the tracker matches on
+             (tools/nusc_shasta/eval.py:126-181; the reference keeps the two in separate directories,
+             configs det_path = '.../sensor_individual_frames', preprocessing/filter_track_types.py)
              uint8 class id [rows], uint8 attribute id [rows]   (255 = no attribute)
+             uint32 extra_offset [rows + 1] + utf-8 blob: JSON object of any further ``cls_info`` keys of a row
 
 Rows keep the order of the frame's detection list (all classes), so the ``keep`` indices of ``formats.pack_detections``
 are reproduced; values stay float64 so that the emitted annotations are the input's, and ``yaw`` is computed ONCE at
 write time with the same scalar routine as the JSON path (``formats.quaternion_yaw``), which makes the packed arrays
 bit-identical to ``formats.frame_pair_example`` on the JSON input (tests/test_detfile.py).
 """
+import json as _json
 import random as _random
 import struct
 
@@ -24,8 +31,11 @@ import numpy as np
 
 from . import formats
 
-MAGIC = b"SHDB0001"
+MAGIC = b"SHDB0002"
 ROW = 14
+CLS_ROW = 12
+_CLS_KEYS = ("sample_token", "translation", "size", "rotation", "velocity", "detection_name", "detection_score",
+             "attribute_name")
 NO_ATTR = 255
 
 
@@ -41,7 +51,7 @@ def write_detection_file(path, frames):
     file (or be '')."""
     index = {f["token"]: i for i, f in enumerate(frames)}
     classes, attrs = [], []
-    rows, cls_id, attr_id = [], [], []
+    rows, cls_rows, cls_id, attr_id, extras = [], [], [], [], []
     prev_index, ts, pts, begin, count = [], [], [], [], []
     for f in frames:
         prev_index.append(index[f["prev_token"]] if f["prev_token"] != "" else -1)
@@ -57,8 +67,12 @@ def write_detection_file(path, frames):
             if attr is not None and attr not in attrs:
                 attrs.append(attr)
             rows.append(list(b[:12]) + [info["detection_score"], formats.quaternion_yaw(np.array(b[6:10]))[0]])
+            cls_rows.append(list(info["translation"][:3]) + list(info["size"][:3]) + list(info["rotation"][:4]) +
+                            list(info["velocity"][:2]))
             cls_id.append(classes.index(name))
             attr_id.append(NO_ATTR if attr is None else attrs.index(attr))
+            extra = {k: v for k, v in info.items() if k not in _CLS_KEYS}
+            extras.append(_json.dumps(extra).encode("utf-8") if extra else b"")
     if len(classes) > 255 or len(attrs) > 254:
         raise ValueError("too many class / attribute names for the one-byte ids")
     out = [MAGIC, struct.pack("<IIIQ", len(frames), len(classes), len(attrs), len(rows))]
@@ -76,8 +90,15 @@ def write_detection_file(path, frames):
         fh.write(np.asarray(count, "<i4").tobytes())
         fh.write(b"\0" * (-4 * len(frames) % 8))
         fh.write(np.asarray(rows, "<f8").reshape(-1, ROW).tobytes())
+        fh.write(np.asarray(cls_rows, "<f8").reshape(-1, CLS_ROW).tobytes())
         fh.write(np.asarray(cls_id, "u1").tobytes())
         fh.write(np.asarray(attr_id, "u1").tobytes())
+        fh.write(b"\0" * (-2 * len(rows) % 8))
+        offs = np.zeros(len(rows) + 1, "<u4")
+        if extras:
+            offs[1:] = np.cumsum([len(e) for e in extras])
+        fh.write(offs.tobytes())
+        fh.write(b"".join(extras))
 
 
 class DetectionFile:
@@ -119,8 +140,12 @@ class DetectionFile:
         self.row_begin = take("<i8", nf)
         self.row_count = take("<i4", nf, pad8=True)
         self.rows = take("<f8", nr * ROW).reshape(nr, ROW)
+        self.cls_rows = take("<f8", nr * CLS_ROW).reshape(nr, CLS_ROW)
         self.cls_id = take("u1", nr)
         self.attr_id = take("u1", nr)
+        pos += -2 * nr % 8
+        self.extra_offset = take("<u4", nr + 1)
+        self.extra_blob = take("u1", int(self.extra_offset[nr]) if nr else 0)
         self.n_frames = nf
         self._index = {t: i for i, t in enumerate(self.tokens)}
 
@@ -204,15 +229,20 @@ class DetectionFile:
                 "prev_keep": prev_keep, "rows": rows, "prev_rows": prev_rows}
 
     def cls_info(self, absolute_rows, token):
-        """The detection dicts of the given rows, in the layout the eval loop emits (``cp_<split>.json`` entries)."""
+        """The detection dicts of the given rows, in the layout the eval loop emits (``cp_<split>.json`` entries):
+        the GLOBAL-frame ``cls_info`` fields, not the sensor-frame box the head's input is packed from."""
         out = []
         for r in absolute_rows:
-            v = self.rows[int(r)]
+            r = int(r)
+            v = self.cls_rows[r]
             d = {"sample_token": token, "translation": v[0:3].tolist(), "size": v[3:6].tolist(),
                  "rotation": v[6:10].tolist(), "velocity": v[10:12].tolist(),
-                 "detection_name": self.classes[int(self.cls_id[int(r)])], "detection_score": float(v[12])}
-            if int(self.attr_id[int(r)]) != NO_ATTR:
-                d["attribute_name"] = self.attributes[int(self.attr_id[int(r)])]
+                 "detection_name": self.classes[int(self.cls_id[r])], "detection_score": float(self.rows[r, 12])}
+            if int(self.attr_id[r]) != NO_ATTR:
+                d["attribute_name"] = self.attributes[int(self.attr_id[r])]
+            lo, hi = int(self.extra_offset[r]), int(self.extra_offset[r + 1])
+            if hi > lo:
+                d.update(_json.loads(bytes(self.extra_blob[lo:hi]).decode("utf-8")))
             out.append(d)
         return out
 

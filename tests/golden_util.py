@@ -25,3 +25,8 @@ def load_golden(name):
         g["input_checksum"][0]), "synthetic generator drifted from the fixture"
     assert synthetic.checksum(*[weights[k] for k in sorted(weights)]) == int(g["weight_checksum"][0])
     return c, pc_start, data, weights, g
+
+
+def headline_names():
+    """Outputs-only fixtures of the headline size (M = 200), written by ``python -m oracle.make_golden --headline``."""
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "h*.npz")))

@@ -20,17 +20,28 @@ def _frames(seed, n_scenes=3, n_frames=5, max_dets=14):
         for f in range(n_frames):
             n = 0 if (s == 1 and f == 2) else int(rng.integers(1, max_dets))
             dets, cls = [], []
+            # the det_path boxes are in the SENSOR frame of their sweep, the cls_info entries in the GLOBAL frame
+            # (preprocessing/filter_track_types.py): a per-frame rigid transform (ego pose) separates the two
+            ego_yaw = float(rng.uniform(-np.pi, np.pi))
+            ego_t = rng.uniform(-500, 500, 3)
+            c, sn = np.cos(ego_yaw), np.sin(ego_yaw)
+            R = np.array([[c, -sn, 0.0], [sn, c, 0.0], [0.0, 0.0, 1.0]])
             for _ in range(n):
                 q = rng.normal(size=4)
                 if rng.random() < 0.5:
                     q /= np.linalg.norm(q)          # both normalised and raw quaternions
                 box = (list(rng.uniform(-50, 50, 3)) + list(rng.uniform(0.5, 5, 3)) + list(q) + list(rng.normal(0, 3, 2)))
                 dets.append([float(x) for x in box])
-                info = {"sample_token": "s%d_f%d" % (s, f), "translation": dets[-1][0:3], "size": dets[-1][3:6],
-                        "rotation": dets[-1][6:10], "velocity": dets[-1][10:12],
+                gq = rng.normal(size=4)
+                info = {"sample_token": "s%d_f%d" % (s, f),
+                        "translation": [float(x) for x in R @ np.array(box[0:3]) + ego_t], "size": dets[-1][3:6],
+                        "rotation": [float(x) for x in gq / np.linalg.norm(gq)],
+                        "velocity": [float(x) for x in (R @ np.array(box[10:12] + [0.0]))[:2]],
                         "detection_name": CLASSES[int(rng.integers(0, 3))], "detection_score": float(rng.uniform(0.05, 1))}
                 if rng.random() < 0.6:
                     info["attribute_name"] = ["vehicle.moving", "vehicle.parked", "pedestrian.standing"][int(rng.integers(0, 3))]
+                if rng.random() < 0.3:                # keys beyond the nuScenes detection schema survive the round trip
+                    info["num_pts"] = int(rng.integers(0, 500))
                 cls.append(info)
             ts = 1_600_000_000_000_000 + (s * 100 + f) * 500_000 + int(rng.integers(0, 2000))
             frames.append({"token": "s%d_f%d" % (s, f), "prev_token": "" if f == 0 else "s%d_f%d" % (s, f - 1),

@@ -6,8 +6,10 @@
 * the literal bench configuration — M = 200, 512 x 512 x 64 maps, B = 64 frame pairs, flags 0, automatic anchors
   path, CUDA-graph replay — in one piece.
 
-Bars: affinities within 1e-3 relative (BASELINE.json north_star), association (the decode of eval.py:126-181)
-identical. The oracle needs ~9 GB (M = 500) / ~40 GB (M = 1000) of host memory: the tests skip with a message when
+Bars: affinities within 1e-3 relative (BASELINE.json north_star); association (the decode of eval.py:126-181):
+every dead / FN / kept / newborn decision identical and every argmax identical, except argmaxes whose top-2 margin in
+the ORACLE is below 2e-5 relative (fp32 rounding noise: the reference's own pick depends on its summation order there;
+counted and printed). The oracle needs ~9 GB (M = 500) / ~40 GB (M = 1000) of host memory: the tests skip with a message when
 the host has less.
 """
 import numpy as np
@@ -17,10 +19,10 @@ import torch
 from oracle import shasta_oracle as O
 from shasta_b200 import synthetic
 from tests import gpu_util as G
+from tests.golden_util import headline_names, load_golden
 
 pytestmark = pytest.mark.gpu
 
-DECODE_KEYS = ("dead", "fn", "keep_prev", "keep_dets", "newborn", "row_argmax", "col_argmax")
 
 
 def _host_free_gb():
@@ -42,7 +44,7 @@ def _device_maps(B, H, W, seed):
 def _check_against_oracle(M, w, bev, prev_bev, data, pc_start, m1, m2, det_after, chunk=1):
     B = bev.shape[0]
     m1c, m2c = m1.cpu(), m2.cpu()
-    worst = 0.0
+    worst, ties, small = 0.0, 0, 0.0
     for b0 in range(0, B, chunk):
         sl = slice(b0, min(B, b0 + chunk))
         det_o = torch.from_numpy(data["det_boxes"][sl].copy())
@@ -51,15 +53,20 @@ def _check_against_oracle(M, w, bev, prev_bev, data, pc_start, m1, m2, det_after
         e1, e2 = G.rel_err(m1c[sl].numpy(), o1.numpy()), G.rel_err(m2c[sl].numpy(), o2.numpy())
         worst = max(worst, e1, e2)
         assert e1 < 1e-3 and e2 < 1e-3, (b0, e1, e2)
+        # the same bar with the denominator floored at 1e-6 (not 1e-3) of the scale: small probabilities relatively
+        s1 = G.rel_err(m1c[sl].numpy(), o1.numpy(), 1e-6)
+        s2 = G.rel_err(m2c[sl].numpy(), o2.numpy(), 1e-6)
+        small = max(small, s1, s2)
+        assert s1 < 1e-3 and s2 < 1e-3, (b0, s1, s2)
         assert np.array_equal(det_after[sl].cpu().numpy(), det_o.numpy()), "in-place back-projection (shasta.py:270)"
         for i, b in enumerate(range(sl.start, sl.stop)):
-            n_prev, n_det = int(data["n_prev"][b]), int(data["n_det"][b])
-            want = O.decode(o1[i], o2[i], n_prev, n_det)
-            got = O.decode(m1c[b], m2c[b], n_prev, n_det)
-            for key in DECODE_KEYS:
-                assert got[key] == want[key], (b, key)
+            ties += G.assert_same_association(O, o1[i], o2[i], m1c[b], m2c[b], int(data["n_prev"][b]),
+                                              int(data["n_det"][b]), where="frame pair %d" % b)
     assert torch.allclose(m1c.sum(2), torch.ones(B, M), atol=1e-5)
     assert torch.allclose(m2c.sum(1), torch.ones(B, M), atol=1e-5)
+    print("worst relative error with the 1e-6 floor: %.3g" % small)
+    print("argmax decisions inside the oracle's fp32 noise (top-2 margin < 2e-5 relative): %d of %d"
+          % (ties, 2 * B * M))
     return worst
 
 
@@ -114,3 +121,23 @@ def test_bench_configuration_against_oracle():
     w = O.weights_to_torch(weights)
     worst = _check_against_oracle(M, w, bev, prev_bev, data, pc_start, m1, m2, det, chunk=4)
     print("bench configuration (M=200, 512^2, B=64, graph replay): worst relative affinity error %.3g" % worst)
+
+
+@pytest.mark.parametrize("name", headline_names())
+def test_forward_matches_reference_golden_at_headline_size(name):
+    """M = 200 against outputs of the UNMODIFIED reference (tests/golden/h200_*.npz, oracle/make_golden.py --headline):
+    no oracle in between."""
+    c, pc_start, data, weights, g = load_golden(name)
+    model = G.make_model(c["M"], pc_start, weights)
+    det = G.t(data["det_boxes"])
+    with torch.no_grad():
+        m1, m2 = model.affinity(G.t(data["bev"]), G.t(data["prev_bev"]), det, G.t(data["prev_det_boxes"]))
+    m1, m2 = m1.cpu(), m2.cpu()
+    assert G.rel_err(m1.numpy(), g["matched1"]) < 1e-3 and G.rel_err(m2.numpy(), g["matched2"]) < 1e-3
+    assert np.array_equal(det.cpu().numpy(), g["det_boxes_after"])
+    ties = 0
+    for b in range(c["B"]):
+        ties += G.assert_same_association(O, torch.from_numpy(g["matched1"][b]), torch.from_numpy(g["matched2"][b]),
+                                          m1[b], m2[b], int(data["n_prev"][b]), int(data["n_det"][b]))
+    print("%s: rel err %.3g / %.3g, fp32-level argmax ties %d" % (name, G.rel_err(m1.numpy(), g["matched1"]),
+                                                                   G.rel_err(m2.numpy(), g["matched2"]), ties))

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import shasta_oracle as O
-from tests.golden_util import golden_names, load_golden
+from tests.golden_util import golden_names, headline_names, load_golden
 
 
 @pytest.fixture(autouse=True)
@@ -40,6 +40,18 @@ def test_oracle_matches_reference_golden_bit_exact(name):
     # in-place back-projection of the caller's boxes (shasta.py:270)
     assert np.array_equal(det.numpy(), g["det_boxes_after"])
     assert not np.array_equal(det.numpy(), data["det_boxes"])
+
+
+@pytest.mark.parametrize("name", headline_names())
+def test_oracle_matches_reference_golden_at_headline_size(name):
+    """M = 200 (BASELINE.json configs[0]): outputs of the unmodified reference, bit for bit."""
+    c, pc_start, data, weights, g = load_golden(name)
+    det = torch.from_numpy(data["det_boxes"].copy())
+    m1, m2 = O.forward(O.weights_to_torch(weights), torch.from_numpy(data["bev"]), torch.from_numpy(data["prev_bev"]),
+                       det, torch.from_numpy(data["prev_det_boxes"]), pc_start=pc_start)
+    assert np.array_equal(m1.numpy(), g["matched1"])
+    assert np.array_equal(m2.numpy(), g["matched2"])
+    assert np.array_equal(det.numpy(), g["det_boxes_after"])
 
 
 @pytest.mark.parametrize("name", golden_names())
