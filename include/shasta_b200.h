@@ -326,15 +326,17 @@ SHASTA_API int shasta_profile_end(float* host_stage_ms, int* host_steps);
  * over the valid region + the two anchor entries and the 0.5 / 0.7 thresholds.
  * n_prev/n_det (B) int32. Outputs (int32 unless noted), all sized for max_obj:
  *   prev_state (B,M): 0 keep, 1 dead, 2 false negative, -1 padding ; prev_argmax (B,M)
- *   fn_score   (B,M) float: 1 - P(dead) for false negatives
+ *   fn_dead_prob (B,M) float: matched1[n,-2] of false negatives, RAW - the reference's ref_detection_score is
+ *                     1 - value formed in double on the host (eval.py:148), which a float32 subtraction here would not
+ *                     reproduce bit for bit
  *   det_state  (B,M): 0 keep, 1 keep+newborn, 2 dropped false positive, -1 padding ; det_argmax (B,M)
  *                     det_argmax indexes the KEPT previous rows followed by newborn, fp (as the reference's
  *                     matched_dets does)
- *   det_score  (B,M) float: 1 - P(fp)   (ref_detection_score) */
+ *   det_fp_prob (B,M) float: matched2[-1,k] of kept detections, RAW (ref_detection_score = 1 - value, eval.py:169) */
 SHASTA_API int shasta_decode_f32(const float* matched1, const float* matched2, const int32_t* n_prev,
                       const int32_t* n_det, int batch, int max_obj, int32_t* prev_state,
-                      int32_t* prev_argmax, float* fn_score, int32_t* det_state, int32_t* det_argmax,
-                      float* det_score, shasta_stream_t stream);
+                      int32_t* prev_argmax, float* fn_dead_prob, int32_t* det_state, int32_t* det_argmax,
+                      float* det_fp_prob, shasta_stream_t stream);
 
 #ifdef __cplusplus
 }

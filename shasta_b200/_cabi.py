@@ -138,6 +138,15 @@ def lib():
     return _lib
 
 
+def lib_has(symbol):
+    """True when the loaded library exports ``symbol`` (entry points added after ABI version 1 are optional)."""
+    try:
+        getattr(lib(), symbol)
+        return True
+    except AttributeError:
+        return False
+
+
 def check(rc, what):
     if rc != 0:
         msg = lib().shasta_last_error_string().decode("utf-8", "replace")

@@ -610,8 +610,8 @@ int shasta_profile_end(float* host_stage_ms, int* host_steps) {
 }
 
 int shasta_decode_f32(const float* matched1, const float* matched2, const int32_t* n_prev, const int32_t* n_det,
-                      int batch, int max_obj, int32_t* prev_state, int32_t* prev_argmax, float* fn_score,
-                      int32_t* det_state, int32_t* det_argmax, float* det_score, shasta_stream_t stream) {
+                      int batch, int max_obj, int32_t* prev_state, int32_t* prev_argmax, float* fn_dead_prob,
+                      int32_t* det_state, int32_t* det_argmax, float* det_fp_prob, shasta_stream_t stream) {
   int rc = check_dims(batch, max_obj);
   if (rc) return rc;
   NOT_NULL(matched1);
@@ -620,12 +620,12 @@ int shasta_decode_f32(const float* matched1, const float* matched2, const int32_
   NOT_NULL(n_det);
   NOT_NULL(prev_state);
   NOT_NULL(prev_argmax);
-  NOT_NULL(fn_score);
+  NOT_NULL(fn_dead_prob);
   NOT_NULL(det_state);
   NOT_NULL(det_argmax);
-  NOT_NULL(det_score);
-  return launch_decode(matched1, matched2, n_prev, n_det, batch, max_obj, prev_state, prev_argmax, fn_score,
-                       det_state, det_argmax, det_score, (cudaStream_t)stream);
+  NOT_NULL(det_fp_prob);
+  return launch_decode(matched1, matched2, n_prev, n_det, batch, max_obj, prev_state, prev_argmax, fn_dead_prob,
+                       det_state, det_argmax, det_fp_prob, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -398,7 +398,7 @@ int launch_project_gemm_tc(const float* packed, int B, int M, float* ws, const W
 bool anchor_uses_featlo(int M, int B);  // true when the anchors path in use for (M, B) reads the FEATLO_* regions
 int anchor_splits_in_use(int M, int B);  // split-K count the forward anchors kernel uses for this (M, B)
 int launch_decode(const float* m1, const float* m2, const int32_t* n_prev, const int32_t* n_det, int B, int M,
-                  int32_t* prev_state, int32_t* prev_argmax, float* fn_score, int32_t* det_state,
-                  int32_t* det_argmax, float* det_score, cudaStream_t s);
+                  int32_t* prev_state, int32_t* prev_argmax, float* fn_dead_prob, int32_t* det_state,
+                  int32_t* det_argmax, float* det_fp_prob, cudaStream_t s);
 
 }  // namespace shasta

@@ -10,8 +10,8 @@ constexpr int kDecThreads = 256;
 __global__ void __launch_bounds__(kDecThreads)
 decode_kernel(const float* __restrict__ m1, const float* __restrict__ m2, const int32_t* __restrict__ n_prev_a,
               const int32_t* __restrict__ n_det_a, int M, int32_t* __restrict__ prev_state,
-              int32_t* __restrict__ prev_argmax, float* __restrict__ fn_score, int32_t* __restrict__ det_state,
-              int32_t* __restrict__ det_argmax, float* __restrict__ det_score) {
+              int32_t* __restrict__ prev_argmax, float* __restrict__ fn_dead_prob, int32_t* __restrict__ det_state,
+              int32_t* __restrict__ det_argmax, float* __restrict__ det_fp_prob) {
   extern __shared__ int s_keep[];  // [M] compacted indices of kept previous rows
   __shared__ int s_nkeep;
   const int b = blockIdx.x;
@@ -48,13 +48,13 @@ decode_kernel(const float* __restrict__ m1, const float* __restrict__ m2, const 
         if ((double)best > 0.5 && arg == nd) state = 1;
         else if ((double)best > 0.5 && arg == nd + 1) {
           state = 2;
-          score = 1.0f - row[M];  // 1 - matched_dets[n,-2]
+          score = row[M];  // matched_dets[n,-2]: the host forms ref_detection_score = 1 - value in double (eval.py:148)
         }
       }
       if (lane == 0) {
         prev_state[(size_t)b * M + n] = state;
         prev_argmax[(size_t)b * M + n] = arg;
-        fn_score[(size_t)b * M + n] = score;
+        fn_dead_prob[(size_t)b * M + n] = score;
       }
     }
   }
@@ -104,21 +104,21 @@ decode_kernel(const float* __restrict__ m1, const float* __restrict__ m2, const 
       if ((double)best > 0.7 && arg == nk + 1) state = 2;
       else {
         state = ((double)best > 0.5 && arg == nk) ? 1 : 0;
-        score = 1.0f - vf;  // ref_detection_score = 1 - matched_dets[-1,k]
+        score = vf;  // matched_dets[-1,k]: ref_detection_score = 1 - value is formed on the host in double (eval.py:169)
       }
     }
     det_state[(size_t)b * M + k] = state;
     det_argmax[(size_t)b * M + k] = arg;
-    det_score[(size_t)b * M + k] = score;
+    det_fp_prob[(size_t)b * M + k] = score;
   }
 }
 
 int launch_decode(const float* m1, const float* m2, const int32_t* n_prev, const int32_t* n_det, int B, int M,
-                  int32_t* prev_state, int32_t* prev_argmax, float* fn_score, int32_t* det_state,
-                  int32_t* det_argmax, float* det_score, cudaStream_t s) {
+                  int32_t* prev_state, int32_t* prev_argmax, float* fn_dead_prob, int32_t* det_state,
+                  int32_t* det_argmax, float* det_fp_prob, cudaStream_t s) {
   if (B == 0) return 0;
-  decode_kernel<<<B, kDecThreads, sizeof(int) * M, s>>>(m1, m2, n_prev, n_det, M, prev_state, prev_argmax, fn_score,
-                                                        det_state, det_argmax, det_score);
+  decode_kernel<<<B, kDecThreads, sizeof(int) * M, s>>>(m1, m2, n_prev, n_det, M, prev_state, prev_argmax, fn_dead_prob,
+                                                        det_state, det_argmax, det_fp_prob);
   SHASTA_CHECK_LAUNCH("decode_kernel");
   return 0;
 }

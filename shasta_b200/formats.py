@@ -158,12 +158,15 @@ def frame_pair_example(prev_dets, prev_cls, cur_dets, cur_cls, max_objects, time
             "prev_keep": pk, "keep": ck}
 
 
-def annos_from_decode(prev_cls, cur_cls, prev_state, fn_score, det_state, det_score, token, time_lag):
+def annos_from_decode(prev_cls, cur_cls, prev_state, fn_dead_prob, det_state, det_fp_prob, token, time_lag):
     """The dict-level half of the eval loop (tools/nusc_shasta/eval.py:126-181) on the arrays ``shasta_decode_f32``
     returns for ONE frame pair (prev_state: 0 keep / 1 dead / 2 FN; det_state: 0 keep / 1 newborn / 2 dropped FP).
     Mutates the cls_info dicts like the reference (FN boxes are propagated by ``velocity * time_lag``, ``newborn`` /
     ``ref_detection_score`` are attached) and returns ``(annos for this token, dead previous indices, kept current
-    indices)`` — the last two feed the reference's ``dead_tracker`` post-pass (eval.py:175-181)."""
+    indices)`` — the last two feed the reference's ``dead_tracker`` post-pass (eval.py:175-181).
+    ``fn_dead_prob[n]`` = matched1[n, -2] of an FN row, ``det_fp_prob[k]`` = matched2[-1, k] of a kept detection (float32,
+    as the decode kernel stores them): ``ref_detection_score = 1 - value`` is formed here in Python double, exactly like
+    the reference's ``1 - tensor.item()`` (eval.py:148,169), so the emitted JSON is bit-identical."""
     annos, fn_annos, dead_idx, keep_dets = [], [], [], []
     for n in range(len(prev_cls)):
         if prev_state[n] == 1:
@@ -173,14 +176,14 @@ def annos_from_decode(prev_cls, cur_cls, prev_state, fn_score, det_state, det_sc
             box["translation"][:2] = [t + time_lag * v for t, v in zip(box["translation"][:2], box["velocity"])]
             box["FN"] = True
             box["token"] = token
-            box["ref_detection_score"] = float(fn_score[n])
+            box["ref_detection_score"] = 1 - float(fn_dead_prob[n])
             fn_annos.append(box)
     for k in range(len(cur_cls)):
         if det_state[k] == 2:
             continue
         if det_state[k] == 1:
             cur_cls[k]["newborn"] = True
-        cur_cls[k]["ref_detection_score"] = float(det_score[k])
+        cur_cls[k]["ref_detection_score"] = 1 - float(det_fp_prob[k])
         keep_dets.append(k)
         annos.append(cur_cls[k])
     annos.extend(fn_annos)

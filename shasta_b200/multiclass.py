@@ -20,7 +20,7 @@ NUSC_CLASS_MAX_OBJ = (("car", 90), ("pedestrian", 90), ("bus", 20), ("truck", 60
 # (configs/nusc/car.py:86) for the synthetic 10-class workload
 SYNTHETIC_CLASS_MAX_OBJ = (("construction_vehicle", 200), ("barrier", 500), ("traffic_cone", 500))
 
-DECODE_FIELDS = ("prev_state", "prev_argmax", "fn_score", "det_state", "det_argmax", "det_score")
+DECODE_FIELDS = ("prev_state", "prev_argmax", "fn_dead_prob", "det_state", "det_argmax", "det_fp_prob")
 
 
 class ClassLane:
@@ -58,7 +58,14 @@ class ClassLane:
         if not self.step_graphs:
             self._body(batch, det_work, dec_out)
             return dec_out
-        key = tuple(batch[k].data_ptr() for k in ("bev", "prev_bev", "det_boxes", "prev_det_boxes", "n_prev", "n_det")) + (B,)
+        # everything the captured launches bake in: input addresses, the packed-weight buffer (re-allocated whenever a
+        # parameter changes), the workspace, kernel flags and precision mode. A stale entry would replay against freed
+        # weights or a freed workspace.
+        model = self.model
+        model._ensure_packed(device)
+        key = (tuple(batch[k].data_ptr() for k in ("bev", "prev_bev", "det_boxes", "prev_det_boxes", "n_prev", "n_det"))
+               + (B, model._pack_key, model._packed.data_ptr(), model._workspace(B, device).buf.data_ptr(),
+                  int(model.kernel_flags), bool(model.bf16)))
         graph = self._graphs.get(key)
         if graph is None:
             if len(self._graphs) >= 64:
@@ -119,7 +126,7 @@ def decode_fields(block):
     res = {}
     for i, k in enumerate(DECODE_FIELDS):
         v = block[..., i, :]
-        res[k] = v.view(torch.float32) if k.endswith("score") else v
+        res[k] = v.view(torch.float32) if k.endswith("prob") else v
     return res
 
 
@@ -236,8 +243,8 @@ class DetectionFileProvider:
                 cur_cls = df.cls_info(packed["rows"][f], token)
                 time_lag = float(packed["prev_det_boxes"][f, 0, 9])
                 annos, dead_idx, keep = formats.annos_from_decode(
-                    prev_cls, cur_cls, fields["prev_state"][f].numpy(), fields["fn_score"][f].numpy(),
-                    fields["det_state"][f].numpy(), fields["det_score"][f].numpy(), token, time_lag)
+                    prev_cls, cur_cls, fields["prev_state"][f].numpy(), fields["fn_dead_prob"][f].numpy(),
+                    fields["det_state"][f].numpy(), fields["det_fp_prob"][f].numpy(), token, time_lag)
                 if len(prev_cls) > 0:
                     dead_tracker.setdefault(prev_token, {"dead_idx": [], "keep_idx": []})["dead_idx"].extend(dead_idx)
                 if len(cur_cls) > 0:

@@ -36,8 +36,8 @@ def run_class_sequence(model, frames, maps_for, det_type=None, device="cuda:0"):
             dec = {k: v[0].cpu().numpy() for k, v in model.decode(m1, m2, [n_prev], [n_det]).items()}
         time_lag = float(ex["prev_det_boxes"][0, 0, 9])
         annos, dead_idx, keep = formats.annos_from_decode(ex["prev_cls_det_boxes"], ex["cls_det_boxes"],
-                                                          dec["prev_state"], dec["fn_score"], dec["det_state"],
-                                                          dec["det_score"], token, time_lag)
+                                                          dec["prev_state"], dec["fn_dead_prob"], dec["det_state"],
+                                                          dec["det_fp_prob"], token, time_lag)
         if n_prev > 0:
             dead_tracker.setdefault(prev_token, {"dead_idx": [], "keep_idx": []})["dead_idx"].extend(dead_idx)
         if n_det > 0:

@@ -231,13 +231,38 @@ class Shasta(nn.Module):
         self._w16_key = key
 
     def _workspace(self, batch, device):
+        """One scratch buffer per (batch size, device). Workspaces are kept for the life of the model: captured CUDA
+        graphs (the model's own and the class lanes') hold their addresses, so evicting one would leave a graph
+        replaying into freed memory. ``release_workspaces()`` drops them together with the graphs."""
         k = (batch, device)
         ws = self._ws.get(k)
         if ws is None:
-            if len(self._ws) > 8:
-                self._ws.clear()
             ws = self._ws[k] = _Workspace(batch, self.max_obj, device)
         return ws
+
+    def release_workspaces(self):
+        """Frees every workspace and every captured graph that references one (call between workloads of very
+        different batch sizes)."""
+        self._graphs.clear()
+        self._ws.clear()
+        self._pipe = None
+
+    def invalidate_packed(self):
+        """Forces a re-pack of the kernel-side weight cache on the next call. The cache is keyed on each parameter's
+        (data_ptr, _version); in-place updates through ``param.data`` (EMA, some AMP / clipping wrappers) do NOT bump
+        ``_version`` - call this after such an update (``load_state_dict`` and ``train()`` do it automatically)."""
+        self._pack_key = None
+        self._w16_key = None
+        self._graphs.clear()
+
+    def load_state_dict(self, *args, **kwargs):
+        res = super().load_state_dict(*args, **kwargs)
+        self.invalidate_packed()
+        return res
+
+    def train(self, mode=True):
+        self.invalidate_packed()
+        return super().train(mode)
 
     # ------------------------------------------------------------------------------------------
     def affinity(self, bev, prev_bev, det_boxes, prev_det_boxes):
@@ -279,6 +304,11 @@ class Shasta(nn.Module):
 
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.aff.parameters()):
             # training configuration: same forward kernels on a private workspace + CUDA backward (training.py)
+            if (bev.requires_grad or prev_bev.requires_grad) and not _cabi.lib_has("shasta_backward_maps_f32"):
+                # the reference trains shared_conv with the head (train.py:184-191 freezes backbone and neck only)
+                raise _cabi.ShastaLibraryError(
+                    "the BEV maps require grad (shared_conv is being trained) but this build of libshasta_b200 has no "
+                    "map-gradient kernels: shared_conv would silently stay at its initialisation")
             from .training import affinity_with_grad
             m1, m2 = affinity_with_grad(self, bev, prev_bev, det_c, prev_c)
         else:
@@ -391,8 +421,9 @@ class Shasta(nn.Module):
     def decode(self, matched1, matched2, n_prev, n_det, out=None):
         """The thresholded argmax of the eval loop (tools/nusc_shasta/eval.py:126-181) for a whole batch on the device:
         returns int32/float32 CUDA tensors of shape (B, M): ``prev_state`` (0 keep, 1 dead, 2 FN, -1 padding),
-        ``prev_argmax``, ``fn_score`` (1 - matched[n,-2] for FN rows), ``det_state`` (0 keep, 1 newborn, 2 dropped FP,
-        -1 padding), ``det_argmax``, ``det_score`` (ref_detection_score). ``n_prev`` / ``n_det``: real counts per
+        ``prev_argmax``, ``fn_dead_prob`` (matched1[n,-2] of FN rows), ``det_state`` (0 keep, 1 newborn, 2 dropped FP,
+        -1 padding), ``det_argmax``, ``det_fp_prob`` (matched2[-1,k] of kept detections; the reference's
+        ``ref_detection_score`` is ``1 - value``, formed on the host in double). ``n_prev`` / ``n_det``: real counts per
         frame pair (sequence or int32 tensor). ``out``: optional contiguous (6, B, M) int32 CUDA tensor the six fields
         are written into in the order above (float fields bit-cast); the returned dict then holds views of it."""
         if not matched1.is_cuda or not matched2.is_cuda:
@@ -402,20 +433,20 @@ class Shasta(nn.Module):
         m1, m2 = matched1.contiguous(), matched2.contiguous()
         npv = torch.as_tensor(n_prev, dtype=torch.int32).to(dev)
         ndv = torch.as_tensor(n_det, dtype=torch.int32).to(dev)
-        fields = ("prev_state", "prev_argmax", "fn_score", "det_state", "det_argmax", "det_score")
+        fields = ("prev_state", "prev_argmax", "fn_dead_prob", "det_state", "det_argmax", "det_fp_prob")
         if out is None:
-            out = {k: torch.empty((B, M), dtype=(torch.float32 if k.endswith("score") else torch.int32), device=dev)
+            out = {k: torch.empty((B, M), dtype=(torch.float32 if k.endswith("prob") else torch.int32), device=dev)
                    for k in fields}
         else:
             if (tuple(out.shape) != (6, B, M) or out.dtype != torch.int32 or out.device != dev
                     or not out.is_contiguous()):
                 raise ValueError("decode: out must be a contiguous (6, %d, %d) int32 tensor on %s" % (B, M, dev))
-            out = {k: (out[i].view(torch.float32) if k.endswith("score") else out[i]) for i, k in enumerate(fields)}
+            out = {k: (out[i].view(torch.float32) if k.endswith("prob") else out[i]) for i, k in enumerate(fields)}
         with torch.cuda.device(dev):
             rc = _cabi.lib().shasta_decode_f32(
                 m1.data_ptr(), m2.data_ptr(), npv.data_ptr(), ndv.data_ptr(), B, M, out["prev_state"].data_ptr(),
-                out["prev_argmax"].data_ptr(), out["fn_score"].data_ptr(), out["det_state"].data_ptr(),
-                out["det_argmax"].data_ptr(), out["det_score"].data_ptr(),
+                out["prev_argmax"].data_ptr(), out["fn_dead_prob"].data_ptr(), out["det_state"].data_ptr(),
+                out["det_argmax"].data_ptr(), out["det_fp_prob"].data_ptr(),
                 ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _cabi.check(rc, "shasta_decode_f32")
         return out

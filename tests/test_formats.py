@@ -95,16 +95,12 @@ def test_annos_from_decode_follows_the_eval_loop():
     m2[2, 3] = 0.9
     want = O.decode(m1, m2, n_prev, n_det)
     prev_state = [1 if n in want["dead"] else 2 if n in want["fn"] else 0 for n in range(n_prev)]
-    fn_score = [0.0] * n_prev
-    for n, s in zip(want["fn"], want["fn_score"]):
-        fn_score[n] = s
+    fn_score = [float(m1[n, -2]) for n in range(n_prev)]       # raw matched1[n,-2]: the helper forms 1 - value
     det_state = [0 if k in want["keep_dets"] else 2 for k in range(n_det)]
     for k, nb in zip(want["keep_dets"], want["newborn"]):
         if nb:
             det_state[k] = 1
-    det_score = [0.0] * n_det
-    for k, s in zip(want["keep_dets"], want["det_score"]):
-        det_score[k] = s
+    det_score = [float(m2[-1, k]) for k in range(n_det)]      # raw matched2[-1,k]
     mk = lambda i: {"translation": [float(i), 2.0 * i, 0.0], "velocity": [1.0, -1.0], "detection_name": "car",  # noqa: E731
                     "detection_score": 0.5}
     prev_cls, cur_cls = [mk(i) for i in range(n_prev)], [mk(10 + i) for i in range(n_det)]

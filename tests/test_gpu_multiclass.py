@@ -29,15 +29,15 @@ def _oracle_states(m1, m2, n_prev, n_det, M):
     d = O.decode(m1, m2, n_prev, n_det)
     prev_state = np.full(M, -1, np.int32)
     prev_state[:n_prev] = [1 if n in d["dead"] else 2 if n in d["fn"] else 0 for n in range(n_prev)]
-    fn_score = np.zeros(M, np.float32)
-    for n, s in zip(d["fn"], d["fn_score"]):
-        fn_score[n] = s
+    fn_score = np.zeros(M, np.float32)        # raw matched1[n,-2] of the FN rows (the kernel stores the raw value)
+    for n in d["fn"]:
+        fn_score[n] = float(m1[n, -2])
     det_state = np.full(M, -1, np.int32)
     det_state[:n_det] = 2
     det_score = np.zeros(M, np.float32)
-    for k, nb, s in zip(d["keep_dets"], d["newborn"], d["det_score"]):
+    for k, nb in zip(d["keep_dets"], d["newborn"]):
         det_state[k] = 1 if nb else 0
-        det_score[k] = s
+        det_score[k] = float(m2[-1, k])         # raw matched2[-1,k]
     return prev_state, fn_score, det_state, det_score
 
 
@@ -65,9 +65,9 @@ def test_three_class_sequence_batch_matches_oracle():
                 assert np.array_equal(got["prev_state"][f].numpy()[:n_prev], ps[:n_prev]), (name, s, f)
                 assert np.array_equal(got["det_state"][f].numpy()[:n_det], ds[:n_det]), (name, s, f)
                 fn_rows = ps[:n_prev] == 2
-                assert np.allclose(got["fn_score"][f].numpy()[:n_prev][fn_rows], fs[:n_prev][fn_rows], atol=1e-4)
+                assert np.allclose(got["fn_dead_prob"][f].numpy()[:n_prev][fn_rows], fs[:n_prev][fn_rows], atol=1e-4)
                 kept = ds[:n_det] != 2
-                assert np.allclose(got["det_score"][f].numpy()[:n_det][kept], sc[:n_det][kept], atol=1e-4)
+                assert np.allclose(got["det_fp_prob"][f].numpy()[:n_det][kept], sc[:n_det][kept], atol=1e-4)
                 decisions += int((ps[:n_prev] > 0).sum() + (ds[:n_det] > 0).sum())
     assert decisions > 0, "weights not peaky enough: no dead / FN / newborn / FP decision was exercised"
 

@@ -648,11 +648,12 @@ def _check_decode(m1, m2, n_prev, n_det):
         assert np.all(ps[b, n_prev[b]:] == -1) and np.all(ds[b, n_det[b]:] == -1)
         assert pa[b, :n_prev[b]].tolist() == want["row_argmax"]
         assert da[b, :n_det[b]].tolist() == want["col_argmax"]
-        assert np.array_equal(fs[b, want["fn"]], np.array(want["fn_score"], np.float64).astype(np.float32))
+        # the kernel stores the raw matched values; ref_detection_score = 1 - value in double must equal the oracle's
+        assert (1.0 - fs[b, want["fn"]].astype(np.float64)).tolist() == want["fn_score"]
         keep = [k for k in range(n_det[b]) if ds[b, k] in (0, 1)]
         assert keep == want["keep_dets"]
         assert [bool(ds[b, k] == 1) for k in keep] == want["newborn"]
-        assert np.array_equal(dsc[b, keep], np.array(want["det_score"], np.float64).astype(np.float32))
+        assert (1.0 - dsc[b, keep].astype(np.float64)).tolist() == want["det_score"]
 
 
 def test_decode_on_planted_matrices():

@@ -62,13 +62,13 @@ def _cpu_chain(weights, frames, maps, M, pc_start):
         d = O.decode(m1[0], m2[0], n_prev, n_det)
         prev_state = [1 if n in d["dead"] else 2 if n in d["fn"] else 0 for n in range(n_prev)]
         fn_score = np.zeros(max(n_prev, 1), np.float32)
-        for n, s in zip(d["fn"], d["fn_score"]):
-            fn_score[n] = s
+        for n in d["fn"]:
+            fn_score[n] = float(m1[0][n, -2])     # raw value: annos_from_decode forms 1 - value in double
         det_state = [2] * n_det
         det_score = np.zeros(max(n_det, 1), np.float32)
-        for k, nb, s in zip(d["keep_dets"], d["newborn"], d["det_score"]):
+        for k, nb in zip(d["keep_dets"], d["newborn"]):
             det_state[k] = 1 if nb else 0
-            det_score[k] = s
+            det_score[k] = float(m2[0][-1, k])
         annos, dead_idx, keep = formats.annos_from_decode(ex["prev_cls_det_boxes"], ex["cls_det_boxes"], prev_state,
                                                           fn_score, det_state, det_score, token,
                                                           float(ex["prev_det_boxes"][0, 0, 9]))

@@ -81,7 +81,7 @@ def test_decode_fields_bitcast():
     block = torch.zeros((2, 6, 3), dtype=torch.int32)
     block[:, 2] = torch.tensor([0.25, 0.5, 1.0]).view(torch.int32)
     f = multiclass.decode_fields(block)
-    assert f["fn_score"].dtype == torch.float32 and torch.equal(f["fn_score"][1], torch.tensor([0.25, 0.5, 1.0]))
+    assert f["fn_dead_prob"].dtype == torch.float32 and torch.equal(f["fn_dead_prob"][1], torch.tensor([0.25, 0.5, 1.0]))
     assert f["prev_state"].dtype == torch.int32 and set(f) == set(multiclass.DECODE_FIELDS)
 
 
