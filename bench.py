@@ -57,6 +57,12 @@ def parse():
     ap.add_argument("--bf16", action="store_true", help="bf16 mode (shasta_forward_bf16): separate tolerance, dtype bf16")
     ap.add_argument("--opt", action="append", default=[], metavar="ID=VALUE",
                     help="shasta_set_option(ID, VALUE) before the run (experiment knob, repeatable)")
+    ap.add_argument("--workload", default="head", choices=["head", "multiclass"],
+                    help="head = the headline metric (BASELINE.json configs[1]); multiclass = configs[2]: the 10-class "
+                         "sequence batch, scenes sharded over the ranks (tools/bench_multiclass.py, its own JSON line)")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_multiclass as _bm
+    _bm.add_args(ap)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -224,21 +230,48 @@ def cpu_reference_run(a, seconds, weights_state=None, sample_pairs=1):
     det = torch.from_numpy(d["det_boxes"])
     prev = torch.from_numpy(d["prev_det_boxes"])
     times = []
+    fwd, kind = cpu_forward_fn(M, pc_start, weights_state)
     with torch.no_grad():
-        O.forward(weights_state, bev, prev_bev, det.clone(), prev, pc_start=pc_start)  # warm-up
+        fwd(bev, prev_bev, det.clone(), prev)  # warm-up
         t_end = time.perf_counter() + seconds
         while time.perf_counter() < t_end or len(times) < 3:
             t0 = time.perf_counter()
-            O.forward(weights_state, bev, prev_bev, det.clone(), prev, pc_start=pc_start)
+            fwd(bev, prev_bev, det.clone(), prev)
             times.append(time.perf_counter() - t0)
             if len(times) >= 200:
                 break
     med = float(np.median(times))
-    return {"value": sample_pairs / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d iterations of %d frame pair(s), M=%d, %dx%d maps, median %.1f ms each; oracle/shasta_oracle.py "
+    return {"value": sample_pairs / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": "%d iterations of %d frame pair(s), M=%d, %dx%d maps, median %.1f ms each; %s "
                       "(reference formulation, materialised pair tensors), torch %s CPU fp32"
-                      % (len(times), sample_pairs, M, hw, hw, med * 1e3, torch.__version__),
+                      % (len(times), sample_pairs, M, hw, hw, med * 1e3,
+                         "the unmodified reference head (oracle/ref_loader.py)" if kind == "reference"
+                         else "oracle/shasta_oracle.py", torch.__version__),
             "ms_per_frame_pair": med * 1e3 / sample_pairs}
+
+
+def cpu_forward_fn(M, pc_start, weights_state):
+    """The CPU implementation of the path that the reference arm / cpu_baseline time: the UNMODIFIED reference
+    (oracle/ref_loader.py, kind "reference") where its tree is present (SHASTA_REF_ROOT, /root/reference or
+    baseline/_ref), else the oracle port (kind "port" - bit-identical to it, tests/test_oracle*.py)."""
+    from oracle import ref_loader
+    if not ref_loader.available() and os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "det3d")):
+        ref_loader.REF_ROOT = os.path.join(ROOT, "baseline", "_ref")
+    if ref_loader.available():
+        try:
+            model = ref_loader.build_reference_head(M, 3, pc_start=pc_start)
+            model.load_state_dict(weights_state, strict=False)
+
+            def fwd(bev, prev_bev, det, prev):
+                return ref_loader.run_reference(model, bev, prev_bev, det, prev)[:2]
+            return fwd, "reference"
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("reference tree present but not loadable (%s): timing the oracle port\n" % e)
+    from oracle import shasta_oracle as O
+
+    def fwd(bev, prev_bev, det, prev):
+        return O.forward(weights_state, bev, prev_bev, det, prev, pc_start=pc_start)
+    return fwd, "port"
 
 
 def run_reference_arm(a):
@@ -253,8 +286,9 @@ def run_reference_arm(a):
             "ms_per_step": t["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": config_dict(a, {"frame_pairs_per_step_per_gpu": 1,
-                                      "note": "reference path on host cores (CPU oracle port); one frame pair per step"}),
-            "cpu_baseline": {"value": t["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                                      "note": "reference path on host cores (%s); one frame pair per step"
+                                              % ("unmodified reference" if t["kind"] == "reference" else "CPU oracle port")}),
+            "cpu_baseline": {"value": t["value"], "unit": UNIT, "cores": res["cores"], "kind": t["kind"],
                              "sample": "%d steps x 1 frame pair after %d warm-up" % (steps, warm)},
             "e2e": {"value": t["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -279,14 +313,15 @@ def cpu_reference_timed(a, steps, warm):
         w[k] = (torch.rand(shp) * 2 - 1) / max(fan_in, 1) ** 0.5
     det = torch.from_numpy(d["det_boxes"])
     prev = torch.from_numpy(d["prev_det_boxes"])
+    fwd, kind = cpu_forward_fn(M, pc_start, w)
     with torch.no_grad():
         for _ in range(warm):
-            O.forward(w, bev, prev_bev, det.clone(), prev, pc_start=pc_start)
+            fwd(bev, prev_bev, det.clone(), prev)
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.forward(w, bev, prev_bev, det.clone(), prev, pc_start=pc_start)
+            fwd(bev, prev_bev, det.clone(), prev)
         dt = time.perf_counter() - t0
-    return {"value": steps / dt, "ms_per_step": dt / steps * 1e3}
+    return {"value": steps / dt, "ms_per_step": dt / steps * 1e3, "kind": kind}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -395,6 +430,10 @@ def main():
     if a.train:
         run_train(a)
         return
+    if a.workload == "multiclass":
+        import bench_multiclass
+        bench_multiclass.run(a)
+        return
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -408,6 +447,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
+        pin_rank_to_cores(local_rank, world)
 
     from shasta_b200 import _cabi, sharding
     lib = _cabi.lib()
@@ -426,10 +466,12 @@ def main():
     B, M = a.batch, a.max_obj
     n_prev = torch.from_numpy(d["n_prev"].astype(np.int32)).to(device)
     n_det = torch.from_numpy(d["n_det"].astype(np.int32)).to(device)
-    # multi-GPU: every step's compact decode output (4 int32 + 2 float32 planes of (B,M)) lands in one block that is
-    # all-gathered ONCE at the end of the timed region - the only collective of the path
-    dec_pack = torch.empty((a.steps, 6, B, M), dtype=torch.int32, device=device) if world > 1 else None
-    dec_one = torch.empty((6, B, M), dtype=torch.int32, device=device) if world > 1 else None
+    # every step ends with the device decode (eval.py:126-181) of its affinities; the compact result (4 int32 + 2
+    # float32 planes of (B,M)) lands in one block per rank. The work per step is the SAME at every N; with N > 1 the
+    # blocks of all ranks are all-gathered ONCE at the end of the timed region - the only collective of the path
+    # The decode is fused into the softmax kernels (shasta_forward_decode_f32) and writes straight into this step's
+    # slot of the ring (device-side call counter): no decode kernel, no copy.
+    dec_pack = torch.empty((a.steps, 6, B, M), dtype=torch.int32, device=device)
     # one CUDA graph per step: box refresh + forward (+ decode when results are gathered across ranks); the model's own
     # per-call graph cache is not needed on top of it
     inner = bool(os.environ.get("BENCH_INNER_GRAPH"))   # A/B knob: the model's per-call graph instead of the step graph
@@ -443,26 +485,25 @@ def main():
         mk = model if k == 0 else build_model(a, pc_start, device)
         mk.cuda_graphs = model.cuda_graphs
         lanes.append({"model": mk, "det": det if k == 0 else det0.clone(),
-                      "dec": dec_one if k == 0 else (torch.empty_like(dec_one) if dec_one is not None else None),
+                      "ring": dec_pack if k == 0 else torch.empty_like(dec_pack),
+                      "counter": torch.zeros(1, dtype=torch.int32, device=device),
                       "stream": torch.cuda.current_stream() if k == 0 else torch.cuda.Stream(), "g": None, "out": None})
 
     def lane_body(ln):
         ln["det"].copy_(det0)  # fresh boxes every step (the forward back-projects det_boxes in place)
-        m1, m2 = ln["model"].affinity(bev, prev_bev, ln["det"], prev)
-        if world > 1:
-            o = [ln["dec"][i].data_ptr() for i in range(6)]  # prev_state, prev_argmax, fn_score, det_state, ...
-            rc = lib.shasta_decode_f32(m1.data_ptr(), m2.data_ptr(), n_prev.data_ptr(), n_det.data_ptr(), B, M,
-                                       o[0], o[1], o[2], o[3], o[4], o[5],
-                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-            _cabi.check(rc, "decode")
-        return m1, m2
+        if a.bf16:   # bf16 mode: separate decode kernel into the latest slot
+            m1, m2 = ln["model"].affinity(bev, prev_bev, ln["det"], prev)
+            ln["model"].decode(m1, m2, n_prev, n_det, out=ln["ring"][0])
+            return m1, m2
+        return ln["model"].affinity(bev, prev_bev, ln["det"], prev,
+                                    decode={"n_prev": n_prev, "n_det": n_det, "out": ln["ring"], "counter": ln["counter"]})
 
     def step_body():
         return lane_body(lanes[0])
 
     counter = [0]
 
-    def step(store=None):
+    def step():
         ln = lanes[counter[0] % nl]
         counter[0] += 1
         if a.no_graph or inner:
@@ -479,11 +520,7 @@ def main():
                 ln["g"] = g
             with torch.cuda.stream(ln["stream"]):
                 ln["g"].replay()
-                if store is not None:
-                    store.copy_(ln["dec"])   # this step's compact decode output
             return ln["out"]
-        if store is not None:
-            store.copy_(ln["dec"])
         return out
 
     def barrier():
@@ -516,7 +553,7 @@ def main():
         for ln in lanes[1:]:
             ln["stream"].wait_event(e0)
         for it in range(a.steps):
-            m1, m2 = step(dec_pack[it] if world > 1 else None)
+            m1, m2 = step()
         for ln in lanes[1:]:
             torch.cuda.current_stream().wait_stream(ln["stream"])
         if world > 1:  # NCCL only gathers the per-rank results
@@ -537,8 +574,6 @@ def main():
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
             ms = float(tms.item())
         value = world * B * a.steps / (ms / 1e3)
-        if world > 1:
-            launches_per_step += 1  # decode_kernel
 
         # ---- per-kernel durations, live, same loop with event records between the kernels -------------------
         model.kernel_flags = a.flags | 0x100
@@ -555,7 +590,7 @@ def main():
         # ---- end to end through the public API with host buffers -----------------------------------------------
         e2e = None
         if not a.no_e2e:
-            e2e = run_e2e(a, model, bev, prev_bev, det0, prev, device, dist, world)
+            e2e = run_e2e(a, model, bev, prev_bev, det0, prev, device, dist, world, n_prev, n_det)
 
     peaks = {}
     try:
@@ -565,10 +600,14 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     dom = max(stages, key=stages.get)
-    ab = algorithmic_bytes_anchor_hidden(M, B, a.bf16 and (a.anchor_path == 2 or (a.anchor_path == 0 and B > 4)))
+    tc_path = a.anchor_path == 2 or (a.anchor_path == 0 and B > 4)
+    bf16_w = a.bf16 and tc_path
+    step_s = ms / a.steps / 1e3
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", 1391.5))   # dense bf16, sustained (a kernel inside a long step)
+    # ---- the HBM-bound kernel: aug_shape.i.0 weight stream ------------------------------------------------------
+    ab = algorithmic_bytes_anchor_hidden(M, B, bf16_w)
     ah_ms = stages["anchor_hidden"]
     achieved = ab / (ah_ms / 1e3) / 1e9 if ah_ms > 0 else 0.0
-    tc_path = a.anchor_path == 2 or (a.anchor_path == 0 and B > 4)
     traffic = None
     if tc_path and M == 200 and B == 64 and not a.bf16:   # dram bytes of one launch from the committed ncu capture
         try:
@@ -576,14 +615,38 @@ def main():
                 "anchor_hidden_tc2_kernel<64>"]["traffic_bytes_per_launch"]
         except Exception:  # noqa: BLE001
             traffic = None
-    roofline = {"kernel": ("anchor_hidden_bf16_kernel (aug_shape.i.0, 0.51 GB of bf16 weights)" if a.bf16 else
-                           "anchor_hidden_tc2_kernel<64> (aug_shape.i.0, the 1.03 GB weight stream)") if tc_path
-                else "anchor_hidden_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ab, "ms_per_launch": ah_ms, "dominant_stage_by_time": dom,
-                "stage_ms": stages, "step_share": ah_ms / max(sum(stages.values()), 1e-9),
-                "path_bytes_per_step": path_bytes(M, B, a.hw, a.bf16 and tc_path),
-                "path_hbm_frac": path_bytes(M, B, a.hw, a.bf16 and tc_path) / (ms / a.steps / 1e3) / 1e9 / hbm_peak}
+    hbm_kernel = {"kernel": ("anchor_hidden_bf16_kernel (aug_shape.i.0, 0.51 GB of bf16 weights)" if a.bf16 else
+                             "anchor_hidden_tc2_kernel<64> (aug_shape.i.0, the 1.03 GB weight stream)") if tc_path
+                  else "anchor_hidden_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                  "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": ab,
+                  "ms_per_launch": ah_ms, "step_share": ah_ms / max(sum(stages.values()), 1e-9)}
+    # ---- the pairwise kernel (largest stage by time at the default configuration): tensor pipe -------------------
+    # algorithmic flops per pair (decomposed formulation): outer sum + ReLU over the 144 first-layer
+    # columns, the three second layers, the third / fourth layers, the hand-designed residuals
+    T = M + 2
+    flop_pair = 2 * (40 * 20 + 20 * 10 + 10) + 2 * (72 * 18 + 18 * 3) + 2 * (32 * 8 + 8) + 2 * 144 + 30
+    pw_flop = float(B) * T * T * flop_pair
+    pw_ms = stages["pairwise"]
+    pw_tf = pw_flop / (pw_ms / 1e3) / 1e12 if pw_ms > 0 else 0.0
+    # the bound this kernel actually runs against (tools/micro/mma_rate.cu, profiles/README.md): a tcgen05.mma with
+    # M = 128, N <= 32 and a TMEM A operand issues every 32.6 clocks; 54 of them per 128-pair tile (3xTF32)
+    sm_mhz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+    tiles = B * ((T + 7) // 8) * ((T + 15) // 16)
+    mma_floor_ms = tiles * 54 * 32.6 / 148.0 / (sm_mhz * 1e3)
+    pair_kernel = {"kernel": "pairwise_tc_kernel<false> (second pairwise layers on tcgen05, 3xTF32)", "bound": "tensor",
+                   "achieved": pw_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": pw_tf / tensor_peak,
+                   "traffic": None, "algorithmic_flop_per_launch": pw_flop, "ms_per_launch": pw_ms,
+                   "step_share": pw_ms / max(sum(stages.values()), 1e-9),
+                   "mma_issue_floor_ms": mma_floor_ms, "frac_of_mma_issue_floor": mma_floor_ms / pw_ms if pw_ms > 0 else None,
+                   "note": "small-N tf32 UMMAs are issue-bound, not FLOP-bound: 32.6 clk per instruction (measured), "
+                           "so the dense bf16 peak is the contract's denominator, the issue floor the attainable one"}
+    pb = path_bytes(M, B, a.hw, bf16_w)
+    dominant = pair_kernel if dom == "pairwise" else hbm_kernel
+    roofline = dict(dominant)
+    roofline.update({"peak_source": peak_src, "dominant_stage_by_time": dom, "stage_ms": stages,
+                     # whole path against the HBM roofline (bytes(M,B) = W(M) + B IO(M) over the step time)
+                     "path_bytes_per_step": pb, "path_hbm_gbs": pb / step_s / 1e9, "path_hbm_frac": pb / step_s / 1e9 / hbm_peak,
+                     "kernels": {"pairwise": pair_kernel, "anchor_hidden": hbm_kernel}})
 
     if rank == 0:
         cpu = None
@@ -601,7 +664,20 @@ def main():
         dist.destroy_process_group()
 
 
-def run_e2e(a, model, bev, prev_bev, det0, prev, device, dist, world):
+def pin_rank_to_cores(local_rank, world):
+    """One slice of the host cores per rank: the e2e path is host-driven (pinned buffers, per-step enqueue), and N
+    ranks time-sharing all cores double the per-step enqueue time at N = 8 (round-1 SCALE record)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world
+        if per >= 1:
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]))
+            torch.set_num_threads(max(1, per))
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def run_e2e(a, model, bev, prev_bev, det0, prev, device, dist, world, n_prev=None, n_det=None):
     """Shasta.forward(example) with pinned HOST tensors: per step the boxes go H2D, the gather kernel samples the
     host-resident BEV maps over PCIe (zero-copy, only the taps move), matched1/matched2 come back D2H."""
     B, M = a.batch, a.max_obj
@@ -617,10 +693,12 @@ def run_e2e(a, model, bev, prev_bev, det0, prev, device, dist, world):
     NBUF = 3
     sets = [{"det": h_det0.clone().pin_memory(),
              "m1": torch.empty((B, M, M + 2), dtype=torch.float32, pin_memory=True),
-             "m2": torch.empty((B, M + 2, M), dtype=torch.float32, pin_memory=True), "ev": None} for _ in range(NBUF)]
+             "m2": torch.empty((B, M + 2, M), dtype=torch.float32, pin_memory=True),
+             "dec": torch.empty((6, B, M), dtype=torch.int32, pin_memory=True),
+             "dec_dev": torch.empty((6, B, M), dtype=torch.int32, device=device), "ev": None} for _ in range(NBUF)]
     counter = [0]
 
-    def step():
+    def step(decode):
         st = sets[counter[0] % NBUF]
         counter[0] += 1
         if st["ev"] is not None:
@@ -629,39 +707,56 @@ def run_e2e(a, model, bev, prev_bev, det0, prev, device, dist, world):
         example = {"det_boxes": st["det"], "prev_det_boxes": h_prev, "bev_feature": h_bev,
                    "prev_bev_feature": h_prev_bev}
         m1, m2, _ = model(example, train_mode=False)
-        st["m1"].copy_(m1, non_blocking=True)
-        st["m2"].copy_(m2, non_blocking=True)
+        if decode:   # what the tracker downstream consumes: the thresholded argmax of eval.py:126-181 (0.3 MB)
+            model.decode(m1, m2, n_prev, n_det, out=st["dec_dev"])
+            st["dec"].copy_(st["dec_dev"], non_blocking=True)
+        else:
+            st["m1"].copy_(m1, non_blocking=True)
+            st["m2"].copy_(m2, non_blocking=True)
         st["ev"] = torch.cuda.Event()
         st["ev"].record()
 
-    for _ in range(3):
-        step()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(a.steps):
-        step()
-    enqueue_ms = (time.perf_counter() - t0) * 1e3
-    e1.record()
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    ms = max(e0.elapsed_time(e1), wall * 1e3)
-    if dist is not None:
-        tms = torch.tensor([ms], device=device)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+    def timed(decode):
+        for _ in range(3):
+            step(decode)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(a.steps):
+            step(decode)
+        enqueue_ms = (time.perf_counter() - t0) * 1e3
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), wall * 1e3)
+        if dist is not None:
+            tms = torch.tensor([ms], device=device)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms, enqueue_ms
+
+    ms, enqueue_ms = timed(False)
     taps = 2 * B * 5 * M * 4 * 64 * 4
     h2d = 2 * B * M * 11 * 4 + taps
     d2h = B * (M * (M + 2) + (M + 2) * M) * 4 + B * M * 11 * 4
-    return {"value": world * B * a.steps / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "ms_per_step": ms / a.steps, "host_enqueue_ms_per_step": enqueue_ms / a.steps,
-            "note": "pinned host inputs; BEV maps sampled in place over PCIe (tap bytes counted), boxes copied, "
-                    "matched1/matched2 and the back-projected boxes copied back; box upload + gather of step i+1 "
-                    "overlap the other stages and the D2H copies of step i (side stream, two workspaces); a ring of "
-                    "%d pinned buffer sets, each reused only after its results reached the host" % NBUF}
+    res = {"value": world * B * a.steps / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": ms / a.steps, "host_enqueue_ms_per_step": enqueue_ms / a.steps,
+           "note": "pinned host inputs; BEV maps sampled in place over PCIe (tap bytes counted), boxes copied, "
+                   "matched1/matched2 and the back-projected boxes copied back; box upload + gather of step i+1 "
+                   "overlap the other stages and the D2H copies of step i (side stream, two workspaces); a ring of "
+                   "%d pinned buffer sets, each reused only after its results reached the host" % NBUF}
+    if n_prev is not None:
+        ms_d, enq_d = timed(True)
+        res["decode_terminated"] = {
+            "value": world * B * a.steps / (ms_d / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": 6 * B * M * 4 + B * M * 11 * 4, "ms_per_step": ms_d / a.steps,
+            "host_enqueue_ms_per_step": enq_d / a.steps,
+            "note": "same inputs; the step ends with the device decode (eval.py:126-181) and only its (6,B,M) block "
+                    "and the back-projected boxes go back to the host - what the tracker consumes"}
+    return res
 
 
 if __name__ == "__main__":

@@ -259,6 +259,28 @@ SHASTA_API int shasta_forward_bf16(const shasta_params_t* host_params, const flo
                         int batch, const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes,
                         float* matched1, float* matched2, uint32_t flags, shasta_stream_t stream);
 
+/* shasta_forward_f32 with the consumer decode (tools/nusc_shasta/eval.py:126-181; see shasta_decode_f32 below) FUSED
+ * into the softmax epilogues: the row-softmax kernels classify every previous object, the column-softmax
+ * kernel every detection, no separate decode kernel and no second pass over matched1 / matched2.
+ * `out` points at slot 0 of a ring of decode blocks, each 6 planes of (batch, max_obj) int32 in the order
+ * prev_state, prev_argmax, fn_dead_prob (float bits), det_state, det_argmax, det_fp_prob (float bits). With a device
+ * `counter` the call writes slot (*counter % nslots) and a one-thread kernel increments the counter afterwards, so a
+ * captured CUDA graph of the call fills consecutive slots on consecutive replays; counter == NULL: always slot 0.
+ * Results are identical to shasta_decode_f32 on the same matched1 / matched2. */
+typedef struct shasta_decode_out {
+  const int32_t* n_prev;   /* (batch) real previous-frame object counts */
+  const int32_t* n_det;    /* (batch) real detection counts */
+  int32_t* out;            /* ring slot 0 */
+  size_t slot_stride;      /* int32 elements between slots (>= 6 * batch * max_obj) */
+  int32_t nslots;          /* ring length (>= 1) */
+  int32_t* counter;        /* device call counter, or NULL */
+} shasta_decode_out_t;
+SHASTA_API int shasta_forward_decode_f32(const shasta_params_t* host_params, const float* packed, const float* bev,
+                              const float* prev_bev, float* det_boxes, const float* prev_det_boxes, int batch,
+                              const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes,
+                              float* matched1, float* matched2, uint32_t flags,
+                              const shasta_decode_out_t* host_decode, shasta_stream_t stream);
+
 /* First stage of shasta_forward_f32 on its own (a1-a2 for both frames, writing FEAT_* and, when the anchors path in
  * use for (max_obj, batch) wants them, FEATLO_*), so that a caller can run it on another stream: the gather of the
  * next batch (PCIe-bound when the BEV maps are host-resident and sampled in place) then overlaps the remaining stages

@@ -55,6 +55,14 @@ class ShastaGeom(ctypes.Structure):
     ]
 
 
+class ShastaDecodeOut(ctypes.Structure):
+    """Mirror of shasta_decode_out_t (fused decode ring of shasta_forward_decode_f32)."""
+    _fields_ = [
+        ("n_prev", ctypes.c_void_p), ("n_det", ctypes.c_void_p), ("out", ctypes.c_void_p),
+        ("slot_stride", ctypes.c_size_t), ("nslots", ctypes.c_int32), ("counter", ctypes.c_void_p),
+    ]
+
+
 # region ids (enum shasta_region)
 WS_FEAT_CUR, WS_FEAT_PREV, WS_BOX_CUR, WS_BOX_PREV, WS_HIDDEN_PART, WS_PROJ_PREV, WS_PROJ_CUR, WS_AUX_PREV, \
     WS_AUX_CUR, WS_COLNORM, WS_RESIDUAL, WS_LOGITS, WS_ANCHOR_BOX, WS_PROJ_CUR_T, WS_DPROJ_PREV, WS_DPROJ_CUR, WS_ANCH_H, \
@@ -92,6 +100,9 @@ SYMBOLS = {
     "shasta_aff_softmax_f32": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "shasta_forward_f32": (_i, [ctypes.POINTER(ShastaParams), _vp, _vp, _vp, _vp, _vp, _i,
                                 ctypes.POINTER(ShastaGeom), _vp, _sz, _vp, _vp, _u32, _vp]),
+    "shasta_forward_decode_f32": (_i, [ctypes.POINTER(ShastaParams), _vp, _vp, _vp, _vp, _vp, _i,
+                                       ctypes.POINTER(ShastaGeom), _vp, _sz, _vp, _vp, _u32,
+                                       ctypes.POINTER(ShastaDecodeOut), _vp]),
     "shasta_anchor_bf16_bytes": (_sz, [_i]),
     "shasta_pack_anchor_bf16": (_i, [ctypes.POINTER(ShastaParams), _vp, _sz, _vp]),
     "shasta_forward_bf16": (_i, [ctypes.POINTER(ShastaParams), _vp, _vp, _vp, _vp, _vp, _vp, _i,

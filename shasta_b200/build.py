@@ -21,7 +21,7 @@ def _stale(obj, src):
     if not os.path.exists(obj):
         return True
     t = os.path.getmtime(obj)
-    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "dense_tile.cuh"), os.path.join(HERE, "..", "include", "shasta_b200.h"), __file__]
+    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "dense_tile.cuh"), os.path.join(CSRC, "decode_fused.cuh"), os.path.join(HERE, "..", "include", "shasta_b200.h"), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

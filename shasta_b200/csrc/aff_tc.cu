@@ -21,6 +21,7 @@
 // outputs whose accumulator the workers drain directly into the global logits, and the row softmax is a separate
 // warp-per-row kernel over the L2-resident logits.
 #include "common.cuh"
+#include "decode_fused.cuh"
 #include "tc_common.cuh"
 
 namespace shasta {
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(kStream ? kAtStreamThreads : kAtThreads, 1)
 aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPlan plan, size_t tc_begin,
               size_t bias_off0, size_t bias_off1, size_t bias_off2, size_t bias_off3, size_t bias_off4,
               size_t bias_off5, int B, int M, const float* __restrict__ residual, float* __restrict__ logits,
-              float* __restrict__ matched1) {
+              float* __restrict__ matched1, DecodeArgs dec) {
   extern __shared__ uint8_t smem_raw[];
   const int T = M + 2, D = M + 2, RS = row_stride(M);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -353,18 +354,28 @@ aff_tc_kernel(const float* __restrict__ packed, const __grid_constant__ AffTcPla
       const int b = (int)(row / T), t = (int)(row % T);
       if (t >= M) continue;
       float* dst = matched1 + ((size_t)b * M + t) * D;
+      float best = -INFINITY, v_dead = -INFINITY, v_fn = -INFINITY;
+      int barg = 0x7fffffff;
+      const int nd = dec.n_prev ? dec.n_det[b] : 0;
 #pragma unroll
       for (int c = 0; c < kTC; ++c) {
         const int d = lane + 32 * c;
-        if (d < D) dst[d] = __fdiv_rn(v[i][c], sum[i]);
+        if (d < D) {
+          const float p = __fdiv_rn(v[i][c], sum[i]);
+          dst[d] = p;
+          if (d < nd && p > best) best = p, barg = d;
+          if (d == M) v_dead = p;
+          if (d == M + 1) v_fn = p;
+        }
       }
+      if (dec.n_prev) dec_row_finish(dec, dec_slot(dec), b, t, best, barg, v_dead, v_fn, lane);
     }
   }
 }
 
 // matched1[b][t][:] = softmax over d of logits[b][t][:], t < M: one warp per row, the row stays in registers (D <= 1024).
 __global__ void __launch_bounds__(256)
-row_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __restrict__ matched1) {
+row_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __restrict__ matched1, DecodeArgs dec) {
   constexpr int kC = kAffTcMaxD / 32;
   const int T = M + 2, D = M + 2, RS = row_stride(M);
   const int lane = threadIdx.x & 31;
@@ -388,17 +399,27 @@ row_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __rest
   }
   sum = warp_sum(sum);
   float* dst = matched1 + (size_t)r * D;
+  float best = -INFINITY, v_dead = -INFINITY, v_fn = -INFINITY;
+  int barg = 0x7fffffff;
+  const int nd = dec.n_prev ? dec.n_det[b] : 0;
 #pragma unroll
   for (int c = 0; c < kC; ++c) {
     const int d = lane + 32 * c;
-    if (d < D) dst[d] = __fdiv_rn(v[c], sum);
+    if (d < D) {
+      const float p = __fdiv_rn(v[c], sum);
+      dst[d] = p;
+      if (d < nd && p > best) best = p, barg = d;
+      if (d == M) v_dead = p;
+      if (d == M + 1) v_fn = p;
+    }
   }
+  if (dec.n_prev) dec_row_finish(dec, dec_slot(dec), b, t, best, barg, v_dead, v_fn, lane);
 }
 
 bool aff_tc_available(int M) { return M + 2 <= kAffTcMaxD; }
 
 int launch_aff_tc(const float* packed, int B, int M, const float* residual, float* logits, float* matched1,
-                  cudaStream_t s) {
+                  cudaStream_t s, const DecodeArgs& dec) {
   const PackLayout P = pack_layout(M);
   const AffTcPlan plan = aff_tc_plan(M);
   if (plan.npieces == 0) {
@@ -415,9 +436,9 @@ int launch_aff_tc(const float* packed, int B, int M, const float* residual, floa
     }
     aff_tc_kernel<true><<<grid, kAtStreamThreads, smem, s>>>(packed, plan, P.aff_tc_begin, P.aff_b[0], P.aff_b[1], P.aff_b[2],
                                                       P.aff_b[3], P.aff_b[4], P.aff_b[5], B, M, residual, logits,
-                                                      matched1);
+                                                      matched1, dec);
     SHASTA_CHECK_LAUNCH("aff_tc_kernel<streamed>");
-    row_softmax_kernel<<<(unsigned)(((long long)B * M + 7) / 8), 256, 0, s>>>(B, M, logits, matched1);
+    row_softmax_kernel<<<(unsigned)(((long long)B * M + 7) / 8), 256, 0, s>>>(B, M, logits, matched1, dec);
     SHASTA_CHECK_LAUNCH("row_softmax_kernel");
     return 0;
   }
@@ -429,7 +450,7 @@ int launch_aff_tc(const float* packed, int B, int M, const float* residual, floa
   }
   aff_tc_kernel<false><<<grid, kAtThreads, smem, s>>>(packed, plan, P.aff_tc_begin, P.aff_b[0], P.aff_b[1], P.aff_b[2],
                                                      P.aff_b[3], P.aff_b[4], P.aff_b[5], B, M, residual, logits,
-                                                     matched1);
+                                                     matched1, dec);
   SHASTA_CHECK_LAUNCH("aff_tc_kernel");
   return 0;
 }

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace shasta {
@@ -43,7 +45,9 @@ struct SideStream {
 // must not share fork / join events
 constexpr int kSidePerDevice = 8;
 static SideStream g_side[64][kSidePerDevice];
+static std::mutex g_side_mutex;   // callers on different host threads (one per stream) may ask for a slot concurrently
 static SideStream* side_stream(cudaStream_t main) {
+  std::lock_guard<std::mutex> lock(g_side_mutex);
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideStream* free_slot = nullptr;
@@ -282,10 +286,20 @@ int shasta_aff_softmax_f32(const float* packed, int batch, int max_obj, float* w
 static int forward_impl(const shasta_params_t* host_params, const float* packed, const void* w16, const float* bev,
                         const float* prev_bev, float* det_boxes, const float* prev_det_boxes, int batch,
                         const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes, float* matched1,
-                        float* matched2, uint32_t flags, shasta_stream_t stream) {
+                        float* matched2, uint32_t flags, shasta_stream_t stream,
+                        const shasta_decode_out_t* decode = nullptr) {
   int rc = check_params(host_params);
   if (rc) return rc;
   const int M = host_params->max_obj;
+  if (decode != nullptr) {
+    NOT_NULL(decode->n_prev);
+    NOT_NULL(decode->n_det);
+    NOT_NULL(decode->out);
+    if (decode->nslots < 1 || (decode->nslots > 1 && decode->slot_stride < (size_t)6 * batch * M)) {
+      set_error("decode ring: nslots must be >= 1 and slot_stride >= 6 * batch * max_obj");
+      return SHASTA_ERR_ARG;
+    }
+  }
   rc = check_dims(batch, M);
   if (rc) return rc;
   rc = check_geom(host_geom);
@@ -360,7 +374,7 @@ static int forward_impl(const shasta_params_t* host_params, const float* packed,
   rc = launch_pairwise(packed, batch, M, workspace, L, (int)((flags >> 4) & 15u), s);  // a5-a9
   if (rc) return rc;
   STAGE_MARK(5);
-  rc = launch_aff_softmax(packed, batch, M, workspace, L, matched1, matched2, s, ev ? ev[6] : nullptr);  // a10-a11
+  rc = launch_aff_softmax(packed, batch, M, workspace, L, matched1, matched2, s, ev ? ev[6] : nullptr, decode);  // a10-a11
   if (rc) return rc;
   STAGE_MARK(7);
 #undef STAGE_MARK
@@ -374,6 +388,16 @@ int shasta_forward_f32(const shasta_params_t* host_params, const float* packed, 
                        float* matched2, uint32_t flags, shasta_stream_t stream) {
   return forward_impl(host_params, packed, nullptr, bev, prev_bev, det_boxes, prev_det_boxes, batch, host_geom,
                       workspace, workspace_bytes, matched1, matched2, flags, stream);
+}
+
+int shasta_forward_decode_f32(const shasta_params_t* host_params, const float* packed, const float* bev,
+                              const float* prev_bev, float* det_boxes, const float* prev_det_boxes, int batch,
+                              const shasta_geom_t* host_geom, float* workspace, size_t workspace_bytes,
+                              float* matched1, float* matched2, uint32_t flags,
+                              const shasta_decode_out_t* host_decode, shasta_stream_t stream) {
+  NOT_NULL(host_decode);
+  return forward_impl(host_params, packed, nullptr, bev, prev_bev, det_boxes, prev_det_boxes, batch, host_geom,
+                      workspace, workspace_bytes, matched1, matched2, flags, stream, host_decode);
 }
 
 int shasta_forward_bf16(const shasta_params_t* host_params, const float* packed, const void* anchor_w_bf16,

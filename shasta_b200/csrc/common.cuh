@@ -366,7 +366,7 @@ int launch_project(const float* packed, int B, int M, float* ws, const WsLayout&
 int launch_pairwise(const float* packed, int B, int M, float* ws, const WsLayout& L, int variant,
                     cudaStream_t s);
 int launch_aff_softmax(const float* packed, int B, int M, float* ws, const WsLayout& L, float* matched1,
-                       float* matched2, cudaStream_t s, cudaEvent_t mid);
+                       float* matched2, cudaStream_t s, cudaEvent_t mid, const shasta_decode_out_t* decode = nullptr);
 int launch_backward(const shasta_params_t& p, const shasta_grads_t& g, const float* packed, int B, float* ws,
                     const WsLayout& L, const float* m1, const float* m2, const float* gm1, const float* gm2,
                     cudaStream_t s);

@@ -67,8 +67,9 @@ def write_detection_file(path, frames):
             if attr is not None and attr not in attrs:
                 attrs.append(attr)
             rows.append(list(b[:12]) + [info["detection_score"], formats.quaternion_yaw(np.array(b[6:10]))[0]])
-            cls_rows.append(list(info["translation"][:3]) + list(info["size"][:3]) + list(info["rotation"][:4]) +
-                            list(info["velocity"][:2]))
+            # cls_info fields the entry does not carry default to the det_path box (synthetic scenes)
+            cls_rows.append(list(info.get("translation", b[0:3])[:3]) + list(info.get("size", b[3:6])[:3]) +
+                            list(info.get("rotation", b[6:10])[:4]) + list(info.get("velocity", b[10:12])[:2]))
             cls_id.append(classes.index(name))
             attr_id.append(NO_ATTR if attr is None else attrs.index(attr))
             extra = {k: v for k, v in info.items() if k not in _CLS_KEYS}

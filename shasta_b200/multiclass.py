@@ -45,8 +45,12 @@ class ClassLane:
         # the forward back-projects the detections in place (shasta.py:270): work on a copy so that a provider's
         # buffers can be served again
         det_work.copy_(batch["det_boxes"])
-        m1, m2 = self.model.affinity(batch["bev"], batch["prev_bev"], det_work, batch["prev_det_boxes"])
-        self.model.decode(m1, m2, batch["n_prev"], batch["n_det"], out=dec_out)
+        if self.model.bf16:
+            m1, m2 = self.model.affinity(batch["bev"], batch["prev_bev"], det_work, batch["prev_det_boxes"])
+            self.model.decode(m1, m2, batch["n_prev"], batch["n_det"], out=dec_out)
+        else:   # the decode runs inside the softmax kernels (shasta_forward_decode_f32): no separate pass
+            self.model.affinity(batch["bev"], batch["prev_bev"], det_work, batch["prev_det_boxes"],
+                                decode={"n_prev": batch["n_prev"], "n_det": batch["n_det"], "out": dec_out})
 
     def step(self, batch):
         """``batch``: dict of CUDA tensors bev, prev_bev (B,H,W,64), det_boxes, prev_det_boxes (B,M,11), n_prev,

@@ -265,9 +265,15 @@ class Shasta(nn.Module):
         return super().train(mode)
 
     # ------------------------------------------------------------------------------------------
-    def affinity(self, bev, prev_bev, det_boxes, prev_det_boxes):
+    def affinity(self, bev, prev_bev, det_boxes, prev_det_boxes, decode=None):
         """Hot path from the channels-last maps: (B,H,W,64) x2, (B,M,11) x2 -> matched1, matched2.
-        ``det_boxes[:, :, :2]`` is back-projected in place (shasta.py:270)."""
+        ``det_boxes[:, :, :2]`` is back-projected in place (shasta.py:270).
+
+        ``decode`` (inference with device-resident inputs): dict(n_prev=, n_det= int32 CUDA tensors (B,), out= int32
+        CUDA tensor (nslots, 6, B, M) or (6, B, M), counter= optional int32 CUDA scalar). The consumer decode of
+        tools/nusc_shasta/eval.py:126-181 then runs inside the softmax kernels (``shasta_forward_decode_f32``) and fills
+        slot ``counter % nslots`` of ``out`` (fields as in ``Shasta.decode``); the counter is incremented on the device,
+        so a captured graph of the call fills consecutive slots on consecutive replays."""
         device = self.aff[0].weight.device
         if device.type != "cuda":
             raise _cabi.ShastaLibraryError("Shasta parameters are on %s: shasta_b200 has no CPU path" % device)
@@ -294,6 +300,9 @@ class Shasta(nn.Module):
         prev_bev = prev_bev if prev_bev.is_contiguous() else prev_bev.contiguous()
         if (not bev.is_cuda or not prev_bev.is_cuda) and (self.kernel_flags & FLAG_TMA_GATHER):
             raise _cabi.ShastaLibraryError("host-resident BEV maps need the LDG sampler (kernel_flags bit 0 clear)")
+        if decode is not None and (not bev.is_cuda or not prev_bev.is_cuda or (torch.is_grad_enabled() and self.training)):
+            raise _cabi.ShastaLibraryError("the fused decode is an inference option for device-resident maps; use "
+                                           "Shasta.decode on the outputs otherwise")
         if (self.pipeline_host_inputs and not self.bf16 and not bev.is_cuda and not prev_bev.is_cuda and not det_boxes.is_cuda
                 and not prev_det_boxes.is_cuda and not (self.kernel_flags & 0x100)
                 and not (torch.is_grad_enabled() and self.training)):
@@ -312,7 +321,7 @@ class Shasta(nn.Module):
             from .training import affinity_with_grad
             m1, m2 = affinity_with_grad(self, bev, prev_bev, det_c, prev_c)
         else:
-            m1, m2, _ = self._launch_forward(bev, prev_bev, det_c, prev_c, self._workspace(B, device))
+            m1, m2, _ = self._launch_forward(bev, prev_bev, det_c, prev_c, self._workspace(B, device), decode)
         if det_c is not det_boxes:
             if det_boxes.is_cuda:
                 det_boxes[:, :, :2] = det_c[:, :, :2]
@@ -451,7 +460,28 @@ class Shasta(nn.Module):
         _cabi.check(rc, "shasta_decode_f32")
         return out
 
-    def _launch_forward(self, bev, prev_bev, det_c, prev_c, ws):
+    def _decode_struct(self, decode, B, device):
+        M = self.max_obj
+        out = decode["out"]
+        if out.dtype != torch.int32 or out.device != device or not out.is_contiguous() or \
+                tuple(out.shape[-3:]) != (6, B, M) or out.dim() not in (3, 4):
+            raise ValueError("decode['out'] must be a contiguous int32 CUDA tensor of shape ([nslots,] 6, %d, %d)" % (B, M))
+        d = _cabi.ShastaDecodeOut()
+        for k in ("n_prev", "n_det"):
+            t = decode[k]
+            if t.dtype != torch.int32 or t.device != device or t.numel() != B or not t.is_contiguous():
+                raise ValueError("decode['%s'] must be a contiguous int32 CUDA tensor with %d entries" % (k, B))
+            setattr(d, k, t.data_ptr())
+        d.out = out.data_ptr()
+        d.nslots = out.shape[0] if out.dim() == 4 else 1
+        d.slot_stride = 6 * B * M
+        counter = decode.get("counter")
+        if counter is not None and (counter.dtype != torch.int32 or counter.device != device or counter.numel() != 1):
+            raise ValueError("decode['counter'] must be an int32 CUDA scalar")
+        d.counter = counter.data_ptr() if counter is not None else None
+        return d
+
+    def _launch_forward(self, bev, prev_bev, det_c, prev_c, ws, decode=None):
         """Enqueues the five forward kernels on the current stream. Inputs are validated, contiguous, boxes on the
         device; ``ws`` is the workspace the activations are left in (the backward pass reads them)."""
         device = det_c.device
@@ -464,6 +494,11 @@ class Shasta(nn.Module):
         use_bf16 = self.bf16 and not (torch.is_grad_enabled() and self.training)
         if use_bf16:
             self._ensure_bf16_anchor_weights(device)
+        dstruct = None
+        if decode is not None:
+            if use_bf16 or not bev.is_cuda:
+                raise _cabi.ShastaLibraryError("the fused decode needs fp32 mode and device-resident inputs")
+            dstruct = self._decode_struct(decode, B, device)
 
         def enqueue(m1, m2):
             with torch.cuda.device(device):
@@ -473,6 +508,11 @@ class Shasta(nn.Module):
                         ctypes.byref(self._cparams), self._packed.data_ptr(), self._w16.data_ptr(), bev.data_ptr(),
                         prev_bev.data_ptr(), det_c.data_ptr(), prev_c.data_ptr(), B, ctypes.byref(geom),
                         ws.buf.data_ptr(), ws.nbytes, m1.data_ptr(), m2.data_ptr(), int(self.kernel_flags), stream)
+                elif dstruct is not None:
+                    rc = lib.shasta_forward_decode_f32(
+                        ctypes.byref(self._cparams), self._packed.data_ptr(), bev.data_ptr(), prev_bev.data_ptr(),
+                        det_c.data_ptr(), prev_c.data_ptr(), B, ctypes.byref(geom), ws.buf.data_ptr(), ws.nbytes,
+                        m1.data_ptr(), m2.data_ptr(), int(self.kernel_flags), ctypes.byref(dstruct), stream)
                 else:
                     rc = lib.shasta_forward_f32(
                         ctypes.byref(self._cparams), self._packed.data_ptr(), bev.data_ptr(), prev_bev.data_ptr(),
@@ -485,7 +525,10 @@ class Shasta(nn.Module):
                      and not self.training and not torch.cuda.is_current_stream_capturing())
         if use_graph:
             key = (bev.data_ptr(), prev_bev.data_ptr(), det_c.data_ptr(), prev_c.data_ptr(), B, H, W,
-                   int(self.kernel_flags), ws.buf.data_ptr(), self._pack_key, use_bf16)
+                   int(self.kernel_flags), ws.buf.data_ptr(), self._pack_key, use_bf16,
+                   None if decode is None else (decode["out"].data_ptr(), tuple(decode["out"].shape),
+                                                decode["n_prev"].data_ptr(), decode["n_det"].data_ptr(),
+                                                None if decode.get("counter") is None else decode["counter"].data_ptr()))
             entry = self._graphs.get(key)
             if entry is None:
                 if len(self._graphs) >= 16:

@@ -713,3 +713,47 @@ def test_decode_large_rows_compaction():
 def test_decode_on_peaky_golden():
     c, pc_start, data, weights, g = load_golden("m20_32px_b3_peaky")
     _check_decode(g["matched1"], g["matched2"], [int(x) for x in data["n_prev"]], [int(x) for x in data["n_det"]])
+
+
+# ------------------------------------------------------------------------------------------------
+# decode fused into the softmax epilogues (shasta_forward_decode_f32) == decode kernel on the same outputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,B,aff_path", [(20, 3, 0), (50, 4, 0), (200, 5, 0), (200, 2, 1), (300, 2, 0), (500, 1, 0)])
+def test_fused_decode_equals_decode_kernel(M, B, aff_path):
+    """aff_path 0 = tcgen05 aff kernels (staged up to D = 224, streamed + row_softmax_kernel beyond), 1 = CUDA-core
+    aff_row_kernel. Every plane of the fused block must equal shasta_decode_f32 on the returned matched1 / matched2
+    bit for bit; the ring slot follows the device counter, also under CUDA-graph replay."""
+    H = W = 48
+    pc_start = (-W * 0.3, -H * 0.3)
+    data = synthetic.make_frame_pairs(B, M, H, W, 900 + M, pc_start=pc_start)
+    torch.manual_seed(M)
+    model = G.make_model(M, pc_start) if M > 200 else G.make_model(M, pc_start, synthetic.make_weights(M, seed=M, peaky=300.0))
+    if M > 200:
+        with torch.no_grad():
+            model.aff[10].weight.mul_(300.0)
+    lib = _cabi.lib()
+    lib.shasta_set_option(_cabi.OPT_AFF_PATH, aff_path)
+    try:
+        n_prev = torch.from_numpy(data["n_prev"].astype(np.int32)).to(G.DEV)
+        n_det = torch.from_numpy(data["n_det"].astype(np.int32)).to(G.DEV)
+        ring = torch.full((3, 6, B, M), -77, dtype=torch.int32, device=G.DEV)
+        counter = torch.zeros(1, dtype=torch.int32, device=G.DEV)
+        args = [G.t(data[k]) for k in ("bev", "prev_bev", "det_boxes", "prev_det_boxes")]
+        model.cuda_graphs = True
+        decisions = 0
+        with torch.no_grad():
+            for call in range(4):      # call 0 captures (eager run + capture run + replay: three forwards), 1-3 replay
+                m1, m2 = model.affinity(args[0], args[1], args[2].clone() if call else args[2], args[3],
+                                        decode={"n_prev": n_prev, "n_det": n_det, "out": ring, "counter": counter})
+                torch.cuda.synchronize()
+                slot = (int(counter.item()) - 1) % 3
+                want = model.decode(m1, m2, n_prev, n_det)
+                got = ring[slot]
+                for i, k in enumerate(("prev_state", "prev_argmax", "fn_dead_prob", "det_state", "det_argmax", "det_fp_prob")):
+                    w = want[k].view(torch.int32) if k.endswith("prob") else want[k]
+                    assert torch.equal(got[i], w), (call, k)
+                decisions += int((want["prev_state"] > 0).sum() + (want["det_state"] > 0).sum())
+        assert int(counter.item()) >= 4
+        assert decisions > 0 or M < 50, "no dead / FN / newborn / FP decision exercised"
+    finally:
+        lib.shasta_set_option(_cabi.OPT_AFF_PATH, 0)
