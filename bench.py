@@ -336,6 +336,9 @@ def run_train(a):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # the gradient all-reduce runs next to the pairwise backward (whose CTAs hold whole SMs for ~2 ms each): NCCL's
+        # stream gets priority so its few CTAs take the first slots that free up
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=device)
     from shasta_b200 import _cabi, loss as L, training
     lib = _cabi.lib()
@@ -347,7 +350,12 @@ def run_train(a):
         p_.requires_grad_(False)
     for p_ in params:
         p_.requires_grad_(True)
-    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-2, fused=True)  # train.py:147 Adam, single multi-tensor kernel
+    # train.py:147 Adam. One fused multi-tensor instance per aug_shape.i generator (4 x 64.3 M parameters) + one for the
+    # rest: with several ranks the update of generator i runs while the all-reduce of generator i+1 is still in flight
+    adam = dict(lr=1e-4, weight_decay=1e-2, fused=True)
+    big_params = [p_ for p_ in params if p_.numel() >= (1 << 22)]          # aug_shape.i.0.weight, i = 0..3
+    opts = [torch.optim.Adam([p_], **adam) for p_ in big_params]
+    opt_rest = torch.optim.Adam([p_ for p_ in params if p_.numel() < (1 << 22)], **adam)
     B, M = a.batch, a.max_obj
     det0 = torch.from_numpy(d["det_boxes"]).to(device)
     prev = torch.from_numpy(d["prev_det_boxes"]).to(device)
@@ -359,28 +367,68 @@ def run_train(a):
             gt[b_, t, rng.integers(0, M + 2)] = 1.0
     gt = torch.from_numpy(gt).to(device)
     flat = torch.zeros(sum(p_.numel() for p_ in params), device=device)
+    # the aug_shape gradients (1.03 GB of the 1.03 GB + 1.6 MB) are final after ~15 % of the backward: their all-reduce
+    # starts on a side stream behind the library's event and overlaps the rest of the backward
+    pending = []
+    if dist is not None and not os.environ.get("BENCH_NO_GRAD_OVERLAP"):
+        side = torch.cuda.Stream()
+
+        def grad_hook(aug_grads, ready):
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                for g_ in aug_grads:
+                    if g_.numel() >= (1 << 22):
+                        pending.append((g_, dist.all_reduce(g_, op=dist.ReduceOp.AVG, async_op=True)))
+        model.grad_sync_hook = grad_hook
+
+    marks = []
+
+    def mark():
+        if os.environ.get("BENCH_TRAIN_PHASES"):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(e)
 
     def step():
+        mark()
         det.copy_(det0)
-        opt.zero_grad(set_to_none=True)
+        for o_ in opts + [opt_rest]:
+            o_.zero_grad(set_to_none=True)
         m1, m2 = model.affinity(bev, prev_bev, det, prev)
         loss = L.affinity_loss(m1, m2, gt)
+        mark()
         loss.backward()
+        mark()
         if dist is not None:   # DDP-style gradient averaging (train.py:154-156): the four 257 MB aug_shape.i.0 gradients
             # are averaged in place, everything else (1.6 MB in 60 tensors) through one flat bucket
             big = [p_ for p_ in params if p_.numel() >= (1 << 22)]
             small = [p_ for p_ in params if p_.numel() < (1 << 22)]
-            works = [dist.all_reduce(p_.grad, op=dist.ReduceOp.AVG, async_op=True) for p_ in big]
+            if pending:   # started from the backward hook, in parameter order
+                assert len(pending) == len(big)
+                works = [w_ for _, w_ in pending]
+            else:
+                works = [dist.all_reduce(p_.grad, op=dist.ReduceOp.AVG, async_op=True) for p_ in big]
             fl = flat[:sum(p_.numel() for p_ in small)]
             torch.cat([p_.grad.reshape(-1) for p_ in small], out=fl)
-            works.append(dist.all_reduce(fl, op=dist.ReduceOp.AVG, async_op=True))
-            for w_ in works:
+            w_small = dist.all_reduce(fl, op=dist.ReduceOp.AVG, async_op=True)
+            mark()
+            for i_, (p_, w_) in enumerate(zip(big, works)):   # generator i: wait for its all-reduce, update it
                 w_.wait()
+                if pending and p_.grad.data_ptr() != pending[i_][0].data_ptr():
+                    p_.grad.copy_(pending[i_][0])      # (autograd normally adopts the buffer the backward returned)
+                opts[i_].step()
+            pending.clear()
+            w_small.wait()                             # queued behind the big ones
             o = 0
-            for p_ in small:
-                p_.grad.copy_(fl[o:o + p_.numel()].view_as(p_))
-                o += p_.numel()
-        opt.step()
+            for q_ in small:
+                q_.grad.copy_(fl[o:o + q_.numel()].view_as(q_))
+                o += q_.numel()
+        else:
+            mark()
+            for o_ in opts:
+                o_.step()
+        opt_rest.step()
+        mark()
         return loss
 
     sampler = ClockSampler(local_rank)
@@ -408,7 +456,15 @@ def run_train(a):
         tms = torch.tensor([ms], device=device)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
+    phases = None
+    if marks:
+        m5 = marks[-5 * a.steps:]
+        names = ["forward+loss", "backward", "small_bucket_enqueue", "sync+adam"]
+        phases = {n: round(sum(m5[5 * i + k].elapsed_time(m5[5 * i + k + 1]) for i in range(a.steps)) / a.steps, 3)
+                  for k, n in enumerate(names)}
     if rank == 0:
+        if phases:
+            sys.stderr.write("train phases (ms, rank 0): %s\n" % json.dumps(phases))
         line = {"metric": "affinity-head training frame-pairs/sec (200x200 pairs)", "value": world * B * a.steps / (ms / 1e3),
                 "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": n_warm, "ms_per_step": ms / a.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

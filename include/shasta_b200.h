@@ -336,6 +336,17 @@ SHASTA_API int shasta_backward_f32(const shasta_params_t* host_params, const sha
                                    const float* packed, int batch, float* workspace, size_t workspace_bytes,
                                    const float* matched1, const float* matched2, const float* gm1, const float* gm2,
                                    shasta_stream_t stream);
+/* Same, for data-parallel training (tools/nusc_shasta/train.py:154-156 wraps the model in apex DDP, which all-reduces
+ * the gradients while the backward is still running): the pairs that touch the anchor rows / columns are processed
+ * first, so the aug_shape.* gradients - 1.03 GB of the 1.03 GB + 1.6 MB a step has to all-reduce at max_obj = 200 -
+ * are complete after ~15 % of the backward. `aug_shape_grads_ready_event` (a cudaEvent_t, or NULL) is recorded on
+ * `stream` at that point: the caller starts its collective on another stream behind the event, the remaining kernels
+ * (bulk of the pairwise backward, first-layer and aug_dets gradients) overlap it. */
+SHASTA_API int shasta_backward_overlap_f32(const shasta_params_t* host_params, const shasta_grads_t* host_grads,
+                                           const float* packed, int batch, float* workspace, size_t workspace_bytes,
+                                           const float* matched1, const float* matched2, const float* gm1,
+                                           const float* gm2, void* aug_shape_grads_ready_event,
+                                           shasta_stream_t stream);
 
 /* Per-kernel timing for the roofline report (no reference counterpart). After shasta_profile_begin(n), every
  * shasta_forward_f32 call with flag bit 8 (0x100) records CUDA events between its kernels (up to n calls);

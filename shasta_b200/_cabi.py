@@ -115,6 +115,8 @@ SYMBOLS = {
     "shasta_shared_conv_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "shasta_backward_f32": (_i, [ctypes.POINTER(ShastaParams), ctypes.POINTER(ShastaGrads), _vp, _i, _vp, _sz, _vp, _vp,
                                  _vp, _vp, _vp]),
+    "shasta_backward_overlap_f32": (_i, [ctypes.POINTER(ShastaParams), ctypes.POINTER(ShastaGrads), _vp, _i, _vp, _sz,
+                                         _vp, _vp, _vp, _vp, _vp, _vp]),
     "shasta_profile_begin": (_i, [_i]),
     "shasta_profile_end": (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "shasta_decode_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

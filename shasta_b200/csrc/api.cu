@@ -534,6 +534,14 @@ int shasta_shared_conv_f32(const float* packed, const float* x_nchw, int nmaps, 
 int shasta_backward_f32(const shasta_params_t* host_params, const shasta_grads_t* host_grads, const float* packed,
                         int batch, float* workspace, size_t workspace_bytes, const float* matched1,
                         const float* matched2, const float* gm1, const float* gm2, shasta_stream_t stream) {
+  return shasta_backward_overlap_f32(host_params, host_grads, packed, batch, workspace, workspace_bytes, matched1,
+                                     matched2, gm1, gm2, nullptr, stream);
+}
+
+int shasta_backward_overlap_f32(const shasta_params_t* host_params, const shasta_grads_t* host_grads,
+                                const float* packed, int batch, float* workspace, size_t workspace_bytes,
+                                const float* matched1, const float* matched2, const float* gm1, const float* gm2,
+                                void* aug_shape_grads_ready_event, shasta_stream_t stream) {
   int rc = check_params(host_params);
   if (rc) return rc;
   const int M = host_params->max_obj;
@@ -590,7 +598,7 @@ int shasta_backward_f32(const shasta_params_t* host_params, const shasta_grads_t
   }
   if (batch == 0) return 0;
   return launch_backward(*host_params, *host_grads, packed, batch, workspace, ws_layout(batch, M), matched1, matched2,
-                         gm1, gm2, (cudaStream_t)stream);
+                         gm1, gm2, (cudaStream_t)stream, (cudaEvent_t)aug_shape_grads_ready_event);
 }
 
 int shasta_profile_begin(int max_steps) {

@@ -185,7 +185,7 @@ aff_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, con
 // ---------------------------------------------------------------------------------------------------
 int launch_backward(const shasta_params_t& p, const shasta_grads_t& g, const float* packed, int B, float* ws,
                     const WsLayout& L, const float* m1, const float* m2, const float* gm1, const float* gm2,
-                    cudaStream_t s) {
+                    cudaStream_t s, cudaEvent_t anchor_grads_ready) {
   const int M = p.max_obj, T = M + 2;
   const PackLayout P = pack_layout(M);
   float* logits = ws + L.off[SHASTA_WS_LOGITS];      // becomes dlogits
@@ -211,10 +211,19 @@ int launch_backward(const shasta_params_t& p, const shasta_grads_t& g, const flo
                                                                                         logits, ag, residual);
   SHASTA_CHECK_LAUNCH("aff_bwd_kernel");
   if (g.fuse_shape_w[0] != nullptr) {
-    int rc = launch_backward_pair(g, packed, B, M, ws, L, s);
-    if (rc) return rc;
+    int rc;
     if (g.aug_shape_w0[0] != nullptr) {
+      // the anchor rows / columns of the pair grid first: the aug_shape gradients (99 % of the bytes a data-parallel
+      // step has to all-reduce) are complete before the bulk of the pairwise backward starts
+      rc = launch_backward_pair(g, packed, B, M, ws, L, s, 0);
+      if (rc) return rc;
       rc = launch_backward_anchor(p, g, B, anchor_splits_in_use(M, B), ws, L, s);
+      if (rc) return rc;
+      if (anchor_grads_ready != nullptr) SHASTA_CUDA(cudaEventRecord(anchor_grads_ready, s));
+      rc = launch_backward_pair(g, packed, B, M, ws, L, s, 1);
+      if (rc) return rc;
+    } else {
+      rc = launch_backward_pair(g, packed, B, M, ws, L, s, -1);
       if (rc) return rc;
     }
     if (g.aug_dets_w0[0] != nullptr) {

@@ -80,10 +80,13 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
                 const float* __restrict__ proj_cur_t, const float* __restrict__ aux_prev,
                 const float* __restrict__ aux_cur, const float* __restrict__ colnorm,
                 const float* __restrict__ dres, PairGrads g, float* __restrict__ dproj_prev,
-                float* __restrict__ dproj_cur, float* __restrict__ ddist) {
+                float* __restrict__ dproj_cur, float* __restrict__ ddist, int db_first, int tt_begin, int tt_end,
+                int tt_chunk) {
   extern __shared__ __align__(16) float sm[];
   const int T = M + 2, D = M + 2, RS = row_stride(M);
-  const int b = blockIdx.y, d0 = blockIdx.x * 16;
+  // a launch covers the column blocks [db_first, db_first + gridDim.x) and the row blocks [tt_begin, tt_end): the
+  // backward runs the pairs that touch the anchor rows / columns first (launch_backward_pair)
+  const int b = blockIdx.y, d0 = (blockIdx.x + db_first) * 16;
   const int p = threadIdx.x, ti = p >> 4, di = p & 15, lane = p & 31;
 
   float* Ps = sm;                          // [8][144]
@@ -154,8 +157,10 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
   __syncthreads();
 
   const float* qrow = Qs + di * kPbQStride;
-  const int ntt = (T + 7) / 8;
-  for (int tt = 0; tt < ntt; ++tt) {
+  // blockIdx.z splits the row blocks of a launch into chunks (more, shorter CTAs: the grid fills the machine evenly)
+  tt_begin += blockIdx.z * tt_chunk;
+  tt_end = min(tt_end, tt_begin + tt_chunk);
+  for (int tt = tt_begin; tt < tt_end; ++tt) {
     const int t0 = tt * 8;
     // ---- stage the previous-frame block of this tile ----
     {
@@ -443,10 +448,11 @@ pair_bwd_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, co
     __syncthreads();   // before the next tile overwrites the stash
   }
 
-  // ---- CTA epilogue: dPROJ_CUR rows are owned by this CTA; weight gradients go out with atomics ----
+  // ---- CTA epilogue: several CTAs (row chunks, launches) add to the same dPROJ_CUR rows - the buffer is zeroed first;
+  // weight gradients go out with atomics as well ----
   for (int v = p; v < 16 * kProj; v += kPbThreads) {
     const int dr = v / kProj;
-    if (d0 + dr < D) dproj_cur[((size_t)b * T + d0 + dr) * kProj + (v % kProj)] = dQs[v];
+    if (d0 + dr < D) atomicAdd(dproj_cur + ((size_t)b * T + d0 + dr) * kProj + (v % kProj), dQs[v]);
   }
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
@@ -579,13 +585,20 @@ first_layer_bwd_kernel(int B, int M, const float* __restrict__ dproj_prev, const
 }
 
 // ---------------------------------------------------------------------------------------------------
+// phase 0: zero d PROJ and run the pairs whose row or column is an anchor (the last row block of every column block and
+//          the whole last column block): afterwards the anchor rows of d PROJ are final, which is all the aug_shape
+//          backward needs - its 1.03 GB of gradients can be on their way to the other ranks while phase 1 runs;
+// phase 1: all other pairs, then the first-layer weight gradients;   phase -1: everything in one go.
 int launch_backward_pair(const shasta_grads_t& gr, const float* packed, int B, int M, float* ws, const WsLayout& L,
-                         cudaStream_t s) {
+                         cudaStream_t s, int phase) {
   const PackLayout P = pack_layout(M);
   const int T = M + 2;
   float* dpp = ws + L.off[SHASTA_WS_DPROJ_PREV];
   float* dpc = ws + L.off[SHASTA_WS_DPROJ_CUR];
-  SHASTA_CUDA(cudaMemsetAsync(dpp, 0, sizeof(float) * (size_t)B * T * kProj, s));
+  if (phase <= 0) {
+    SHASTA_CUDA(cudaMemsetAsync(dpp, 0, sizeof(float) * (size_t)B * T * kProj, s));
+    SHASTA_CUDA(cudaMemsetAsync(dpc, 0, sizeof(float) * (size_t)B * T * kProj, s));
+  }
 
   PairGrads g;
   g.w2a = gr.fuse_shape_w[1], g.b2a = gr.fuse_shape_b[1], g.w3a = gr.fuse_shape_w[2], g.b3a = gr.fuse_shape_b[2];
@@ -599,13 +612,36 @@ int launch_backward_pair(const shasta_grads_t& gr, const float* packed, int B, i
   if (configured.first()) {
     SHASTA_CUDA(cudaFuncSetAttribute(pair_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  dim3 grid((T + 15) / 16, B);
-  pair_bwd_kernel<<<grid, kPbThreads, smem, s>>>(packed, P, B, M, ws + L.off[SHASTA_WS_PROJ_PREV],
-                                                 ws + L.off[SHASTA_WS_PROJ_CUR_T], ws + L.off[SHASTA_WS_AUX_PREV],
-                                                 ws + L.off[SHASTA_WS_AUX_CUR], ws + L.off[SHASTA_WS_COLNORM],
-                                                 ws + L.off[SHASTA_WS_RESIDUAL], g, dpp, dpc,
-                                                 ws + L.off[SHASTA_WS_LOGITS]);  // dlogits is dead by now
-  SHASTA_CHECK_LAUNCH("pair_bwd_kernel");
+  const int ndb = (T + 15) / 16, ntt = (T + 7) / 8;
+  auto run = [&](int db_first, int ndbs, int tt_begin, int tt_end) -> int {
+    if (ndbs <= 0 || tt_end <= tt_begin) return 0;
+    // row chunks: enough CTAs for ~4 waves of 2 CTAs per SM, at least 4 row blocks per CTA (the per-CTA epilogue
+    // - 16 x 144 + ~2 400 atomics - is amortised over them)
+    int nz = (4 * 2 * 148 + ndbs * B - 1) / (ndbs * B);
+    const int ntt_ = tt_end - tt_begin;
+    nz = nz < 1 ? 1 : nz;
+    nz = nz > (ntt_ + 3) / 4 ? (ntt_ + 3) / 4 : nz;
+    const int chunk = (ntt_ + nz - 1) / nz;
+    nz = (ntt_ + chunk - 1) / chunk;
+    pair_bwd_kernel<<<dim3(ndbs, B, nz), kPbThreads, smem, s>>>(
+        packed, P, B, M, ws + L.off[SHASTA_WS_PROJ_PREV], ws + L.off[SHASTA_WS_PROJ_CUR_T],
+        ws + L.off[SHASTA_WS_AUX_PREV], ws + L.off[SHASTA_WS_AUX_CUR], ws + L.off[SHASTA_WS_COLNORM],
+        ws + L.off[SHASTA_WS_RESIDUAL], g, dpp, dpc, ws + L.off[SHASTA_WS_LOGITS],   // dlogits is dead by now
+        db_first, tt_begin, tt_end, chunk);
+    SHASTA_CHECK_LAUNCH("pair_bwd_kernel");
+    return 0;
+  };
+  int rc = 0;
+  if (phase < 0) {
+    rc = run(0, ndb, 0, ntt);
+  } else if (phase == 0) {
+    rc = run(ndb - 1, 1, 0, ntt);                        // the column block that holds the dead / FN anchors
+    if (rc == 0) rc = run(0, ndb - 1, ntt - 1, ntt);     // the row block that holds the newborn / FP anchors
+    return rc;
+  } else {
+    rc = run(0, ndb - 1, 0, ntt - 1);
+  }
+  if (rc) return rc;
 
   FirstGrads fg;
   fg.fs_w = gr.fuse_shape_w[0], fg.fs_b = gr.fuse_shape_b[0];
