@@ -433,10 +433,21 @@ def run_train(a):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # warm-up: >= W steps and >= 0.6 s. Every step contains collectives, so all ranks must run the SAME number of
+    # steps: rank 0 decides after each step and broadcasts the decision (a per-rank clock would let one rank leave
+    # the loop a step earlier than its peers - a deadlock, seen once in a while at N = 2)
     t_w, n_warm = time.time(), 0
-    while n_warm < max(a.warmup, 3) or time.time() - t_w < 0.6:
+    go = torch.ones(1, dtype=torch.int32, device=device)
+    while True:
         step()
         n_warm += 1
+        more = n_warm < max(a.warmup, 3) or time.time() - t_w < 0.6
+        if dist is not None:
+            go.fill_(1 if more else 0)
+            dist.broadcast(go, 0)
+            more = bool(go.item())
+        if not more:
+            break
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()

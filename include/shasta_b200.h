@@ -348,6 +348,19 @@ SHASTA_API int shasta_backward_overlap_f32(const shasta_params_t* host_params, c
                                            const float* gm2, void* aug_shape_grads_ready_event,
                                            shasta_stream_t stream);
 
+/* Gradients of the two channels-last BEV maps (training: the reference trains shared_conv together with the head,
+ * tools/nusc_shasta/train.py:184-191, so autograd has to get d example['bev_feature'] back from this path).
+ * Call after shasta_backward_f32 / _overlap_f32 on the same workspace, with the boxes the forward saw (det_boxes already
+ * back-projected in place - the pre-projection x,y are kept in the workspace). d_bev / d_prev_bev: (batch,H,W,64),
+ * ZERO-INITIALISED by the caller, either may be NULL. scratch: 2 * batch * max_obj * 320 floats (d feature).
+ *   d feature = d PROJ . W1 (first layers of fuse_shape / res_coeff) + W0_i^T dz_i (aug_shape.i.0, 1.03 GB streamed once)
+ *   d bev    += bilinear tap weights * d feature   (center_utils.py:92-121; the boxes receive no gradient) */
+SHASTA_API size_t shasta_backward_maps_scratch_bytes(int batch, int max_obj);
+SHASTA_API int shasta_backward_maps_f32(const shasta_params_t* host_params, int batch, const shasta_geom_t* host_geom,
+                                        float* workspace, size_t workspace_bytes, const float* det_boxes,
+                                        const float* prev_det_boxes, float* scratch, size_t scratch_bytes,
+                                        float* d_bev, float* d_prev_bev, shasta_stream_t stream);
+
 /* Per-kernel timing for the roofline report (no reference counterpart). After shasta_profile_begin(n), every
  * shasta_forward_f32 call with flag bit 8 (0x100) records CUDA events between its kernels (up to n calls);
  * shasta_profile_end synchronises on them and returns the mean milliseconds of the 7 kernels in launch order:

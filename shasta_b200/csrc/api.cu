@@ -601,6 +601,39 @@ int shasta_backward_overlap_f32(const shasta_params_t* host_params, const shasta
                          gm1, gm2, (cudaStream_t)stream, (cudaEvent_t)aug_shape_grads_ready_event);
 }
 
+size_t shasta_backward_maps_scratch_bytes(int batch, int max_obj) {
+  if (batch < 0 || max_obj < 1) return 0;
+  return (size_t)2 * batch * max_obj * kF * sizeof(float);
+}
+
+int shasta_backward_maps_f32(const shasta_params_t* host_params, int batch, const shasta_geom_t* host_geom,
+                             float* workspace, size_t workspace_bytes, const float* det_boxes,
+                             const float* prev_det_boxes, float* scratch, size_t scratch_bytes, float* d_bev,
+                             float* d_prev_bev, shasta_stream_t stream) {
+  int rc = check_params(host_params);
+  if (rc) return rc;
+  const int M = host_params->max_obj;
+  rc = check_dims(batch, M);
+  if (rc) return rc;
+  rc = check_geom(host_geom);
+  if (rc) return rc;
+  NOT_NULL(workspace);
+  NOT_NULL(det_boxes);
+  NOT_NULL(prev_det_boxes);
+  NOT_NULL(scratch);
+  ALIGNED16(workspace);
+  ALIGNED16(scratch);
+  if (d_bev != nullptr) ALIGNED16(d_bev);
+  if (d_prev_bev != nullptr) ALIGNED16(d_prev_bev);
+  if (workspace_bytes < shasta_workspace_bytes(batch, M) || scratch_bytes < shasta_backward_maps_scratch_bytes(batch, M)) {
+    set_error("backward_maps: workspace or scratch too small");
+    return SHASTA_ERR_SIZE;
+  }
+  if (batch == 0 || (d_bev == nullptr && d_prev_bev == nullptr)) return 0;
+  return launch_backward_maps(*host_params, batch, *host_geom, workspace, ws_layout(batch, M), det_boxes, prev_det_boxes,
+                              11, scratch, d_bev, d_prev_bev, (cudaStream_t)stream);
+}
+
 int shasta_profile_begin(int max_steps) {
   if (max_steps < 1 || max_steps > 4096) {
     set_error("profile: max_steps out of range");

@@ -346,4 +346,62 @@ int launch_gather(const float* bev0, const float* boxes0, float* feat0, const fl
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Backward of the sampler (training: lets autograd reach shared_conv): d bev += tap weight * d feature. The taps are
+// recomputed with the forward's arithmetic; the boxes get no gradient through them (the reference's coordinates are
+// built from floor / clamp of detached box values, center_utils.py:100-119). Half-warp per sample point.
+// ------------------------------------------------------------------------------------------------
+struct MapsBwdJob {
+  const float* boxes[2];    // side 0: previous boxes, side 1: current boxes (x,y taken from raw_xy)
+  const float* raw_xy;      // (B,M,2) x,y of the current boxes BEFORE the in-place back-projection (shasta.py:270)
+  float* dbev[2];           // (B,H,W,64), zero-initialised by the caller; nullptr = side not wanted
+};
+
+__global__ void __launch_bounds__(kGatherThreads)
+gather_bwd_kernel(MapsBwdJob job, int box_stride, int B, int M, shasta_geom_t g, const float* __restrict__ dfeat) {
+  const int side = blockIdx.y;
+  float* __restrict__ dbev = job.dbev[side];
+  if (dbev == nullptr) return;
+  const int lane16 = threadIdx.x & 15;
+  const long long total = (long long)B * M * 5;
+  const long long gp = (long long)blockIdx.x * kPointsPerCta0 + (threadIdx.x >> 4);
+  if (gp >= total) return;
+  const int bm = (int)(gp / 5), p = (int)(gp % 5);
+  const int b = bm / M;
+  const float* src = job.boxes[side] + (size_t)bm * box_stride;
+  float bx[7];
+#pragma unroll
+  for (int e = 0; e < 7; ++e) bx[e] = src[e];
+  if (side == 1) bx[0] = job.raw_xy[(size_t)bm * 2], bx[1] = job.raw_xy[(size_t)bm * 2 + 1];
+  float xs, ys;
+  box_point_pixels(bx, p, g, xs, ys);
+  const Taps t = make_taps(xs, ys, g.height, g.width);
+  const float4 gf = __ldg(reinterpret_cast<const float4*>(dfeat + ((size_t)side * B * M + bm) * kF + p * kC) + lane16);
+  float4* base = reinterpret_cast<float4*>(dbev) + (size_t)b * g.height * g.width * (kC / 4);
+  // Ia = im[y0,x0] (wa), Ib = im[y1,x0] (wb), Ic = im[y0,x1] (wc), Id = im[y1,x1] (wd)      center_utils.py:111-120
+  const int ty[4] = {t.y0, t.y1, t.y0, t.y1}, tx[4] = {t.x0, t.x0, t.x1, t.x1};
+  const float w[4] = {t.wa, t.wb, t.wc, t.wd};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float* dst = reinterpret_cast<float*>(base + ((size_t)ty[k] * g.width + tx[k]) * (kC / 4) + lane16);
+    atomicAdd(dst + 0, __fmul_rn(gf.x, w[k]));
+    atomicAdd(dst + 1, __fmul_rn(gf.y, w[k]));
+    atomicAdd(dst + 2, __fmul_rn(gf.z, w[k]));
+    atomicAdd(dst + 3, __fmul_rn(gf.w, w[k]));
+  }
+}
+
+int launch_gather_bwd(const float* prev_boxes, const float* cur_boxes, const float* raw_xy, int box_stride, int B, int M,
+                      const shasta_geom_t& g, const float* dfeat, float* d_prev_bev, float* d_bev, cudaStream_t s) {
+  MapsBwdJob job;
+  job.boxes[0] = prev_boxes, job.boxes[1] = cur_boxes, job.raw_xy = raw_xy;
+  job.dbev[0] = d_prev_bev, job.dbev[1] = d_bev;
+  const long long total = (long long)B * M * 5;
+  gather_bwd_kernel<<<dim3((unsigned)((total + kPointsPerCta0 - 1) / kPointsPerCta0), 2), kGatherThreads, 0, s>>>(
+      job, box_stride, B, M, g, dfeat);
+  SHASTA_CHECK_LAUNCH("gather_bwd_kernel");
+  return 0;
+}
+
 }  // namespace shasta

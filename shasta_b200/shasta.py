@@ -388,8 +388,9 @@ class Shasta(nn.Module):
         """``self.shared_conv(x).permute(0, 2, 3, 1).contiguous()`` (shasta.py:223-228) for inference: one tcgen05
         implicit-GEMM kernel (3xTF32, fp32-equivalent) with the bias / BatchNorm (running statistics) / ReLU folded
         into its epilogue, writing the channels-last map directly. x: (N,512,H,W) float32 CUDA tensor.
-        In training mode BatchNorm needs batch statistics: that case stays on the nn.Sequential (and receives no
-        gradient from the CUDA head)."""
+        In training mode BatchNorm needs batch statistics: that case stays on the nn.Sequential under autograd; the CUDA
+        head hands the gradients of the two maps back (``shasta_backward_maps_f32``), so shared_conv is trained with
+        the head like in the reference (train.py:184-191)."""
         conv, bn = self.shared_conv[0], self.shared_conv[1]
         if self.training or not x.is_cuda:
             if not x.is_cuda:

@@ -8,8 +8,9 @@ dual-softmax backward, the aff row-MLP backward, the pairwise-MLP backward and t
 Gradient coverage of this revision: ``aff.*``, ``fuse_shape.*``, ``res_coeff.*``, ``fuse_det.*`` (the pairwise MLPs
 incl. their decomposed first layers), ``aug_shape.*`` (the anchor shape generators, 99 % of the parameters) and
 ``aug_dets.*`` (anchor boxes, through the first-layer box columns and the hand-designed residual incl. the F.normalize
-backward) - i.e. every parameter of the head. ``shared_conv`` (the producer left of the path; needs the gather's
-scatter-add) is not differentiated yet and receives no gradient, like the frozen trunk. DESIGN.md §7 tracks it.
+backward) - i.e. every parameter of the head - and the two channels-last BEV maps (``shasta_backward_maps_f32``:
+d feature through the first layers and aug_shape.i.0, scattered back through the bilinear taps), so that autograd trains
+``shared_conv`` with the head exactly as the reference does (train.py:184-191 freezes only backbone and neck).
 """
 import ctypes
 
@@ -52,6 +53,8 @@ class _AffinityFunction(torch.autograd.Function):
         ws = _Workspace(B, model.max_obj, det_c.device)   # private: the backward reads the saved activations
         m1, m2, _ = model._launch_forward(bev, prev_bev, det_c, prev_c, ws)
         ctx.model, ctx.ws, ctx.batch = model, ws, B
+        ctx.boxes = (det_c, prev_c)          # det_c is back-projected by now; the raw x,y live in the workspace
+        ctx.map_shape = tuple(bev.shape)
         ctx.save_for_backward(m1, m2)
         return m1, m2
 
@@ -99,7 +102,26 @@ class _AffinityFunction(torch.autograd.Function):
         _cabi.check(rc, "shasta_backward_overlap_f32")
         if hook is not None:
             hook(grads[n_small:n_small + 16], ready)     # aug_shape.{0..3}.{0,2}.{weight,bias}
-        return (None, None, None, None, None) + tuple(grads)
+        d_bev = d_prev = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            # the maps came out of shared_conv under autograd: hand their gradients back (the reference trains it)
+            Bm, H, W, C = ctx.map_shape
+            det_c, prev_c = ctx.boxes
+            if ctx.needs_input_grad[1]:
+                d_bev = torch.zeros((Bm, H, W, C), dtype=torch.float32, device=device)
+            if ctx.needs_input_grad[2]:
+                d_prev = torch.zeros((Bm, H, W, C), dtype=torch.float32, device=device)
+            nbytes = lib.shasta_backward_maps_scratch_bytes(B, model.max_obj)
+            scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+            geom = model.bev_extractor.geom(H, W)
+            with torch.cuda.device(device):
+                rc = lib.shasta_backward_maps_f32(
+                    ctypes.byref(model._cparams), B, ctypes.byref(geom), ws.buf.data_ptr(), ws.nbytes, det_c.data_ptr(),
+                    prev_c.data_ptr(), scratch.data_ptr(), nbytes,
+                    d_bev.data_ptr() if d_bev is not None else None, d_prev.data_ptr() if d_prev is not None else None,
+                    ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+            _cabi.check(rc, "shasta_backward_maps_f32")
+        return (None, d_bev, d_prev, None, None) + tuple(grads)
 
 
 def affinity_with_grad(model, bev, prev_bev, det_c, prev_c):

@@ -65,8 +65,83 @@ def test_gradients_match_autograd_through_oracle(name):
         err = np.abs(got - want[n]).max() / scale
         print("%-22s grad max err / scale = %.3g (scale %.3g)" % (n, err, scale))
         assert err < 2e-3, "%s: grad max err / scale = %g" % (n, err)
-    # the producer left of the path is not differentiated in this revision
+    # the maps of this test are leaves without requires_grad: nothing flows to the producer
     assert sd["shared_conv.0.weight"].grad is None
+
+
+@pytest.mark.parametrize("name", ["m6_16px_b2", "m20_32px_b2", "m50_48x40_b2_peaky"])
+def test_map_gradients_match_autograd_through_oracle(name):
+    """d loss / d bev_feature and d prev_bev_feature (what trains shared_conv, train.py:184-191) against float64
+    autograd through the oracle: the gather's bilinear scatter, the first-layer path and the aug_shape.i.0 path."""
+    c, pc_start, data, weights, g = load_golden(name)
+    B, M = c["B"], c["M"]
+    gt = _gt(B, M, data["n_prev"], data["n_det"], seed=c["seed"])
+    w = {k: torch.from_numpy(v).double() for k, v in weights.items()}
+    bev64 = torch.from_numpy(data["bev"]).double().requires_grad_(True)
+    prev64 = torch.from_numpy(data["prev_bev"]).double().requires_grad_(True)
+    m1, m2 = O.forward(w, bev64, prev64, torch.from_numpy(data["det_boxes"].copy()).double(),
+                       torch.from_numpy(data["prev_det_boxes"]).double(), pc_start=pc_start)
+    O.affinity_loss(m1, m2, torch.from_numpy(gt).double()).backward()
+
+    model = G.make_model(M, pc_start, weights)
+    model.train()
+    bev = G.t(data["bev"]).requires_grad_(True)
+    prev = G.t(data["prev_bev"]).requires_grad_(True)
+    example = {"det_boxes": G.t(data["det_boxes"]), "prev_det_boxes": G.t(data["prev_det_boxes"]),
+               "bev_feature": bev, "prev_bev_feature": prev}
+    a1, a2, _ = model(example, train_mode=True)
+    L.affinity_loss(a1, a2, G.t(gt)).backward()
+    for got, want, nm in ((bev.grad, bev64.grad, "bev_feature"), (prev.grad, prev64.grad, "prev_bev_feature")):
+        assert got is not None, nm
+        got = got.cpu().numpy().astype(np.float64)
+        want = want.numpy()
+        scale = np.abs(want).max() + 1e-30
+        err = np.abs(got - want).max() / scale
+        nz = float((want != 0).mean())
+        print("%-18s grad max err / scale = %.3g (scale %.3g, %.1f%% of the map touched)" % (nm, err, scale, 100 * nz))
+        assert err < 2e-3, "%s: grad max err / scale = %g" % (nm, err)
+
+
+def test_shared_conv_receives_gradients_in_train_mode():
+    """End to end like train.py:195-215 with a trunk stub: (B,512,H,W) maps -> shared_conv (autograd, train-mode
+    BatchNorm) -> CUDA head -> loss.backward(): shared_conv.0.weight / shared_conv.1.weight get gradients that match
+    the same graph with the head replaced by the float64 oracle."""
+    c, pc_start, data, weights, g = load_golden("m6_16px_b2")
+    B, M, H, W = c["B"], c["M"], c["H"], c["W"]
+    gt = _gt(B, M, data["n_prev"], data["n_det"], seed=5)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn((B, 512, H, W), generator=gen) * 0.1
+    xp = torch.randn((B, 512, H, W), generator=gen) * 0.1
+    model = G.make_model(M, pc_start, weights)
+    model.train()
+    torch.backends.cudnn.allow_tf32 = False      # fp32 convolution: the comparison below is against float64
+    model.extract_feat = lambda ex: (G.t(x.numpy()), None, G.t(xp.numpy()), None)
+    example = {"det_boxes": G.t(data["det_boxes"]), "prev_det_boxes": G.t(data["prev_det_boxes"])}
+    m1, m2, _ = model(example, train_mode=True)
+    L.affinity_loss(m1, m2, G.t(gt)).backward()
+    got = {k: v.grad.detach().cpu().double() for k, v in model.shared_conv.named_parameters()}
+    assert all(v is not None and torch.isfinite(v).all() for v in got.values())
+
+    # reference graph on the CPU in float64: same shared_conv weights, train-mode BN, oracle head
+    import copy
+    conv = copy.deepcopy(model.shared_conv).cpu().double()
+    conv.train()
+    for p_ in conv.parameters():
+        p_.grad = None
+    w = {k: torch.from_numpy(v).double() for k, v in weights.items()}
+    bev = conv(x.double()).permute(0, 2, 3, 1).contiguous()
+    prev_bev = conv(xp.double()).permute(0, 2, 3, 1).contiguous()
+    o1, o2 = O.forward(w, bev, prev_bev, torch.from_numpy(data["det_boxes"].copy()).double(),
+                       torch.from_numpy(data["prev_det_boxes"]).double(), pc_start=pc_start)
+    O.affinity_loss(o1, o2, torch.from_numpy(gt).double()).backward()
+    top = max(float(p_.grad.abs().max()) for p_ in conv.parameters())
+    for k, p_ in conv.named_parameters():
+        # (the convolution bias has an exactly-zero gradient under train-mode BatchNorm - fp32 leaves rounding noise
+        # there: the scale is floored at 1e-3 of the largest gradient)
+        scale = max(float(p_.grad.abs().max()), 1e-3 * top)
+        err = float((got[k] - p_.grad).abs().max()) / scale
+        print("shared_conv.%-10s grad max err / scale = %.3g (scale %.3g)" % (k, err, scale))
+        assert err < 5e-3, (k, err)
 
 
 def test_training_steps_lower_the_loss():
