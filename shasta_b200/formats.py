@@ -112,36 +112,45 @@ def build_gt_affinity(matched, newborn, prev_keep, keep, max_objects, has_prev, 
 
 
 def label_affinity(tp_ind_pairs, frame_gt_ids, fn_inds, num_dets, prev=None):
-    """preprocessing/make_gt_shasta.py:88-157 for one frame, given the detection<->GT association of the frame
-    (``tp_ind_pairs``: detection index -> GT index, ``fn_inds``: GT indices without a detection, ``frame_gt_ids``:
-    instance id per GT index) and, unless it is the first frame of a scene, ``prev = (prev_tp_ind_pairs,
-    prev_gt_ids, num_prev_dets)``. Returns ``(matched (N, K+2) or None, newborn (K,))``."""
+    """Ground-truth affinity of one frame from the detection<->GT association, as preprocessing/make_gt_shasta.py:88-157
+    defines it (pinned against that script's own output: oracle/make_labelaff_golden.py, tests/golden/labelaff_*.json).
+
+    ``tp_ind_pairs``: detection index -> GT index of the true positives, ``frame_gt_ids``: instance id per GT index,
+    ``fn_inds``: GT indices nobody detected, ``num_dets`` = K. ``prev = (prev_tp_ind_pairs, prev_gt_ids, N)`` of the
+    previous frame, or None at the start of a scene. Returns ``(matched (N, K+2) or None, newborn (K,))``:
+    a previous true positive is matched to the current true positive of the same instance, else it is an FN track
+    (column K+1) when that instance is still annotated but undetected, else dead (column K); previous false positives
+    are dead; a current true positive whose instance had no previous true positive is newborn."""
     K = num_dets
+    newborn = np.zeros((K,))
     if prev is None:
-        newborn = np.zeros((K,))
-        for k in range(K):
-            if k in tp_ind_pairs.keys():
-                newborn[k] = 1
+        newborn[[k for k in tp_ind_pairs if k < K]] = 1
         return None, newborn
     prev_tp_ind_pairs, prev_gt_ids, N = prev
     matched = np.zeros((N, K + 2))
-    newborn = np.zeros((K,))
-    prev_tp_ids = [prev_gt_ids[g] for g in prev_tp_ind_pairs.values()]
-    prev_tp_idx = list(prev_tp_ind_pairs.keys())
-    matched_prev_tp_ids = []
-    for curr_idx, gt_idx in tp_ind_pairs.items():
-        gt_id = frame_gt_ids[gt_idx]
-        if gt_id in prev_tp_ids:
-            matched_prev_tp_ids.append(gt_id)
-            matched[prev_tp_idx[prev_tp_ids.index(gt_id)], curr_idx] = 1
+    # instance id -> the FIRST previous detection that was a true positive of it (the script resolves ids with
+    # list.index, i.e. first occurrence in association order)
+    prev_det_of = {}
+    prev_tp = [(det, prev_gt_ids[g]) for det, g in prev_tp_ind_pairs.items()]
+    for det, inst in prev_tp:
+        prev_det_of.setdefault(inst, det)
+    continued = set()
+    for det, g in tp_ind_pairs.items():
+        inst = frame_gt_ids[g]
+        if inst in prev_det_of:
+            matched[prev_det_of[inst], det] = 1
+            continued.add(inst)
         else:
-            newborn[curr_idx] = 1
-    for i, prev_tp_id in enumerate(prev_tp_ids):
-        if prev_tp_id not in matched_prev_tp_ids:
-            if prev_tp_id in frame_gt_ids:
-                if frame_gt_ids.index(prev_tp_id) in fn_inds:
-                    matched[prev_tp_idx[i], -1] = 1          # FN track
-    matched[:, -2] = 1 - matched.sum(axis=1)                  # dead tracks
+            newborn[det] = 1
+    # still annotated, but undetected in this frame: the track goes on as a false negative
+    first_gt_of = {}
+    for g, inst in enumerate(frame_gt_ids):
+        first_gt_of.setdefault(inst, g)
+    undetected = set(fn_inds)
+    for det, inst in prev_tp:
+        if inst not in continued and first_gt_of.get(inst, -1) in undetected:
+            matched[det, K + 1] = 1
+    matched[:, K] = 1 - matched.sum(axis=1)      # everything else died (false positives included)
     return matched, newborn
 
 

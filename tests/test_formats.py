@@ -112,3 +112,32 @@ def test_annos_from_decode_follows_the_eval_loop():
     assert cur_cls[1].get("newborn") is True and "newborn" not in cur_cls[2]
     res = F.mark_dead({"t0": [{"a": 1}, {"a": 2}]}, {"t0": {"dead_idx": [3], "keep_idx": [1, 3]}})
     assert res["t0"][1].get("dead") is True and "dead" not in res["t0"][0]
+
+
+@pytest.mark.parametrize("path", sorted(__import__("glob").glob(os.path.join(os.path.dirname(__file__), "golden", "labelaff_seed*.json"))),
+                         ids=lambda p: os.path.basename(p))
+def test_label_affinity_matches_reference_script(path):
+    """Fixtures written by the UNMODIFIED preprocessing/make_gt_shasta.py (oracle/make_labelaff_golden.py runs its
+    main() on a synthetic scene with the devkit stubbed): matched / newborn per frame must be identical."""
+    import json
+    g = json.load(open(path))
+    scene = g["scene"]
+
+    def assoc(f):
+        tp = {d: gi for d, gi in enumerate(f["det_gt"]) if gi >= 0}
+        fn = [gi for gi in range(len(f["gt_ids"])) if gi not in tp.values()]
+        return tp, fn
+
+    for i, (f, want) in enumerate(zip(scene, g["outputs"])):
+        tp, fn = assoc(f)
+        prev = None
+        if i > 0:
+            ptp, _ = assoc(scene[i - 1])
+            prev = (ptp, scene[i - 1]["gt_ids"], len(scene[i - 1]["det_gt"]))
+        matched, newborn = F.label_affinity(tp, f["gt_ids"], fn, len(f["det_gt"]), prev)
+        assert newborn.tolist() == want["newborn"], i
+        if want["matched"] is None:
+            assert matched is None
+        else:
+            assert matched.tolist() == want["matched"], i
+            assert np.all(matched.sum(axis=1) == 1)

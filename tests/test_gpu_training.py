@@ -27,6 +27,35 @@ def _gt(B, M, n_prev, n_det, seed):
     return gt
 
 
+def _gt_from_builder(B, M, n_prev, n_det, seed):
+    """Targets built the way the reference's dataset builds them: a per-frame label (matched (N, K+2), newborn (K),
+    preprocessing/make_gt_shasta.py via formats.label_affinity) pushed through formats.build_gt_affinity
+    (det3d/datasets/nuscenes/nuscenes.py:297-349: dead-track / FP sub-sampling, compaction to the padded layout)."""
+    import random
+
+    from shasta_b200 import formats as F
+    rng = np.random.default_rng(seed)
+    out = np.zeros((B, M + 2, M + 2), np.float32)
+    for b in range(B):
+        N, K = int(n_prev[b]), int(n_det[b])
+        # a synthetic association: instance ids for the GT boxes of both frames, detections as TPs / FPs
+        prev_gt_ids = list(range(N + 2))
+        prev_tp = {d: d for d in range(N) if rng.random() < 0.8}
+        cur_gt_ids = [i for i in prev_gt_ids if rng.random() < 0.85] + [1000 + i for i in range(3)]
+        cur_tp = {}
+        free = list(range(len(cur_gt_ids)))
+        rng.shuffle(free)
+        for d in range(K):
+            if free and rng.random() < 0.8:
+                cur_tp[d] = free.pop()
+        fn = [g for g in range(len(cur_gt_ids)) if g not in cur_tp.values()]
+        matched, newborn = F.label_affinity(cur_tp, cur_gt_ids, fn, K, prev=(prev_tp, prev_gt_ids, N))
+        gt, _, _ = F.build_gt_affinity(matched, newborn, list(range(N)), list(range(K)), M, True, fp_ratio=0.5,
+                                       dead_trk_ratio=0.5, rng=random.Random(seed + b))
+        out[b] = gt
+    return out
+
+
 def _oracle_grads(weights, data, pc_start, gt, names):
     w = {k: torch.from_numpy(v).double() for k, v in weights.items()}
     for n in names:
@@ -147,7 +176,9 @@ def test_shared_conv_receives_gradients_in_train_mode():
 def test_training_steps_lower_the_loss():
     c, pc_start, data, weights, g = load_golden("m20_32px_b2")
     B, M = c["B"], c["M"]
-    gt = G.t(_gt(B, M, data["n_prev"], data["n_det"], seed=3))
+    gt_np = _gt_from_builder(B, M, data["n_prev"], data["n_det"], seed=3)   # targets from the dataset-side builder
+    assert gt_np[:, :-2, :].sum() > 0 and gt_np[:, :, :-2].sum() > 0
+    gt = G.t(gt_np)
     model = G.make_model(M, pc_start, weights)
     model.train()
     opt = torch.optim.Adam(training.differentiable_parameters(model), lr=1e-3)
