@@ -52,8 +52,10 @@ def parse():
                          "+ Adam on the differentiated parameters) instead of inference")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
-    ap.add_argument("--streams", type=int, default=1,
-                    help="independent batches in flight: N step graphs replayed round-robin on N streams (experiment)")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="independent batches in flight: N step graphs replayed round-robin on N streams, each with its "
+                         "own model instance / workspace (default 2: the tail of one batch's kernels - 101-CTA aff "
+                         "tiles, the second wave of the projection GEMM, small launches - overlaps the next batch)")
     ap.add_argument("--bf16", action="store_true", help="bf16 mode (shasta_forward_bf16): separate tolerance, dtype bf16")
     ap.add_argument("--opt", action="append", default=[], metavar="ID=VALUE",
                     help="shasta_set_option(ID, VALUE) before the run (experiment knob, repeatable)")
@@ -538,7 +540,9 @@ def main():
     # blocks of all ranks are all-gathered ONCE at the end of the timed region - the only collective of the path
     # The decode is fused into the softmax kernels (shasta_forward_decode_f32) and writes straight into this step's
     # slot of the ring (device-side call counter): no decode kernel, no copy.
-    dec_pack = torch.empty((a.steps, 6, B, M), dtype=torch.int32, device=device)
+    nl_ = max(1, a.streams) if not (a.no_graph or os.environ.get("BENCH_INNER_GRAPH")) else 1
+    slots = (a.steps + nl_ - 1) // nl_        # ring slots per lane (steps go to the lanes round-robin)
+    dec_pack = torch.empty((nl_, slots, 6, B, M), dtype=torch.int32, device=device)
     # one CUDA graph per step: box refresh + forward (+ decode when results are gathered across ranks); the model's own
     # per-call graph cache is not needed on top of it
     inner = bool(os.environ.get("BENCH_INNER_GRAPH"))   # A/B knob: the model's per-call graph instead of the step graph
@@ -552,7 +556,7 @@ def main():
         mk = model if k == 0 else build_model(a, pc_start, device)
         mk.cuda_graphs = model.cuda_graphs
         lanes.append({"model": mk, "det": det if k == 0 else det0.clone(),
-                      "ring": dec_pack if k == 0 else torch.empty_like(dec_pack),
+                      "ring": dec_pack[k],
                       "counter": torch.zeros(1, dtype=torch.int32, device=device),
                       "stream": torch.cuda.current_stream() if k == 0 else torch.cuda.Stream(), "g": None, "out": None})
 
