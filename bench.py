@@ -700,16 +700,17 @@ def main():
     pw_ms = stages["pairwise"]
     pw_tf = pw_flop / (pw_ms / 1e3) / 1e12 if pw_ms > 0 else 0.0
     # the bound this kernel actually runs against (tools/micro/mma_rate.cu, profiles/README.md): a tcgen05.mma with
-    # M = 128, N <= 32 and a TMEM A operand issues every 32.6 clocks; 54 of them per 128-pair tile (3xTF32)
+    # M = 128 and a TMEM A operand issues every 32.6 clocks at N <= 32, 42 at N = 64; per 128-pair tile (3xTF32 with the
+    # hi | lo weight images merged along N): fuse_det 4 x (32.6 + 32.6), fuse_shape 5 x (42 + 32.6), res_coeff 9 x (42 + 32.6)
     sm_mhz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
     tiles = B * ((T + 7) // 8) * ((T + 15) // 16)
-    mma_floor_ms = tiles * 54 * 32.6 / 148.0 / (sm_mhz * 1e3)
+    mma_floor_ms = tiles * (8 * 32.6 + 14 * (42.0 + 32.6)) / 148.0 / (sm_mhz * 1e3)
     pair_kernel = {"kernel": "pairwise_tc_kernel<false> (second pairwise layers on tcgen05, 3xTF32)", "bound": "tensor",
                    "achieved": pw_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": pw_tf / tensor_peak,
                    "traffic": None, "algorithmic_flop_per_launch": pw_flop, "ms_per_launch": pw_ms,
                    "step_share": pw_ms / max(sum(stages.values()), 1e-9),
                    "mma_issue_floor_ms": mma_floor_ms, "frac_of_mma_issue_floor": mma_floor_ms / pw_ms if pw_ms > 0 else None,
-                   "note": "small-N tf32 UMMAs are issue-bound, not FLOP-bound: 32.6 clk per instruction (measured), "
+                   "note": "small-N tf32 UMMAs are issue-bound, not FLOP-bound: 32.6 / 42 clk per instruction (measured), "
                            "so the dense bf16 peak is the contract's denominator, the issue floor the attainable one"}
     pb = path_bytes(M, B, a.hw, bf16_w)
     dominant = pair_kernel if dom == "pairwise" else hbm_kernel

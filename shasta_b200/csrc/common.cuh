@@ -199,6 +199,9 @@ struct PackLayout {
   size_t tc32_begin;  // tf32 block: w2a hi, w2a lo (10x32x4 each), w2b hi, lo (18x32x4), w2c hi, lo (8x16x4)
   size_t tc32_w2a_hi, tc32_w2a_lo, tc32_w2b_hi, tc32_w2b_lo, tc32_w2c_hi, tc32_w2c_lo;
   size_t tc32_end;
+  // the same three matrices with the hi and lo images side by side along N ([k/4][2 n_pad][4]: rows 0..n_pad-1 = hi,
+  // n_pad..2 n_pad-1 = lo): one N = 2 n_pad MMA then forms A_hi B_hi and A_hi B_lo together (pairwise_tc.cu)
+  size_t tc32m_begin, tc32m_w2a, tc32m_w2b, tc32m_w2c, tc32m_end;
   size_t tc16_begin;  // bf16 block (counted in floats): w2a (6x32x8 bf16), w2b (10x32x8), w2c (4x16x8)
   size_t tc16_w2a, tc16_w2b, tc16_w2c;
   size_t tc16_end;
@@ -265,6 +268,11 @@ __host__ inline PackLayout pack_layout(int M) {
   P.tc32_w2c_hi = take(8 * 16 * 4);
   P.tc32_w2c_lo = take(8 * 16 * 4);
   P.tc32_end = o;
+  P.tc32m_begin = o;
+  P.tc32m_w2a = take(10 * 64 * 4);
+  P.tc32m_w2b = take(18 * 64 * 4);
+  P.tc32m_w2c = take(8 * 32 * 4);
+  P.tc32m_end = o;
   P.tc16_begin = o;
   P.tc16_w2a = take(6 * 32 * 8 / 2);   // K = 40 padded to 48 (3 MMA steps of 16), pad chunks stay zero
   P.tc16_w2b = take(10 * 32 * 8 / 2);  // K = 72 padded to 80

@@ -119,6 +119,19 @@ __global__ void tc3_pack_kernel(float* __restrict__ xhi, float* __restrict__ xlo
   }
 }
 
+// hi | lo images side by side along N: img[k/4][2 n_pad][4], rows n < n_pad = tf32 high parts, n_pad + n = low parts
+__global__ void umma_b_image_merged_kernel(float* __restrict__ img, const float* __restrict__ src, int src_ld,
+                                           int n_valid, int n_pad, int K) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pad * K) return;
+  const int n = idx / K, k = idx % K;
+  const float v = (n < n_valid) ? src[(size_t)n * src_ld + k] : 0.f;
+  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  const size_t o = (size_t)(k / 4) * (2 * n_pad * 4) + (k % 4);
+  img[o + (size_t)n * 4] = h;
+  img[o + (size_t)(n_pad + n) * 4] = v - h;
+}
+
 static int bimage(float* hi, float* lo, float* bf, const float* src, int src_ld, int n_valid, int n_pad, int K,
                   cudaStream_t s) {
   umma_b_image_kernel<<<(n_pad * K + 255) / 256, 256, 0, s>>>(hi, lo, reinterpret_cast<__nv_bfloat16*>(bf), src,
@@ -221,6 +234,12 @@ int launch_pack(const shasta_params_t& p, float* packed, cudaStream_t s) {
   if (rc) return rc;
   rc = bimage(packed + P.tc32_w2c_hi, packed + P.tc32_w2c_lo, packed + P.tc16_w2c, p.fuse_det_w[1], 32, 8, 16, 32, s);
   if (rc) return rc;
+  umma_b_image_merged_kernel<<<(32 * 40 + 255) / 256, 256, 0, s>>>(packed + P.tc32m_w2a, p.fuse_shape_w[1], 40, 20, 32, 40);
+  SHASTA_CHECK_LAUNCH("umma_b_image_merged_kernel");
+  umma_b_image_merged_kernel<<<(32 * 72 + 255) / 256, 256, 0, s>>>(packed + P.tc32m_w2b, p.res_coeff_w[1], 72, 18, 32, 72);
+  SHASTA_CHECK_LAUNCH("umma_b_image_merged_kernel");
+  umma_b_image_merged_kernel<<<(16 * 32 + 255) / 256, 256, 0, s>>>(packed + P.tc32m_w2c, p.fuse_det_w[1], 32, 8, 16, 32);
+  SHASTA_CHECK_LAUNCH("umma_b_image_merged_kernel");
   Tc3Src t3 = {p.fuse_det_w[1],    p.fuse_shape_w[1], p.res_coeff_w[1], p.fuse_shape_w[2], p.fuse_shape_b[2], p.fuse_shape_w[3],
                p.fuse_shape_b[3], p.res_coeff_w[2],  p.res_coeff_b[2], p.fuse_det_w[2],   p.fuse_det_b[2]};
   tc3_pack_kernel<<<(2 * 72 * 32 + 255) / 256, 256, 0, s>>>(packed + P.tc3_x_hi, packed + P.tc3_x_lo, packed + P.tc3_y_hi,

@@ -9,7 +9,12 @@
 // with the weights as pre-split, zero-padded B-operand images in shared memory (pack.cu). Accumulators come back
 // with tcgen05.ld; bias/ReLU, the tiny third/fourth layers, the hand-designed residuals and the weighted sum
 // (shasta.py:277-319) finish in the same thread.
-//   variant 1 (fp32 mode): kind::tf32, three MMAs per K step on hi/lo splits (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo)
+//   variant 1 (fp32 mode): kind::tf32, 3xTF32 on hi/lo splits (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo) as TWO MMAs per K
+//                          step: the hi and lo images of a weight matrix sit side by side along N, so one N = 2 n
+//                          instruction forms A_hi*B_hi and A_hi*B_lo into two accumulator halves (added in the
+//                          epilogue), a second N = n instruction adds A_lo*B_hi. A small tcgen05.mma costs 32.6
+//                          clocks for any N <= 32 and 42 at N = 64 (tools/micro/mma_rate.cu), so this is 36 instead of
+//                          54 instructions and 1 305 instead of 1 760 tensor-issue clocks per 128-pair tile.
 //   variant 2 (bf16 mode): kind::f16 with bf16 operands, one MMA per K step, fp32 accumulate.
 #include <cuda_bf16.h>
 
@@ -34,7 +39,11 @@ constexpr int kPtTmemCols = 256;
 constexpr int kColDetHi = 0, kColDetLo = 32;       // K = 32
 constexpr int kColShpHi = 64, kColShpLo = 104;     // K = 40
 constexpr int kColCofHi = 0, kColCofLo = 72;       // K = 72 (reuses the det/shape columns once their MMAs retired)
-constexpr int kColDShp = 144, kColDCof = 176, kColDDet = 208;
+constexpr int kColDShp = 144, kColDCof = 176, kColDDet = 208;   // bf16 mode: one accumulator per layer
+// fp32 mode: [main | lo-product] halves per layer. fuse_det (2 x 16) and fuse_shape (2 x 32) are drained into registers
+// before the res_coeff MMAs start (both worker groups arrive on bar_a(2) only after their tcgen05.ld), and the next
+// tile's fuse_det MMAs wait for group A, which has read res_coeff by then - so res_coeff (2 x 32) ALIASES them
+constexpr int kColMDet = 144, kColMShp = 176, kColMCof = 144;
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
@@ -140,7 +149,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
   // ---- shared memory carve-up: [B-operand images (128 B aligned)] [barriers] [small layers] [2 item buffers]
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
-  const int bimg_floats = BF16 ? (int)(P.tc16_end - P.tc16_begin) : (int)(P.tc32_end - P.tc32_begin);
+  const int bimg_floats = BF16 ? (int)(P.tc16_end - P.tc16_begin) : (int)(P.tc32m_end - P.tc32m_begin);
   float* bimg = reinterpret_cast<float*>(gbase);
   const uint32_t bars = sbase + bimg_floats * 4;                     // 11 mbarriers + tmem slot
   const int wbase = (int)P.l2a, wcount = (int)(P.pair_end - P.l2a);
@@ -166,7 +175,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
 
   // ---- per-CTA constants (all threads): weight images and the small layers ----
   {
-    const float4* src = reinterpret_cast<const float4*>(packed + (BF16 ? P.tc16_begin : P.tc32_begin));
+    const float4* src = reinterpret_cast<const float4*>(packed + (BF16 ? P.tc16_begin : P.tc32m_begin));
     for (int v = tid; v < bimg_floats / 4; v += kPtThreads) reinterpret_cast<float4*>(bimg)[v] = __ldg(src + v);
     for (int v = tid; v < wcount / 4; v += kPtThreads)
       reinterpret_cast<float4*>(Ws)[v] = __ldg(reinterpret_cast<const float4*>(packed + wbase) + v);
@@ -223,27 +232,29 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         off_c_hi = (uint32_t)(P.tc16_w2c - P.tc16_begin) * 4;
         off_a_lo = off_b_lo = off_c_lo = 0;
       } else {
-        off_a_hi = (uint32_t)(P.tc32_w2a_hi - P.tc32_begin) * 4, off_a_lo = (uint32_t)(P.tc32_w2a_lo - P.tc32_begin) * 4;
-        off_b_hi = (uint32_t)(P.tc32_w2b_hi - P.tc32_begin) * 4, off_b_lo = (uint32_t)(P.tc32_w2b_lo - P.tc32_begin) * 4;
-        off_c_hi = (uint32_t)(P.tc32_w2c_hi - P.tc32_begin) * 4, off_c_lo = (uint32_t)(P.tc32_w2c_lo - P.tc32_begin) * 4;
+        off_a_hi = (uint32_t)(P.tc32m_w2a - P.tc32m_begin) * 4, off_b_hi = (uint32_t)(P.tc32m_w2b - P.tc32m_begin) * 4;
+        off_c_hi = (uint32_t)(P.tc32m_w2c - P.tc32m_begin) * 4;
+        off_a_lo = off_b_lo = off_c_lo = 0;   // (merged images: the lo half follows the hi half along N)
       }
       constexpr uint32_t fmt = BF16 ? kFmtBF16 : kFmtTF32;
       constexpr uint32_t idesc32 = umma_idesc(fmt, 128, 32), idesc16 = umma_idesc(fmt, 128, 16);
+      constexpr uint32_t idesc64 = umma_idesc(fmt, 128, 64);
       // one K step = 32 bytes of K per row = 2 chunks of the B image = 8 A columns (tf32: 8 x 32 bit, bf16: 16 x 16 bit)
       auto run = [&](int ksteps, int n, uint32_t idesc, uint32_t d_col, int a_hi, int a_lo, uint32_t b_hi,
                      uint32_t b_lo) {
-        const uint32_t lbo = (uint32_t)n * 16u;
+        // fp32 mode: the image holds 2 n rows per K chunk (hi | lo), bf16 mode n rows
+        const uint32_t lbo = (uint32_t)(BF16 ? n : 2 * n) * 16u;
+        const uint32_t idesc_wide = (n == 16) ? idesc32 : idesc64;
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t dbh = umma_desc_noswz(bi + b_hi + (uint32_t)k * 2u * lbo, lbo, 128);
           if (BF16) {
             mma_ts_f16(tmem + d_col, tmem + (uint32_t)(a_hi + 8 * k), dbh, idesc, k != 0);
           } else {
-            const uint64_t dbl = umma_desc_noswz(bi + b_lo + (uint32_t)k * 2u * lbo, lbo, 128);
-            mma_ts_tf32(tmem + d_col, tmem + (uint32_t)(a_hi + 8 * k), dbh, idesc, k != 0);
-            mma_ts_tf32(tmem + d_col, tmem + (uint32_t)(a_lo + 8 * k), dbh, idesc, 1);
-            mma_ts_tf32(tmem + d_col, tmem + (uint32_t)(a_hi + 8 * k), dbl, idesc, 1);
+            mma_ts_tf32(tmem + d_col, tmem + (uint32_t)(a_hi + 8 * k), dbh, idesc_wide, k != 0);   // A_hi [B_hi | B_lo]
+            mma_ts_tf32(tmem + d_col, tmem + (uint32_t)(a_lo + 8 * k), dbh, idesc, 1);             // A_lo  B_hi
           }
         }
+        (void)b_lo;
       };
       uint32_t seq = 0;
       for (int it = 0;; ++it) {
@@ -257,15 +268,15 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
           const uint32_t ph = seq & 1;
           mbar_wait_sleep(bar_a(0), ph);
           tc_fence_after();
-          run(BF16 ? 2 : 4, 16, idesc16, kColDDet, kColDetHi, kColDetLo, off_c_hi, off_c_lo);   // fuse_det.2, K = 32
+          run(BF16 ? 2 : 4, 16, idesc16, BF16 ? kColDDet : kColMDet, kColDetHi, kColDetLo, off_c_hi, off_c_lo);   // fuse_det.2, K = 32
           mma_commit(bar_d(0));
           mbar_wait_sleep(bar_a(1), ph);
           tc_fence_after();
-          run(BF16 ? 3 : 5, 32, idesc32, kColDShp, kColShpHi, kColShpLo, off_a_hi, off_a_lo);   // fuse_shape.2, K = 40
+          run(BF16 ? 3 : 5, 32, idesc32, BF16 ? kColDShp : kColMShp, kColShpHi, kColShpLo, off_a_hi, off_a_lo);   // fuse_shape.2, K = 40
           mma_commit(bar_d(1));
           mbar_wait_sleep(bar_a(2), ph);
           tc_fence_after();
-          run(BF16 ? 5 : 9, 32, idesc32, kColDCof, kColCofHi, kColCofLo, off_b_hi, off_b_lo);   // res_coeff.2, K = 72
+          run(BF16 ? 5 : 9, 32, idesc32, BF16 ? kColDCof : kColMCof, kColCofHi, kColCofLo, off_b_hi, off_b_lo);   // res_coeff.2, K = 72
           mma_commit(bar_d(2));
         }
       }
@@ -330,8 +341,17 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         mbar_wait_sleep(bar_d(1), ph);
         tc_fence_after();
         uint32_t vd[8];
-        tmem_ld8(lane_base + kColDDet, vd);
-        tmem_ld_wait();
+        if (BF16) {
+          tmem_ld8(lane_base + kColDDet, vd);
+          tmem_ld_wait();
+        } else {   // main + lo-product halves of the fuse_det accumulator
+          uint32_t vl[8];
+          tmem_ld8(lane_base + kColMDet, vd);
+          tmem_ld8(lane_base + kColMDet + 16, vl);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) vd[k] = __float_as_uint(__uint_as_float(vd[k]) + __uint_as_float(vl[k]));
+        }
         tc_fence_before();
         build_a<BF16, 40>(prow, qrow, 40, lane_base, kColCofHi, kColCofLo);          // res_coeff K 0..39
         tmem_st_wait();
@@ -356,9 +376,22 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         mbar_wait_sleep(bar_d(2), ph);
         tc_fence_after();
         uint32_t v[16], v2[8];
-        tmem_ld16(lane_base + kColDCof, v);
-        tmem_ld8(lane_base + kColDCof + 16, v2);
-        tmem_ld_wait();
+        if (BF16) {
+          tmem_ld16(lane_base + kColDCof, v);
+          tmem_ld8(lane_base + kColDCof + 16, v2);
+          tmem_ld_wait();
+        } else {
+          uint32_t w[16], w2[8];
+          tmem_ld16(lane_base + kColMCof, v);
+          tmem_ld8(lane_base + kColMCof + 16, v2);
+          tmem_ld16(lane_base + kColMCof + 32, w);
+          tmem_ld8(lane_base + kColMCof + 48, w2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + __uint_as_float(w[k]));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v2[k] = __float_as_uint(__uint_as_float(v2[k]) + __uint_as_float(w2[k]));
+        }
         tc_fence_before();
         const float4 b3 = *reinterpret_cast<const float4*>(B3b);
         float alpha = b3.x, beta = b3.y, omega = b3.z;
@@ -393,9 +426,22 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         mbar_wait_sleep(bar_d(1), ph);
         tc_fence_after();
         uint32_t v[16], v2[8];
-        tmem_ld16(lane_base + kColDShp, v);
-        tmem_ld8(lane_base + kColDShp + 16, v2);
-        tmem_ld_wait();
+        if (BF16) {
+          tmem_ld16(lane_base + kColDShp, v);
+          tmem_ld8(lane_base + kColDShp + 16, v2);
+          tmem_ld_wait();
+        } else {
+          uint32_t w[16], w2[8];
+          tmem_ld16(lane_base + kColMShp, v);
+          tmem_ld8(lane_base + kColMShp + 16, v2);
+          tmem_ld16(lane_base + kColMShp + 32, w);
+          tmem_ld8(lane_base + kColMShp + 48, w2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + __uint_as_float(w[k]));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v2[k] = __float_as_uint(__uint_as_float(v2[k]) + __uint_as_float(w2[k]));
+        }
         tc_fence_before();
         if (BF16) {
           // bf16 columns: res_coeff K 40..71 = packed columns 20..35, then zero padding 36..39 (K 72 -> 80)
@@ -455,7 +501,7 @@ int launch_pairwise_tc(const float* packed, int B, int M, float* ws, const WsLay
   const PackLayout P = pack_layout(M);
   const int T = M + 2;
   const bool bf16 = variant == 2;
-  const size_t bimg = (bf16 ? (P.tc16_end - P.tc16_begin) : (P.tc32_end - P.tc32_begin)) * sizeof(float);
+  const size_t bimg = (bf16 ? (P.tc16_end - P.tc16_begin) : (P.tc32m_end - P.tc32m_begin)) * sizeof(float);
   const size_t smem = 128 + bimg + 128 + sizeof(float) * ((P.pair_end - P.l2a) + 256 + 2 * PtBuf::floats);
   static OncePerDevice configured[2];
   if (configured[bf16].first()) {
