@@ -33,20 +33,24 @@ __device__ __forceinline__ int32_t* dec_plane(const DecodeArgs& a, int32_t* slot
 }
 
 // Row n of frame pair b. Every lane brings its first maximum (best, barg) over the columns d < n_det it holds
-// (barg = 0x7fffffff when it holds none) and the probabilities of the two anchor columns (any lane may hold them: pass
-// -inf elsewhere, they are max-reduced). Whole warp must call.
+// (barg = 0x7fffffff when it holds none) and, in the lanes that hold them (column d lives in lane d % 32), the
+// probabilities of the two anchor columns d = M (dead) and d = M + 1 (FN). Whole warp must call.
 __device__ __forceinline__ void dec_row_finish(const DecodeArgs& a, int32_t* slot, int b, int n, float best, int barg,
                                                float v_dead, float v_fn, int lane) {
   const int M = a.M;
   const int np = a.n_prev[b], nd = a.n_det[b];
+  // probabilities are non-negative floats: their bit patterns order like the values, so (value bits, ~index) packs
+  // into one 64-bit key whose maximum is the first maximum - two shuffles per round instead of three
+  unsigned long long key = ((unsigned long long)__float_as_uint(fmaxf(best, 0.f)) << 32) | (unsigned)(0x7fffffff - barg);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oa = __shfl_xor_sync(0xffffffffu, barg, o);
-    if (ob > best || (ob == best && oa < barg)) best = ob, barg = oa;
-    v_dead = fmaxf(v_dead, __shfl_xor_sync(0xffffffffu, v_dead, o));
-    v_fn = fmaxf(v_fn, __shfl_xor_sync(0xffffffffu, v_fn, o));
+    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
+    key = ok > key ? ok : key;
   }
+  best = __uint_as_float((unsigned)(key >> 32));
+  barg = 0x7fffffff - (int)(unsigned)(key & 0xffffffffu);
+  v_dead = __shfl_sync(0xffffffffu, v_dead, M & 31);
+  v_fn = __shfl_sync(0xffffffffu, v_fn, (M + 1) & 31);
   if (lane != 0) return;
   int state = -1, arg = -1;
   float score = 0.f;
