@@ -682,7 +682,7 @@ def main():
     traffic = None
     if tc_path and M == 200 and B == 64 and not a.bf16:   # dram bytes of one launch from the committed ncu capture
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[
                 "anchor_hidden_tc2_kernel<64>"]["traffic_bytes_per_launch"]
         except Exception:  # noqa: BLE001
             traffic = None
