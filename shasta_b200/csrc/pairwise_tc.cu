@@ -336,6 +336,17 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         tc_fence_before();
         mbar_arrive(bar_a(0));
 
+        // the hand-designed residuals need no MMA result: they fill the wait for the first two GEMMs    shasta.py:277-283
+        const float4 ac0 = *reinterpret_cast<const float4*>(Ac + dl * 8);
+        const float4 ac1 = *reinterpret_cast<const float4*>(Ac + dl * 8 + 4);
+        const float dx = ap0.x - ac0.x, dy = ap0.y - ac0.y, dz = ap0.z - ac0.z;
+        float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        dist = __fdiv_rn(dist, fmaxf(Cn[dl], 1e-12f));
+        const float dim = __fadd_rn(__fadd_rn(fabsf(ap0.w - ac0.w), fabsf(ap1.x - ac1.x)), fabsf(ap1.y - ac1.y));
+        const float dc = ap1.z - ac1.z, ds = ap1.w - ac1.w;
+        const float rot = sqrtf(__fadd_rn(__fmul_rn(dc, dc), __fmul_rn(ds, ds)));
+        const float res_dist = __fadd_rn(__fadd_rn(dist, dim), rot);
+
         // both first MMAs must have retired before their TMEM columns are recycled for res_coeff
         mbar_wait_sleep(bar_d(0), ph);
         mbar_wait_sleep(bar_d(1), ph);
@@ -353,7 +364,10 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
           for (int k = 0; k < 8; ++k) vd[k] = __float_as_uint(__uint_as_float(vd[k]) + __uint_as_float(vl[k]));
         }
         tc_fence_before();
-        build_a<BF16, 40>(prow, qrow, 40, lane_base, kColCofHi, kColCofLo);          // res_coeff K 0..39
+        if (BF16)
+          build_a<true, 40>(prow, qrow, 40, lane_base, kColCofHi, kColCofLo);         // res_coeff K 0..39
+        else
+          build_a<false, 48>(prow, qrow, 40, lane_base, kColCofHi, kColCofLo);        // res_coeff K 0..47
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_a(2));
@@ -362,15 +376,6 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         float fused = B3c[0];
 #pragma unroll
         for (int k = 0; k < 8; ++k) fused = fmaf(relu_f(__uint_as_float(vd[k]) + B2c[k]), W3c[k], fused);
-        const float4 ac0 = *reinterpret_cast<const float4*>(Ac + dl * 8);
-        const float4 ac1 = *reinterpret_cast<const float4*>(Ac + dl * 8 + 4);
-        const float dx = ap0.x - ac0.x, dy = ap0.y - ac0.y, dz = ap0.z - ac0.z;
-        float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        dist = __fdiv_rn(dist, fmaxf(Cn[dl], 1e-12f));
-        const float dim = __fadd_rn(__fadd_rn(fabsf(ap0.w - ac0.w), fabsf(ap1.x - ac1.x)), fabsf(ap1.y - ac1.y));
-        const float dc = ap1.z - ac1.z, ds = ap1.w - ac1.w;
-        const float rot = sqrtf(__fadd_rn(__fmul_rn(dc, dc), __fmul_rn(ds, ds)));
-        const float res_dist = __fadd_rn(__fadd_rn(dist, dim), rot);
 
         // res_coeff epilogue 18 -> 3
         mbar_wait_sleep(bar_d(2), ph);
@@ -449,7 +454,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
           const uint32_t z[4] = {0u, 0u, 0u, 0u};
           tmem_st4(lane_base + (uint32_t)(kColCofHi + 36), z);
         } else {
-          build_a<false, 32>(prow, qrow, 80, lane_base, kColCofHi + 40, kColCofLo + 40);  // res_coeff K 40..71
+          build_a<false, 24>(prow, qrow, 88, lane_base, kColCofHi + 48, kColCofLo + 48);  // res_coeff K 48..71
         }
         tmem_st_wait();
         tc_fence_before();

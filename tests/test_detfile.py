@@ -163,3 +163,22 @@ def test_json_dirs_to_file_and_results_json(tmp_path):
     assert back["results"] == results
     assert back["meta"] == {"use_camera": False, "use_lidar": True, "use_radar": False, "use_map": False,
                             "use_external": False}
+
+
+def test_cls_info_is_the_global_frame_entry_not_the_sensor_box(tmp_path):
+    """the emitted detection dicts must carry the cls_info (GLOBAL frame) translation /
+    rotation / velocity, not the det_path (SENSOR frame) box the head's input is packed from; further keys survive."""
+    frames = _frames(21, n_scenes=1, n_frames=3)
+    path = str(tmp_path / "g.shdb")
+    detfile.write_detection_file(path, frames)
+    df = detfile.DetectionFile(path)
+    differs = extras = 0
+    for i, f in enumerate(frames):
+        b, n = int(df.row_begin[i]), int(df.row_count[i])
+        got = df.cls_info(range(b, b + n), f["token"])
+        assert got == f["cls"]
+        for d, c in zip(f["dets"], got):
+            differs += c["translation"] != d[0:3]
+            extras += "num_pts" in c
+            assert df.rows[b:b + n][:, 0:3].tolist() == [x[0:3] for x in f["dets"]]
+    assert differs > 0 and extras > 0

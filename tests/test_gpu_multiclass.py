@@ -166,3 +166,43 @@ def test_detection_file_provider_matches_json_loop(tmp_path):
                 assert abs(x["ref_detection_score"] - y["ref_detection_score"]) < 1e-6
                 flags += bool(x.get("newborn")) + bool(x.get("dead")) + bool(x.get("FN"))
     assert flags > 0
+
+
+def test_step_graphs_follow_weight_updates_and_data_writes():
+    """a lane's captured step graph bakes in the packed-weight buffer. After load_state_dict (new packed
+    buffer) and after an in-place ``param.data`` update + ``invalidate_packed()`` the lane must produce what an eager
+    model with the same weights produces - not replay the stale capture."""
+    M, H = 20, 32
+    pc_start = (-H * 0.3, -H * 0.3)
+    data = synthetic.make_frame_pairs(3, M, H, H, 77, pc_start=pc_start)
+    w_a = synthetic.make_weights(M, seed=41, peaky=300.0)
+    w_b = synthetic.make_weights(M, seed=42, peaky=300.0)
+    model = G.make_model(M, pc_start, w_a)
+    lane = multiclass.ClassLane("x", model, step_graphs=True)
+    batch = {"bev": G.t(data["bev"]), "prev_bev": G.t(data["prev_bev"]), "det_boxes": G.t(data["det_boxes"]),
+             "prev_det_boxes": G.t(data["prev_det_boxes"]),
+             "n_prev": torch.from_numpy(data["n_prev"].astype(np.int32)).to(G.DEV),
+             "n_det": torch.from_numpy(data["n_det"].astype(np.int32)).to(G.DEV)}
+
+    def eager(weights):
+        ref = G.make_model(M, pc_start, weights)
+        with torch.no_grad():
+            m1, m2 = ref.affinity(batch["bev"], batch["prev_bev"], batch["det_boxes"].clone(), batch["prev_det_boxes"])
+            d = ref.decode(m1, m2, batch["n_prev"], batch["n_det"])
+        return torch.stack([d[k].view(torch.int32) if k.endswith("prob") else d[k] for k in multiclass.DECODE_FIELDS])
+
+    with torch.no_grad():
+        first = lane.step(batch).clone()
+        assert torch.equal(first, eager(w_a))
+        assert torch.equal(lane.step(batch), first)                      # replay of the captured graph
+        from shasta_b200 import load_matching_state_dict
+        load_matching_state_dict(model, {k: torch.from_numpy(v) for k, v in w_b.items()})
+        model.invalidate_packed()
+        second = lane.step(batch).clone()
+        assert torch.equal(second, eager(w_b)) and not torch.equal(second, first)
+        # in-place update through .data does not bump the tensor version: invalidate_packed() is the documented hook
+        model.aff[10].weight.data.mul_(0.5)
+        model.invalidate_packed()
+        w_c = {k: v.copy() for k, v in w_b.items()}
+        w_c["aff.10.weight"] = w_c["aff.10.weight"] * np.float32(0.5)
+        assert torch.equal(lane.step(batch), eager(w_c))
