@@ -29,8 +29,12 @@ using namespace tc;
 // = up to 2 x 2 MMA tiles) handed out by an atomic counter. A producer warp stages the next item's operands
 // (PROJ_PREV / PROJ_CUR rows, AUX rows, column norms) with cp.async.bulk into the other half of a double buffer while
 // the workers are busy; the weight images are staged once per CTA.
-constexpr int kPtTT = 16;           // t rows per item (two 8-row tile rows)
-constexpr int kPtDT = 32;           // d columns per item (two 16-column tile columns)
+// An MMA tile is 16 t rows x 8 d columns; inside a warp the 32 lanes are 8 t x 4 d. The ncu capture of the 8 x 16
+// lane layout showed the shared-memory data pipe at 75 % of its peak (45 M wavefronts): per 16-byte operand load a
+// warp then touched 2 distinct p rows (1 wavefront) and 16 distinct q rows (256 bytes = 2 wavefronts); with 8 x 4 it
+// touches 8 p rows (128 bytes) and 4 q rows (64 bytes) = 1 + 1 wavefronts - a third less traffic for the operand build.
+constexpr int kPtTT = 16;           // t rows per item (one tile row)
+constexpr int kPtDT = 32;           // d columns per item (four 8-column tiles)
 constexpr int kPtQStride = 148;     // floats per d row of the staged PROJ_CUR tile (148 % 32 = 20: conflict-free LDS.128)
 constexpr int kPtThreads = 320;     // 8 worker warps (two threads per pair) + MMA warp + producer warp
 constexpr int kPtTmemCols = 256;
@@ -118,7 +122,7 @@ __device__ __forceinline__ void build_a(const float* __restrict__ prow, const fl
 
 struct PtBuf {   // float offsets of one item buffer
   static constexpr int ps = 0;                                  // [16][144]
-  static constexpr int qs = ps + kPtTT * kProj;                 // [32][148]
+  static constexpr int qs = ps + kPtTT * kPtQStride;            // [32][148]   (ps: [16][148], both padded rows)
   static constexpr int auxp = qs + kPtDT * kPtQStride;          // [16][8]
   static constexpr int auxc = auxp + kPtTT * 8;                 // [32][8]
   static constexpr int cn = auxc + kPtDT * 8;                   // [32]
@@ -133,12 +137,21 @@ __device__ __forceinline__ void pt_bulk_load(uint32_t dst, const void* src, uint
                : "memory");
 }
 
+// barrier wait of the workers / issuer / producer: try_wait with a suspend-time hint of wait_ns, or a plain try_wait
+// loop when wait_ns == 0
+__device__ __forceinline__ void pt_wait(uint32_t wait_ns, uint32_t bar, uint32_t parity) {
+  if (wait_ns == 0)
+    mbar_wait(bar, parity);
+  else
+    mbar_wait_sleep(bar, parity, wait_ns);
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(kPtThreads, 2)
 pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, const float* __restrict__ proj_prev,
                    const float* __restrict__ proj_cur_t, const float* __restrict__ aux_prev,
                    const float* __restrict__ aux_cur, const float* __restrict__ colnorm,
-                   float* __restrict__ residual, int* __restrict__ counter) {
+                   float* __restrict__ residual, int* __restrict__ counter, uint32_t wait_ns) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int T = M + 2, D = M + 2;
   const int RS = row_stride(M);
@@ -190,7 +203,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
     // ===================== producer: next item's operands into the free buffer =====================
     for (int it = 0;; ++it) {
       const int buf = it & 1;
-      if (it >= 2) mbar_wait_sleep(item_empty(buf), (uint32_t)((it >> 1) - 1) & 1u);
+      if (it >= 2) pt_wait(wait_ns, item_empty(buf), (uint32_t)((it >> 1) - 1) & 1u);
       int item = 0;
       if (lane == 0) item = atomicAdd(counter, 1);
       item = __shfl_sync(0xffffffffu, item, 0);
@@ -212,12 +225,14 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
       const uint32_t bu = bufs_u32 + (uint32_t)(buf * PtBuf::floats) * 4u;
       if (lane == 0) {
         mbar_expect_tx(item_full(buf), (uint32_t)(nt + nd) * (kProj + 8) * 4u);
-        pt_bulk_load(bu + PtBuf::ps * 4, proj_prev + ((size_t)b * T + t0) * kProj, (uint32_t)nt * kProj * 4u, item_full(buf));
         pt_bulk_load(bu + PtBuf::auxp * 4, aux_prev + ((size_t)b * T + t0) * 8, (uint32_t)nt * 32u, item_full(buf));
         pt_bulk_load(bu + PtBuf::auxc * 4, aux_cur + ((size_t)b * T + d0) * 8, (uint32_t)nd * 32u, item_full(buf));
       }
       __syncwarp();
-      if (lane < nd)   // PROJ_CUR_T rows into rows padded to 148 floats
+      if (lane < nt)   // PROJ_PREV rows into rows padded to 148 floats (conflict-free 16-byte reads down a column)
+        pt_bulk_load(bu + (PtBuf::ps + lane * kPtQStride) * 4, proj_prev + ((size_t)b * T + t0 + lane) * kProj,
+                     kProj * 4u, item_full(buf));
+      if (lane < nd)   // PROJ_CUR_T rows likewise
         pt_bulk_load(bu + (PtBuf::qs + lane * kPtQStride) * 4, proj_cur_t + ((size_t)b * T + d0 + lane) * kProj,
                      kProj * 4u, item_full(buf));
     }
@@ -259,22 +274,23 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
       uint32_t seq = 0;
       for (int it = 0;; ++it) {
         const int buf = it & 1;
-        mbar_wait_sleep(item_full(buf), (uint32_t)(it >> 1) & 1u);
+        pt_wait(wait_ns, item_full(buf), (uint32_t)(it >> 1) & 1u);
         const volatile int* desc = reinterpret_cast<const volatile int*>(bufs + buf * PtBuf::floats + PtBuf::desc);
         if (desc[3] == 0) break;
         const int t0 = desc[1], d0 = desc[2];
-        const int ntiles = min(kPtDT / 16, (D - d0 + 15) / 16) * min(kPtTT / 8, (T - t0 + 7) / 8);
+        const int ntiles = min(kPtDT / 8, (D - d0 + 7) / 8);
+        (void)t0;
         for (int tile = 0; tile < ntiles; ++tile, ++seq) {
           const uint32_t ph = seq & 1;
-          mbar_wait_sleep(bar_a(0), ph);
+          pt_wait(wait_ns, bar_a(0), ph);
           tc_fence_after();
           run(BF16 ? 2 : 4, 16, idesc16, BF16 ? kColDDet : kColMDet, kColDetHi, kColDetLo, off_c_hi, off_c_lo);   // fuse_det.2, K = 32
           mma_commit(bar_d(0));
-          mbar_wait_sleep(bar_a(1), ph);
+          pt_wait(wait_ns, bar_a(1), ph);
           tc_fence_after();
           run(BF16 ? 3 : 5, 32, idesc32, BF16 ? kColDShp : kColMShp, kColShpHi, kColShpLo, off_a_hi, off_a_lo);   // fuse_shape.2, K = 40
           mma_commit(bar_d(1));
-          mbar_wait_sleep(bar_a(2), ph);
+          pt_wait(wait_ns, bar_a(2), ph);
           tc_fence_after();
           run(BF16 ? 5 : 9, 32, idesc32, BF16 ? kColDCof : kColMCof, kColCofHi, kColCofLo, off_b_hi, off_b_lo);   // res_coeff.2, K = 72
           mma_commit(bar_d(2));
@@ -287,7 +303,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
     // group B (warps 4-7): fuse_shape operand, last 32 K of res_coeff; epilogue of fuse_shape (the heaviest)
     const bool grp_b = warp >= 4;
     const int r = tid & 127;           // pair row inside the tile == TMEM lane
-    const int ti = r >> 4, di = r & 15;
+    const int ti = ((warp >> 1) & 1) * 8 + (lane >> 2), di = (warp & 1) * 4 + (lane & 3);   // 16 t x 8 d tile
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float* B2a = Ws + (P.l2a_b - wbase);
     const float* B2b = Ws + (P.l2b_b - wbase);
@@ -304,7 +320,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
     uint32_t seq = 0;
     for (int it = 0;; ++it) {
       const int buf = it & 1;
-      mbar_wait_sleep(item_full(buf), (uint32_t)(it >> 1) & 1u);
+      pt_wait(wait_ns, item_full(buf), (uint32_t)(it >> 1) & 1u);
       const float* bf = bufs + buf * PtBuf::floats;
       const int* desc = reinterpret_cast<const int*>(bf + PtBuf::desc);
       if (desc[3] == 0) break;
@@ -315,16 +331,14 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
       const float* Ac = bf + PtBuf::auxc;
       const float* Cn = bf + PtBuf::cn;
       // only the tiles that contain real pairs
-      const int ntd = min(kPtDT / 16, (D - d0 + 15) / 16);
-      const int ntt = min(kPtTT / 8, (T - t0 + 7) / 8);
-      const int ntiles = ntd * ntt;
+      const int ntiles = min(kPtDT / 8, (D - d0 + 7) / 8);
 
     for (int tile = 0; tile < ntiles; ++tile, ++seq) {
       const uint32_t ph = seq & 1;
-      const int tl = ((ntd == 2) ? (tile >> 1) : tile) * 8 + ti;     // row of the staged PROJ_PREV block
-      const int dl = ((ntd == 2) ? (tile & 1) : 0) * 16 + di;        // row of the staged PROJ_CUR block
+      const int tl = ti;                  // row of the staged PROJ_PREV block
+      const int dl = tile * 8 + di;       // row of the staged PROJ_CUR block
       const int t = t0 + tl;
-      const float* prow = Ps + tl * kProj;
+      const float* prow = Ps + tl * kPtQStride;
       const float* qrow = Qs + dl * kPtQStride;
       const float4 ap0 = *reinterpret_cast<const float4*>(Ap + tl * 8);
       const float4 ap1 = *reinterpret_cast<const float4*>(Ap + tl * 8 + 4);
@@ -348,8 +362,8 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         const float res_dist = __fadd_rn(__fadd_rn(dist, dim), rot);
 
         // both first MMAs must have retired before their TMEM columns are recycled for res_coeff
-        mbar_wait_sleep(bar_d(0), ph);
-        mbar_wait_sleep(bar_d(1), ph);
+        pt_wait(wait_ns, bar_d(0), ph);
+        pt_wait(wait_ns, bar_d(1), ph);
         tc_fence_after();
         uint32_t vd[8];
         if (BF16) {
@@ -378,7 +392,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         for (int k = 0; k < 8; ++k) fused = fmaf(relu_f(__uint_as_float(vd[k]) + B2c[k]), W3c[k], fused);
 
         // res_coeff epilogue 18 -> 3
-        mbar_wait_sleep(bar_d(2), ph);
+        pt_wait(wait_ns, bar_d(2), ph);
         tc_fence_after();
         uint32_t v[16], v2[8];
         if (BF16) {
@@ -408,7 +422,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
           beta = fmaf(h, w.y, beta);
           omega = fmaf(h, w.z, omega);
         }
-        mbar_wait_sleep(bar_s, ph);
+        pt_wait(wait_ns, bar_s, ph);
         const float shape = Sh[(seq & 1) * 128 + r];
         const float out = __fadd_rn(__fadd_rn(__fmul_rn(alpha, fused), __fmul_rn(beta, res_dist)),
                                     __fmul_rn(omega, shape));
@@ -427,8 +441,8 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         tc_fence_before();
         mbar_arrive(bar_a(1));
 
-        mbar_wait_sleep(bar_d(0), ph);
-        mbar_wait_sleep(bar_d(1), ph);
+        pt_wait(wait_ns, bar_d(0), ph);
+        pt_wait(wait_ns, bar_d(1), ph);
         tc_fence_after();
         uint32_t v[16], v2[8];
         if (BF16) {
@@ -482,7 +496,7 @@ pairwise_tc_kernel(const float* __restrict__ packed, PackLayout P, int B, int M,
         Sh[(seq & 1) * 128 + r] = sres;
         mbar_arrive(bar_s);   // mbarrier arrive has release semantics: the shared-memory write above is visible
         // the res_coeff MMAs read this group's TMEM columns: they must retire before the next tile rewrites them
-        mbar_wait_sleep(bar_d(2), ph);
+        pt_wait(wait_ns, bar_d(2), ph);
         tc_fence_after();
       }
     }   // tiles of the item
@@ -521,6 +535,9 @@ int launch_pairwise_tc(const float* packed, int B, int M, float* ws, const WsLay
   const long long nitems = (long long)B * ((T + kPtTT - 1) / kPtTT) * ((T + kPtDT - 1) / kPtDT);
   const int grid = (int)(nitems < 2LL * sm_count ? nitems : 2LL * sm_count);   // persistent: two CTAs per SM
   int* counter = reinterpret_cast<int*>(ws + L.off[SHASTA_WS_COUNTERS]);
+  // experiment knob (bench.py --dbg 0x100 * k): suspend-time hint of the barrier waits = 100 ns * k; 0xff00 = spin
+  const int knob = (g_options[2] >> 8) & 0xff;
+  const uint32_t wait_ns = knob == 0 ? 20000u : (knob == 0xff ? 0u : 100u * (uint32_t)knob);
   SHASTA_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
   const float* pp = ws + L.off[SHASTA_WS_PROJ_PREV];
   const float* pc = ws + L.off[SHASTA_WS_PROJ_CUR_T];
@@ -529,9 +546,9 @@ int launch_pairwise_tc(const float* packed, int B, int M, float* ws, const WsLay
   const float* cn = ws + L.off[SHASTA_WS_COLNORM];
   float* res = ws + L.off[SHASTA_WS_RESIDUAL];
   if (bf16)
-    pairwise_tc_kernel<true><<<grid, kPtThreads, smem, s>>>(packed, P, B, M, pp, pc, ap, ac, cn, res, counter);
+    pairwise_tc_kernel<true><<<grid, kPtThreads, smem, s>>>(packed, P, B, M, pp, pc, ap, ac, cn, res, counter, wait_ns);
   else
-    pairwise_tc_kernel<false><<<grid, kPtThreads, smem, s>>>(packed, P, B, M, pp, pc, ap, ac, cn, res, counter);
+    pairwise_tc_kernel<false><<<grid, kPtThreads, smem, s>>>(packed, P, B, M, pp, pc, ap, ac, cn, res, counter, wait_ns);
   SHASTA_CHECK_LAUNCH("pairwise_tc_kernel");
   return 0;
 }
