@@ -77,6 +77,17 @@ def config_dict(a, extra=None):
          "l2_policy": "inputs larger than L2: 1.03 GB of streamed weights + %.1f GB of BEV maps per step vs 126 MB L2"
                       % (2 * a.batch * a.hw * a.hw * 64 * 4 / 1e9),
          "parallelism": "independent frame-pair shards per GPU (no data-path collective)"}
+    try:   # recorded B sweep of this code (profiles/r2_batch_sweep.json): which frames-per-step is the best throughput
+        rows = json.load(open(os.path.join(ROOT, "profiles", "r2_batch_sweep.json")))["rows"]
+        best = max(rows, key=lambda r: r["frame_pairs_per_s"])
+        same = max((r for r in rows if r["batch"] == 64), key=lambda r: r["frame_pairs_per_s"])
+        c["batch_sweep_recorded"] = {"file": "profiles/r2_batch_sweep.json", "best_batch": best["batch"],
+                                     "best_frame_pairs_per_s": best["frame_pairs_per_s"],
+                                     "batch_64_same_box": same["frame_pairs_per_s"],
+                                     "note": "larger --batch amortises the 1.03 GB weight stream over more pairs "
+                                             "(one BN = 128 GEMM tile up to 128; two passes above)"}
+    except Exception:  # noqa: BLE001
+        pass
     if extra:
         c.update(extra)
     return c
