@@ -194,7 +194,8 @@ SHASTA_API int shasta_bilinear_f32(const float* im, int height, int width, int c
 /* shasta.py:121-161 get_box_center (num_point = 5) + bird_eye_view.py:18-41 BEVFeatureExtractor.forward for one
  * frame: bev (B,H,W,64), boxes (B,M,box_stride>=7) [x,y,z,w,l,h,yaw,..] -> feat rows [0,M) of a (B,*,320)
  * array whose batch stride is feat_batch_stride floats. variant: 0 = vectorised LDG sampler,
- * 1 = cp.async.bulk (TMA) shared-memory-staged sampler. */
+ * 1 = cp.async.bulk (TMA) shared-memory-staged sampler, 2 = narrow persistent grid (host-resident maps),
+ * 3 = one 4-D TMA box per sample point. All four produce the same bits. */
 SHASTA_API int shasta_gather_f32(const float* bev, const float* boxes, int box_stride, int batch, int max_obj,
                       const shasta_geom_t* host_geom, float* feat, size_t feat_batch_stride, int variant,
                       shasta_stream_t stream);
@@ -229,13 +230,15 @@ SHASTA_API int shasta_aff_softmax_f32(const float* packed, int batch, int max_ob
  * det_boxes/prev_det_boxes (B,M,11). det_boxes[:,:,:2] is back-projected IN PLACE like the reference.
  * Outputs matched1 (B,M,M+2), matched2 (B,M+2,M); the anchors stay in the workspace (ANCHOR_BOX).
  * flags: bits 0-1 = gather variant (0 LDG, 1 cp.async.bulk staged, 2 LDG on a narrow persistent grid - for
- * host-resident maps, leaves the SMs to the compute kernels of another stream), bits 4-7 = pairwise variant, bit8 = record per-kernel events (profiling),
+ * host-resident maps, leaves the SMs to the compute kernels of another stream, 3 one cp.async.bulk.tensor box
+ * {64 ch, 2 px, 2 px} per sample point through a shared-memory ring), bits 4-7 = pairwise variant, bit8 = record per-kernel events (profiling),
  * bit9 = the gather already ran on this workspace (shasta_gather_pair_f32): start at the anchors stage,
  * bit10 = no internal side stream. By default the kernels that only need the input boxes (box copy, aug_dets, AUX,
  * column norms, back-projection) are forked onto a library-owned stream and joined before the projections, so they
  * overlap the HBM-bound aug_shape GEMM; the caller only ever sees work ordered on `stream`. */
 #define SHASTA_FLAG_TMA_GATHER 0x1u
 #define SHASTA_FLAG_NARROW_GATHER 0x2u
+#define SHASTA_FLAG_TMA_BOX_GATHER 0x3u
 #define SHASTA_FLAG_PROFILE 0x100u
 #define SHASTA_FLAG_SKIP_GATHER 0x200u
 #define SHASTA_FLAG_NO_OVERLAP 0x400u   /* keep every kernel on `stream` (no internal side stream) */

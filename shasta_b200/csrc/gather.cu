@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace shasta {
 
@@ -305,6 +306,156 @@ gather_bulk_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Variant 3: one cp.async.bulk.tensor box {64 channels, 2 px, 2 px} per sample point (4-D tensor map over the
+// (B, H, W, 64) batch of maps), staged through a ring of shared-memory stages by a producer warp; persistent CTAs,
+// frames folded into the tile index. The four taps of an interior point are exactly that box. A point whose clamped
+// taps are not a 2 x 2 block (map border, out-of-range boxes: center_utils.py:104-107 clamps, TMA would zero-fill)
+// takes the direct loads of variant 0 instead. Same blend arithmetic, so the outputs are bit-identical.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTmaPts = 32;            // points per stage: one per producer lane
+constexpr int kTmaStages = 3;
+constexpr int kTmaConsumerWarps = 8;
+constexpr int kTmaThreads = 32 * (1 + kTmaConsumerWarps);
+struct GatherTmaStage {
+  float taps[kTmaPts][4][kC];          // [point][(y0,x0) (y0,x1) (y1,x0) (y1,x1)][channel]: the TMA box order
+};
+struct GatherTmaMeta {
+  Taps t[kTmaPts];
+  long long src[kTmaPts];              // float4 offset of the point's map (border points), -1 = no point (ragged tail)
+  long long dst[kTmaPts];
+  long long dstlo[kTmaPts];
+  int interior[kTmaPts];
+};
+constexpr size_t kTmaSmemBytes = 1024 + kTmaStages * (sizeof(GatherTmaStage) + sizeof(GatherTmaMeta)) + 64;
+
+__global__ void __launch_bounds__(kTmaThreads)
+gather_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, GatherJob job,
+                  int nframes, int box_stride, int B, int M, shasta_geom_t g, size_t feat_batch_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  GatherTmaStage* stages = reinterpret_cast<GatherTmaStage*>(base);
+  GatherTmaMeta* metas = reinterpret_cast<GatherTmaMeta*>(base + kTmaStages * sizeof(GatherTmaStage));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kTmaStages * (sizeof(GatherTmaStage) + sizeof(GatherTmaMeta)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total = (long long)B * M * 5;
+  const long long tiles_per_frame = (total + kTmaPts - 1) / kTmaPts;
+  const long long ntiles = tiles_per_frame * nframes;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTmaStages; ++s) {
+      tc::mbar_init(tc::smem_u32(&bars[s]), kTmaPts);                          // full: every producer lane arrives
+      tc::mbar_init(tc::smem_u32(&bars[kTmaStages + s]), kTmaConsumerWarps);   // empty: one arrival per consumer warp
+    }
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ---- producer: point arithmetic (one point per lane) + one TMA box per interior point -------------------
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it % kTmaStages;
+      if (it >= kTmaStages) tc::mbar_wait(tc::smem_u32(&bars[kTmaStages + s]), (uint32_t)((it / kTmaStages - 1) & 1));
+      const int f = (int)(tile / tiles_per_frame);
+      const long long gp = (tile - (long long)f * tiles_per_frame) * kTmaPts + lane;
+      GatherTmaMeta& mt = metas[s];
+      const uint32_t full = tc::smem_u32(&bars[s]);
+      if (gp < total) {
+        const int bm = (int)(gp / 5), p = (int)(gp % 5);
+        const int b = bm / M, m = bm % M;
+        float xs, ys;
+        box_point_pixels(job.boxes[f] + (size_t)bm * box_stride, p, g, xs, ys);
+        const Taps t = make_taps(xs, ys, g.height, g.width);
+        const int interior = (t.x1 == t.x0 + 1) && (t.y1 == t.y0 + 1);
+        mt.t[lane] = t;
+        mt.src[lane] = (long long)b * g.height * g.width * (kC / 4);
+        mt.dst[lane] = (long long)((size_t)b * feat_batch_stride + (size_t)m * kF + p * kC);
+        mt.dstlo[lane] = gp * kC;
+        mt.interior[lane] = interior;
+        if (interior) {
+          tc::mbar_expect_tx(full, (uint32_t)(4 * kC * sizeof(float)));
+          tc::tma_load_4d(tc::smem_u32(&stages[s].taps[lane][0][0]), f ? &map1 : &map0, full, 0, t.x0, t.y0, b,
+                          tc::kEvictFirst);
+        } else {
+          tc::mbar_arrive(full);
+        }
+      } else {
+        mt.src[lane] = -1;
+        tc::mbar_arrive(full);
+      }
+    }
+  } else {
+    // ---- consumers: 16 lanes per point, two points per warp pass --------------------------------------------
+    const int cw = warp - 1, lane16 = lane & 15;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it % kTmaStages;
+      tc::mbar_wait(tc::smem_u32(&bars[s]), (uint32_t)((it / kTmaStages) & 1));
+      const int f = (int)(tile / tiles_per_frame);
+      const GatherTmaMeta& mt = metas[s];
+      float* __restrict__ feat = job.feat[f];
+      __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(job.featlo[f]);
+#pragma unroll
+      for (int k = 0; k < kTmaPts / (2 * kTmaConsumerWarps); ++k) {
+        const int pt = (k * kTmaConsumerWarps + cw) * 2 + (lane >> 4);
+        const long long src = mt.src[pt];
+        if (src >= 0) {
+          const Taps t = mt.t[pt];
+          float4 a, bb, c, d;
+          if (mt.interior[pt]) {
+            const float4* tp = reinterpret_cast<const float4*>(&stages[s].taps[pt][0][0]) + lane16;
+            a = tp[0], c = tp[kC / 4], bb = tp[2 * (kC / 4)], d = tp[3 * (kC / 4)];
+          } else {
+            const float4* gb = reinterpret_cast<const float4*>(job.bev[f]) + src + lane16;
+            a = __ldg(gb + (t.y0 * g.width + t.x0) * (kC / 4));
+            bb = __ldg(gb + (t.y1 * g.width + t.x0) * (kC / 4));
+            c = __ldg(gb + (t.y0 * g.width + t.x1) * (kC / 4));
+            d = __ldg(gb + (t.y1 * g.width + t.x1) * (kC / 4));
+          }
+          const float4 v = blend4(a, bb, c, d, t);
+          reinterpret_cast<float4*>(feat + mt.dst[pt])[lane16] = v;
+          if (lo != nullptr) reinterpret_cast<uint2*>(lo + mt.dstlo[pt])[lane16] = job.lo_mode ? bf16x4(v) : tf32_lo4(v);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bars[kTmaStages + s]));
+    }
+  }
+}
+
+typedef CUresult (*GatherEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// (B, H, W, 64) fp32 maps as a 4-D tensor, box = {64, 2, 2, 1}: the four taps of one sample point
+static int make_tap_map(CUtensorMap* m, const float* bev, int B, int H, int W) {
+  static GatherEncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<GatherEncodeFn>(p);
+  }
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return SHASTA_ERR_UNSUPPORTED;
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)kC, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)kC * sizeof(float), (cuuint64_t)W * kC * sizeof(float),
+                                 (cuuint64_t)H * W * kC * sizeof(float)};
+  const cuuint32_t box[4] = {(cuuint32_t)kC, 2u, 2u, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(bev), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (gather taps) failed with CUresult %d", (int)r);
+    return SHASTA_ERR_ARG;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 int launch_bilinear(const float* im, int H, int W, int C, const float* xs, const float* ys, int n, float* out,
                     cudaStream_t s) {
   if (n == 0) return 0;
@@ -334,6 +485,25 @@ int launch_gather(const float* bev0, const float* boxes0, float* feat0, const fl
     dim3 grid((unsigned)(need < cap ? need : cap), nframes);
     gather_ldg_kernel<<<grid, kGatherThreads, 0, s>>>(job, box_stride, B, M, g, feat_batch_stride);
     SHASTA_CHECK_LAUNCH("gather_ldg_kernel");
+  } else if (variant == 3 && g.height >= 2 && g.width >= 2) {
+    CUtensorMap maps[2];
+    for (int f = 0; f < nframes; ++f) {
+      const int rc = make_tap_map(&maps[f], f ? bev1 : bev0, B, g.height, g.width);
+      if (rc) return rc;
+    }
+    if (nframes < 2) maps[1] = maps[0];
+    static OncePerDevice configured;
+    if (configured.first())
+      SHASTA_CUDA(cudaFuncSetAttribute(gather_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
+    const long long ntiles = ((total + kTmaPts - 1) / kTmaPts) * nframes;
+    int dev = 0, sm_count = 0;
+    SHASTA_CUDA(cudaGetDevice(&dev));
+    SHASTA_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    const int per_sm = g_options[2] & 0xf ? (g_options[2] & 0xf) : 2;   // experiment knob: resident CTAs per SM
+    const long long cap = (long long)per_sm * sm_count;
+    gather_tma_kernel<<<(unsigned)(ntiles < cap ? ntiles : cap), kTmaThreads, kTmaSmemBytes, s>>>(
+        maps[0], maps[1], job, nframes, box_stride, B, M, g, feat_batch_stride);
+    SHASTA_CHECK_LAUNCH("gather_tma_kernel");
   } else if (variant == 1) {
     dim3 grid((unsigned)((total + kPointsPerCta1 - 1) / kPointsPerCta1), nframes);
     gather_bulk_kernel<<<grid, kGatherThreads, 0, s>>>(job, box_stride, B, M, g, feat_batch_stride);

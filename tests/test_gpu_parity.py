@@ -73,7 +73,7 @@ def test_bev_extractor_module_api():
 # ------------------------------------------------------------------------------------------------
 # a1+a2: fused box gather, both samplers
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("name", golden_names())
 def test_gather_from_boxes(name, variant):
     c, pc_start, data, weights, g = load_golden(name)
@@ -87,6 +87,59 @@ def test_gather_from_boxes(name, variant):
         exact = float(np.mean(got == want))
         assert np.allclose(got, want, rtol=1e-4, atol=1e-4), (gold_k, np.abs(got - want).max())
         assert exact > 0.5, "only %.3f of the gathered values are bit-identical" % exact
+
+
+@pytest.mark.parametrize("M,H,W,B", [(7, 9, 11, 3), (200, 180, 180, 2), (33, 2, 2, 1), (5, 1, 6, 2)])
+def test_gather_samplers_bit_identical(M, H, W, B):
+    """The four samplers (direct loads, bulk-copy staged, narrow grid, one TMA box {64 ch, 2 px, 2 px} per point) run
+    the same tap / blend arithmetic: identical bits, also for boxes on the border and far outside the map (clamped
+    taps: center_utils.py:104-107; the TMA variant must not zero-fill them), ragged last tiles and maps too small
+    for a 2 x 2 box."""
+    rng = np.random.default_rng(M * 7 + H)
+    pc_start = (-W * 0.6 / 2.0, -H * 0.6 / 2.0)
+    model = G.make_model(M, pc_start)
+    st = G.Stages(model, B)
+    bev = rng.standard_normal((B, H, W, 64)).astype(np.float32)
+    boxes = np.zeros((B, M, 11), np.float32)
+    boxes[..., 0] = rng.uniform(-W * 0.45, W * 0.45, (B, M))
+    boxes[..., 1] = rng.uniform(-H * 0.45, H * 0.45, (B, M))
+    boxes[..., 3:6] = rng.uniform(0.5, 6.0, (B, M, 3))
+    boxes[..., 6] = rng.uniform(-3.2, 3.2, (B, M))
+    boxes[:, 0, 0] = -W * 0.3 + 0.01          # left border: x0 clamps
+    boxes[:, 1, 1] = H * 0.3 - 0.01           # bottom border
+    boxes[:, 2, :2] = 1e4                     # far outside
+    boxes[:, 3, :2] = -1e4
+    dbev, dbox = G.t(bev), G.t(boxes)
+    got = {}
+    for variant in (0, 1, 2, 3):
+        st.ws.buf.zero_()
+        got[variant] = st.gather(dbev, dbox, _cabi.WS_FEAT_CUR, variant)[:, :M].cpu().numpy().copy()
+    for variant in (1, 2, 3):
+        assert np.array_equal(got[variant], got[0]), (variant, np.abs(got[variant] - got[0]).max())
+    # and against the oracle's sampler on the same pixel coordinates (bit-exact blend, coordinates to 1e-4)
+    want = O.gather_box_features(torch.from_numpy(bev), torch.from_numpy(boxes[..., :7].copy()), pc_start,
+                                 (0.075, 0.075), 8).numpy()
+    assert np.allclose(got[3], want, rtol=1e-4, atol=2e-4), np.abs(got[3] - want).max()
+
+
+def test_forward_with_tma_gather_bit_identical():
+    """Whole forward with the TMA-box sampler (flags & 3 = 3, writes the features AND their tf32 low parts for the
+    anchors GEMM) against the default sampler: same bits out."""
+    c, pc_start, data, weights, g = load_golden("m20_32px_b3_peaky")
+    outs = []
+    for flags in (0, 3):
+        model = G.make_model(c["M"], pc_start, weights)
+        model.kernel_flags = flags
+        model.cuda_graphs = False
+        lib = _cabi.lib()
+        lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, _cabi.ANCHOR_TC)   # the GEMM that reads FEATLO
+        try:
+            m1, m2 = model.affinity(G.t(data["bev"]), G.t(data["prev_bev"]), G.t(data["det_boxes"]), G.t(data["prev_det_boxes"]))
+            torch.cuda.synchronize()
+        finally:
+            lib.shasta_set_option(_cabi.OPT_ANCHOR_PATH, _cabi.ANCHOR_AUTO)
+        outs.append((m1.cpu().numpy(), m2.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
 
 
 # ------------------------------------------------------------------------------------------------
