@@ -96,6 +96,19 @@ col_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __rest
   float mx = -INFINITY;
   int nk = 0;
   int32_t* slot = nullptr;
+  // the column's logits first: their L2 round trip then overlaps the flag fetch and the rank scan of the fused decode
+  if (valid) {
+    if (in_regs) {
+#pragma unroll
+      for (int i = 0; i < kColRegs; ++i) {
+        const int t = ty + 8 * i;
+        v[i] = (t < T) ? src[(size_t)t * RS] : -INFINITY;
+        mx = fmaxf(mx, v[i]);
+      }
+    } else {
+      for (int t = ty; t < T; t += 8) mx = fmaxf(mx, src[(size_t)t * RS]);
+    }
+  }
   if (dec.n_prev) {
     // ranks of the kept previous rows (prev_state == 0, written by the row kernel of this forward): all threads fetch
     // the flags in one round trip, warp 0 turns them into exclusive ranks with a ballot scan over shared memory
@@ -119,18 +132,6 @@ col_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __rest
     }
     __syncthreads();
     nk = s_rank[M];
-  }
-  if (valid) {
-    if (in_regs) {
-#pragma unroll
-      for (int i = 0; i < kColRegs; ++i) {
-        const int t = ty + 8 * i;
-        v[i] = (t < T) ? src[(size_t)t * RS] : -INFINITY;
-        mx = fmaxf(mx, v[i]);
-      }
-    } else {
-      for (int t = ty; t < T; t += 8) mx = fmaxf(mx, src[(size_t)t * RS]);
-    }
   }
   red[ty][threadIdx.x] = mx;
   __syncthreads();
