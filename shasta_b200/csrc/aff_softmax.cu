@@ -79,7 +79,9 @@ aff_row_kernel(const float* __restrict__ packed, PackLayout P, int B, int M, con
 // once; longer columns fall back to re-reading them (L2-resident).
 constexpr int kColRegs = 32;
 
-__global__ void __launch_bounds__(256)
+// 4 CTAs per SM (<= 64 registers): the headline grid of 7 x 64 = 448 CTAs then fits one wave of 148 x 4 (at 3 per SM
+// it was 1.01 waves: four CTAs ran alone in a second one and doubled the kernel's time)
+__global__ void __launch_bounds__(256, 4)
 col_softmax_kernel(int B, int M, const float* __restrict__ logits, float* __restrict__ matched2, DecodeArgs dec) {
   __shared__ float red[8][33];
   __shared__ int redi[8][33];

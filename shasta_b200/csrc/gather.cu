@@ -174,20 +174,21 @@ gather_ldg_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, 
 // arithmetic, not memory, as its limiter (issue slots 66 % active at 2.6 TB/s of DRAM traffic); here a half-warp
 // walks 8 points with the loads of 4 of them in flight.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPointsPerCta3 = 128;
+constexpr int kPointsPerCta3 = 128;      // default; the launcher sizes the CTAs so that the grid is whole waves
+constexpr int kMaxPointsPerCta3 = kGatherThreads;
 
 __global__ void __launch_bounds__(kGatherThreads)
-gather_pts_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, size_t feat_batch_stride) {
-  __shared__ Taps s_t[kPointsPerCta3];
-  __shared__ long long s_src[kPointsPerCta3];   // float4 offset of the point's map in the batch of maps
-  __shared__ long long s_dst[kPointsPerCta3];   // float offset of the point's 64 output channels
+gather_pts_kernel(GatherJob job, int box_stride, int B, int M, shasta_geom_t g, size_t feat_batch_stride, int ppc) {
+  __shared__ Taps s_t[kMaxPointsPerCta3];
+  __shared__ long long s_src[kMaxPointsPerCta3];   // float4 offset of the point's map in the batch of maps
+  __shared__ long long s_dst[kMaxPointsPerCta3];   // float offset of the point's 64 output channels
   const int f = blockIdx.y;
   const float* __restrict__ bev = job.bev[f];
   const float* __restrict__ boxes = job.boxes[f];
   float* __restrict__ feat = job.feat[f];
   const long long total = (long long)B * M * 5;
-  const long long gp0 = (long long)blockIdx.x * kPointsPerCta3;
-  const int npts = (int)min((long long)kPointsPerCta3, total - gp0);
+  const long long gp0 = (long long)blockIdx.x * ppc;
+  const int npts = (int)min((long long)ppc, total - gp0);
   if (threadIdx.x < npts) {
     const long long gp = gp0 + threadIdx.x;
     const int bm = (int)(gp / 5), p = (int)(gp % 5);
@@ -509,8 +510,24 @@ int launch_gather(const float* bev0, const float* boxes0, float* feat0, const fl
     gather_bulk_kernel<<<grid, kGatherThreads, 0, s>>>(job, box_stride, B, M, g, feat_batch_stride);
     SHASTA_CHECK_LAUNCH("gather_bulk_kernel");
   } else {
-    dim3 grid((unsigned)((total + kPointsPerCta3 - 1) / kPointsPerCta3), nframes);
-    gather_pts_kernel<<<grid, kGatherThreads, 0, s>>>(job, box_stride, B, M, g, feat_batch_stride);
+    // CTA size in points: the default unless the grid would end in a partly filled wave (the headline's 2 x 500 CTAs
+    // at 6 resident CTAs per SM were 1.13 waves): then the points are spread over whole waves
+    int dev = 0, sm_count = 0, per_sm = 0;
+    SHASTA_CUDA(cudaGetDevice(&dev));
+    SHASTA_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    SHASTA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_pts_kernel, kGatherThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    const long long wave = (long long)per_sm * sm_count / nframes;          // CTAs of one frame in one wave
+    long long ctas = (total + kPointsPerCta3 - 1) / kPointsPerCta3;
+    int ppc = kPointsPerCta3;
+    if (ctas > wave / 2) {
+      const long long waves = (total + wave * kMaxPointsPerCta3 - 1) / (wave * kMaxPointsPerCta3);   // fewest waves
+      const long long want = (total + waves * wave - 1) / (waves * wave);
+      ppc = (int)(want < 32 ? 32 : (want > kMaxPointsPerCta3 ? kMaxPointsPerCta3 : want));
+      ctas = (total + ppc - 1) / ppc;
+    }
+    dim3 grid((unsigned)ctas, nframes);
+    gather_pts_kernel<<<grid, kGatherThreads, 0, s>>>(job, box_stride, B, M, g, feat_batch_stride, ppc);
     SHASTA_CHECK_LAUNCH("gather_pts_kernel");
   }
   return 0;
