@@ -355,6 +355,7 @@ def run_train(a):
         dist.init_process_group("nccl", device_id=device)
     from shasta_b200 import _cabi, loss as L, training
     lib = _cabi.lib()
+    lib.shasta_set_option(2, a.dbg)
     pc_start, d, bev, prev_bev = make_inputs(a, device, seed=2000 + rank)
     model = build_model(a, pc_start, device)
     model.train()

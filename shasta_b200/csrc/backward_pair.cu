@@ -613,16 +613,26 @@ int launch_backward_pair(const shasta_grads_t& gr, const float* packed, int B, i
     SHASTA_CUDA(cudaFuncSetAttribute(pair_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   const int ndb = (T + 15) / 16, ntt = (T + 7) / 8;
+  int dev = 0, sm_count = 0, per_sm = 0;
+  SHASTA_CUDA(cudaGetDevice(&dev));
+  SHASTA_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  SHASTA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_bwd_kernel, kPbThreads, smem));
+  const long long slots = (long long)(per_sm < 1 ? 1 : per_sm) * sm_count;
   auto run = [&](int db_first, int ndbs, int tt_begin, int tt_end) -> int {
     if (ndbs <= 0 || tt_end <= tt_begin) return 0;
-    // row chunks: enough CTAs for ~4 waves of 2 CTAs per SM, at least 4 row blocks per CTA (the per-CTA epilogue
-    // - 16 x 144 + ~2 400 atomics - is amortised over them)
-    int nz = (4 * 2 * 148 + ndbs * B - 1) / (ndbs * B);
+    // row chunks: a CTA walks `chunk` row blocks of its column block and then pays a fixed epilogue (16 x 144 + ~2 400
+    // atomics: about a quarter of a row block, measured). All CTAs take the same time, so the launch runs in whole
+    // rounds of `slots` CTAs: pick the chunk that minimises rounds x (chunk + 0.25). (Round 2 measurement at M = 200,
+    // B = 64: 13-block chunks ran 5.2 rounds -> 6; 5-block chunks run 12.97 -> 13 rounds of 0.4 the length.)
     const int ntt_ = tt_end - tt_begin;
-    nz = nz < 1 ? 1 : nz;
-    nz = nz > (ntt_ + 3) / 4 ? (ntt_ + 3) / 4 : nz;
-    const int chunk = (ntt_ + nz - 1) / nz;
-    nz = (ntt_ + chunk - 1) / chunk;
+    int chunk = ntt_;
+    double best = 1e30;
+    for (int c = 1; c <= ntt_; ++c) {
+      const long long ctas = (long long)ndbs * B * ((ntt_ + c - 1) / c);
+      const double cost = (double)((ctas + slots - 1) / slots) * (c + 0.25);
+      if (cost < best - 1e-9) best = cost, chunk = c;
+    }
+    const int nz = (ntt_ + chunk - 1) / chunk;
     pair_bwd_kernel<<<dim3(ndbs, B, nz), kPbThreads, smem, s>>>(
         packed, P, B, M, ws + L.off[SHASTA_WS_PROJ_PREV], ws + L.off[SHASTA_WS_PROJ_CUR_T],
         ws + L.off[SHASTA_WS_AUX_PREV], ws + L.off[SHASTA_WS_AUX_CUR], ws + L.off[SHASTA_WS_COLNORM],
