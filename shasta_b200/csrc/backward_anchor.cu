@@ -184,9 +184,11 @@ struct AnchorW0Grads {
 // into tf32 high and low parts and three products per step (hi.hi + lo.hi + hi.lo): fp32-equivalent, like the
 // forward's 3xTF32. (The CUDA-core version - 8 x 4 register tiles, 0.95 ms at M = 200, B = 64 - was bound by FMA issue;
 // 8 x 8 tiles and packed fma.rn.f32x2 were measured slower: 1.00 / 1.07 ms.)
-// grid (ceil(K/128), ceil(N5/64), 4), block 256 = 8 warps: warp = 16 hidden units x 64 k.
+// grid (ceil(K/128), ceil(N5/128), 4), block 256 = 8 warps: warp = 32 hidden units x 64 k (the operand splits are
+// the instruction overhead: 24 per 48 MMAs at this warp tile, 20 per 24 at 16 x 64 - 0.71 ms).
 constexpr int kW0BC = 64;            // frame pairs staged at a time (the MMA's K dimension, 8 per step)
-constexpr int kW0ZS = 72;            // floats per staged dz row  (72 % 32 = 8: conflict-free fragment loads)
+constexpr int kW0NT = 128;           // hidden units per CTA
+constexpr int kW0ZS = 136;           // floats per staged dz row  (136 % 32 = 8: conflict-free fragment loads)
 constexpr int kW0XS = 136;           // floats per staged x row
 constexpr size_t kW0Smem = sizeof(float) * (size_t)kW0BC * (kW0ZS + kW0XS);
 __device__ __forceinline__ void w0_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -199,7 +201,7 @@ __device__ __forceinline__ void w0_split(float v, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(v) & 0xffffe000u;
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 anchor_w0_grad_kernel(int B, int M, const float* __restrict__ dzbuf, const float* __restrict__ feat_cur,
                       const float* __restrict__ feat_prev, AnchorW0Grads g) {
   extern __shared__ __align__(16) float w0sm[];
@@ -208,21 +210,23 @@ anchor_w0_grad_kernel(int B, int M, const float* __restrict__ dzbuf, const float
   const int N5 = 5 * M, K = kF * M;
   const size_t xstride = (size_t)(M + 2) * kF;
   const int i = blockIdx.z;
-  const int k0 = blockIdx.x * 128, n0 = blockIdx.y * 64;
+  const int k0 = blockIdx.x * 128, n0 = blockIdx.y * kW0NT;
   const float* __restrict__ X = (i < 2) ? feat_cur : feat_prev;   // aug_shape 0,1 read the current features
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, tq = lane & 3;
-  const int wn = (warp & 3) * 16, wk = (warp >> 2) * 64;
-  float acc[8][4];
+  const int wn = (warp & 3) * 32, wk = (warp >> 2) * 64;
+  float acc[2][8][4];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e][0] = acc[e][1] = acc[e][2] = acc[e][3] = 0.f;
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[h][e][0] = acc[h][e][1] = acc[h][e][2] = acc[h][e][3] = 0.f;
 
   for (int b0 = 0; b0 < B; b0 += kW0BC) {
     const int nb = min(kW0BC, B - b0);
     const int nb8 = (nb + 7) & ~7;
     __syncthreads();
-    for (int v = threadIdx.x; v < nb8 * 64; v += 256) {
-      const int bb = v >> 6, nn = v & 63;
+    for (int v = threadIdx.x; v < nb8 * kW0NT; v += 256) {
+      const int bb = v / kW0NT, nn = v % kW0NT;
       dzs[bb * kW0ZS + nn] = (bb < nb && n0 + nn < N5) ? dzbuf[((size_t)(b0 + bb) * 4 + i) * N5 + n0 + nn] : 0.f;
     }
     for (int v = threadIdx.x; v < nb8 * 32; v += 256) {
@@ -236,34 +240,43 @@ anchor_w0_grad_kernel(int B, int M, const float* __restrict__ dzbuf, const float
     // (splitting the operands once while staging them - (hi, lo) pairs in shared memory, 8-byte fragment loads - was
     // measured slower: 0.96 against 0.70 ms)
     for (int bs = 0; bs < nb8; bs += 8) {
-      // A fragment (16 n x 8 b, row-major in n): a0 (g, t), a1 (g + 8, t), a2 (g, t + 4), a3 (g + 8, t + 4)
-      uint32_t ah[4], al[4];
-      w0_split(dzs[(bs + tq) * kW0ZS + wn + gq], ah[0], al[0]);
-      w0_split(dzs[(bs + tq) * kW0ZS + wn + gq + 8], ah[1], al[1]);
-      w0_split(dzs[(bs + tq + 4) * kW0ZS + wn + gq], ah[2], al[2]);
-      w0_split(dzs[(bs + tq + 4) * kW0ZS + wn + gq + 8], ah[3], al[3]);
+      // A fragments (16 n x 8 b, row-major in n): a0 (g, t), a1 (g + 8, t), a2 (g, t + 4), a3 (g + 8, t + 4)
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int nn = wn + 16 * h + gq;
+        w0_split(dzs[(bs + tq) * kW0ZS + nn], ah[h][0], al[h][0]);
+        w0_split(dzs[(bs + tq) * kW0ZS + nn + 8], ah[h][1], al[h][1]);
+        w0_split(dzs[(bs + tq + 4) * kW0ZS + nn], ah[h][2], al[h][2]);
+        w0_split(dzs[(bs + tq + 4) * kW0ZS + nn + 8], ah[h][3], al[h][3]);
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         // B fragment (8 b x 8 k): b0 (b = t, k = g), b1 (b = t + 4, k = g)
         uint32_t bh0, bl0, bh1, bl1;
         w0_split(xs[(bs + tq) * kW0XS + wk + e * 8 + gq], bh0, bl0);
         w0_split(xs[(bs + tq + 4) * kW0XS + wk + e * 8 + gq], bh1, bl1);
-        w0_mma(acc[e], al, bh0, bh1);
-        w0_mma(acc[e], ah, bl0, bl1);
-        w0_mma(acc[e], ah, bh0, bh1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          w0_mma(acc[h][e], al[h], bh0, bh1);
+          w0_mma(acc[h][e], ah[h], bl0, bl1);
+          w0_mma(acc[h][e], ah[h], bh0, bh1);
+        }
       }
     }
   }
   // C fragment (16 n x 8 k): c0 (g, 2t), c1 (g, 2t + 1), c2 (g + 8, 2t), c3 (g + 8, 2t + 1)
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int k = k0 + wk + e * 8 + 2 * tq;
-    if (k < K) {   // K is a multiple of 4 and k is even: k + 1 < K too
-      const int na = n0 + wn + gq, nb_ = na + 8;
-      if (na < N5) *reinterpret_cast<float2*>(g.w0[i] + (size_t)na * K + k) = make_float2(acc[e][0], acc[e][1]);
-      if (nb_ < N5) *reinterpret_cast<float2*>(g.w0[i] + (size_t)nb_ * K + k) = make_float2(acc[e][2], acc[e][3]);
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + wk + e * 8 + 2 * tq;
+      if (k < K) {   // K is a multiple of 4 and k is even: k + 1 < K too
+        const int na = n0 + wn + 16 * h + gq, nb_ = na + 8;
+        if (na < N5) *reinterpret_cast<float2*>(g.w0[i] + (size_t)na * K + k) = make_float2(acc[h][e][0], acc[h][e][1]);
+        if (nb_ < N5) *reinterpret_cast<float2*>(g.w0[i] + (size_t)nb_ * K + k) = make_float2(acc[h][e][2], acc[h][e][3]);
+      }
     }
-  }
 }
 
 int launch_backward_anchor(const shasta_params_t& p, const shasta_grads_t& gr, int B, int S, float* ws,
@@ -301,7 +314,7 @@ int launch_backward_anchor(const shasta_params_t& p, const shasta_grads_t& gr, i
   static OncePerDevice w0_configured;
   if (w0_configured.first())
     SHASTA_CUDA(cudaFuncSetAttribute(anchor_w0_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kW0Smem));
-  anchor_w0_grad_kernel<<<dim3((K + 127) / 128, (N5 + 63) / 64, 4), 256, kW0Smem, s>>>(
+  anchor_w0_grad_kernel<<<dim3((K + 127) / 128, (N5 + kW0NT - 1) / kW0NT, 4), 256, kW0Smem, s>>>(
       B, M, dzbuf, ws + L.off[SHASTA_WS_FEAT_CUR], ws + L.off[SHASTA_WS_FEAT_PREV], wg);
   SHASTA_CHECK_LAUNCH("anchor_w0_grad_kernel");
   return 0;
