@@ -368,7 +368,10 @@ def run_train(a):
     # rest: with several ranks the update of generator i runs while the all-reduce of generator i+1 is still in flight
     adam = dict(lr=1e-4, weight_decay=1e-2, fused=True)
     big_params = [p_ for p_ in params if p_.numel() >= (1 << 22)]          # aug_shape.i.0.weight, i = 0..3
-    opts = [torch.optim.Adam([p_], **adam) for p_ in big_params]
+    # the big ones: the library's streaming Adam kernel (28 bytes per parameter at HBM speed); BENCH_TORCH_ADAM=1: torch's
+    big_adam = dict(lr=adam["lr"], weight_decay=adam["weight_decay"])
+    opts = [(torch.optim.Adam([p_], **adam) if os.environ.get("BENCH_TORCH_ADAM") else training.StreamAdam([p_], **big_adam))
+            for p_ in big_params]
     opt_rest = torch.optim.Adam([p_ for p_ in params if p_.numel() < (1 << 22)], **adam)
     B, M = a.batch, a.max_obj
     det0 = torch.from_numpy(d["det_boxes"]).to(device)

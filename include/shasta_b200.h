@@ -364,6 +364,15 @@ SHASTA_API int shasta_backward_maps_f32(const shasta_params_t* host_params, int 
                                         const float* prev_det_boxes, float* scratch, size_t scratch_bytes,
                                         float* d_bev, float* d_prev_bev, shasta_stream_t stream);
 
+/* tools/nusc_shasta/train.py:146 optim.Adam(model.parameters(), lr, weight_decay): one update of one parameter tensor
+ * with torch.optim.Adam semantics (L2 weight decay added to the gradient, bias-corrected first / second moments, no
+ * amsgrad). `step` is the 1-based update count. All four arrays hold `count` floats, 16-byte aligned; param, exp_avg
+ * and exp_avg_sq are updated in place. Meant for the four 64 M-element aug_shape.i.0.weight tensors (a pure
+ * 28-bytes-per-parameter stream); small tensors are better served by a multi-tensor optimizer. */
+SHASTA_API int shasta_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count,
+                                    float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                    shasta_stream_t stream);
+
 /* Per-kernel timing for the roofline report (no reference counterpart). After shasta_profile_begin(n), every
  * shasta_forward_f32 call with flag bit 8 (0x100) records CUDA events between its kernels (up to n calls);
  * shasta_profile_end synchronises on them and returns the mean milliseconds of the 7 kernels in launch order:

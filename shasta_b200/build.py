@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libshasta_b200.so")
 SOURCES = ["api.cu", "pack.cu", "gather.cu", "anchors.cu", "anchors_tc.cu", "anchors_tc2.cu", "anchors_bf16.cu", "project.cu", "project_tc.cu", "pairwise.cu", "pairwise_tc.cu", "pairwise_tc3.cu",
-           "aff_softmax.cu", "aff_tc.cu", "backward.cu", "backward_pair.cu", "backward_anchor.cu", "backward_box.cu", "backward_maps.cu", "decode.cu", "greedy.cu"]
+           "aff_softmax.cu", "aff_tc.cu", "backward.cu", "backward_pair.cu", "backward_anchor.cu", "backward_box.cu", "backward_maps.cu", "optimizer.cu", "decode.cu", "greedy.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

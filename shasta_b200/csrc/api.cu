@@ -601,6 +601,25 @@ int shasta_backward_overlap_f32(const shasta_params_t* host_params, const shasta
                          gm1, gm2, (cudaStream_t)stream, (cudaEvent_t)aug_shape_grads_ready_event);
 }
 
+int shasta_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, int step, shasta_stream_t stream) {
+  if (count == 0) return 0;
+  NOT_NULL(param);
+  NOT_NULL(grad);
+  NOT_NULL(exp_avg);
+  NOT_NULL(exp_avg_sq);
+  ALIGNED16(param);
+  ALIGNED16(grad);
+  ALIGNED16(exp_avg);
+  ALIGNED16(exp_avg_sq);
+  if (step < 1 || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(eps >= 0.f)) {
+    set_error("adam: step must be >= 1, betas in [0, 1), eps >= 0");
+    return SHASTA_ERR_ARG;
+  }
+  return launch_adam(param, grad, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, weight_decay, step,
+                     (cudaStream_t)stream);
+}
+
 size_t shasta_backward_maps_scratch_bytes(int batch, int max_obj) {
   if (batch < 0 || max_obj < 1) return 0;
   return (size_t)2 * batch * max_obj * kF * sizeof(float);

@@ -126,3 +126,43 @@ class _AffinityFunction(torch.autograd.Function):
 
 def affinity_with_grad(model, bev, prev_bev, det_c, prev_c):
     return _AffinityFunction.apply(model, bev, prev_bev, det_c, prev_c, *differentiable_parameters(model))
+
+
+class StreamAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam`` semantics (train.py:146: lr, weight_decay as L2 on the gradient, betas (0.9, 0.999),
+    eps 1e-8, no amsgrad) for LARGE fp32 CUDA tensors, one ``shasta_adam_step_f32`` launch per tensor: the four
+    ``aug_shape.i.0.weight`` matrices are 99.8 % of the head's parameters and their update is a pure 28-bytes-per-parameter
+    stream. Same constructor keywords and ``state_dict`` layout (``step``, ``exp_avg``, ``exp_avg_sq``) as torch's."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
+            raise ValueError("invalid Adam hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _cabi.lib()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise ValueError("StreamAdam: contiguous fp32 CUDA parameters only")
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] += 1
+                _cabi.check(lib.shasta_adam_step_f32(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
+                                                     st["exp_avg_sq"].data_ptr(), p.numel(), group["lr"], b1, b2,
+                                                     group["eps"], group["weight_decay"], st["step"], stream),
+                            "shasta_adam_step_f32")
+        return loss

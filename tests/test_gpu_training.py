@@ -201,3 +201,35 @@ def test_training_steps_lower_the_loss():
                       torch.from_numpy(data["det_boxes"].copy()), torch.from_numpy(data["prev_det_boxes"]),
                       pc_start=pc_start)
     assert G.rel_err(e1.cpu().numpy(), o1.numpy()) < 2e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 7, 4096 + 3, 1 << 20])
+def test_stream_adam_matches_torch_adam(n):
+    """shasta_adam_step_f32 (training.StreamAdam) against torch.optim.Adam on the same parameters and gradients
+    (train.py:146: lr, weight_decay): three steps, parameters and both moments to 1e-6 relative."""
+    from shasta_b200 import training
+    gen = torch.Generator(device="cpu").manual_seed(n)
+    p0 = torch.randn(n, generator=gen)
+    grads = [torch.randn(n, generator=gen) * (10.0 ** (k - 1)) for k in range(3)]
+    kw = dict(lr=1e-2, weight_decay=1e-2, betas=(0.9, 0.999), eps=1e-8)
+    pa = torch.nn.Parameter(p0.clone().to(G.DEV))
+    pb = torch.nn.Parameter(p0.clone().to(G.DEV))
+    oa = torch.optim.Adam([pa], **kw)
+    ob = training.StreamAdam([pb], **kw)
+    for g in grads:
+        pa.grad = g.to(G.DEV)
+        pb.grad = g.to(G.DEV)
+        oa.step()
+        ob.step()
+    torch.cuda.synchronize()
+    sa, sb = oa.state[pa], ob.state[pb]
+    for name, a, b in (("param", pa.data, pb.data), ("exp_avg", sa["exp_avg"], sb["exp_avg"]),
+                       ("exp_avg_sq", sa["exp_avg_sq"], sb["exp_avg_sq"])):
+        a, b = a.cpu().double(), b.cpu().double()
+        # relative, floored at 1e-4 of the tensor's scale (and at 1e-3 for the parameters: an update of ~lr can leave a
+        # parameter arbitrarily close to zero, where one ulp of the update is a large relative error)
+        floor = max(1e-4 * float(a.abs().max()), 1e-3 if name == "param" else 0.0)
+        err = float(((a - b).abs() / a.abs().clamp_min(floor)).max())
+        assert err < 5e-6, (name, err)
+    assert int(sb["step"]) == 3
