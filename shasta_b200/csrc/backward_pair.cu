@@ -511,8 +511,9 @@ __global__ void __launch_bounds__(256)
 first_layer_bwd_kernel(int B, int M, const float* __restrict__ dproj_prev, const float* __restrict__ dproj_cur,
                        const float* __restrict__ feat_prev, const float* __restrict__ feat_cur,
                        const float* __restrict__ box_prev, const float* __restrict__ box_cur, FirstGrads g) {
-  __shared__ __align__(16) float dps[kFlRows][kProjShape];   // 28 KB
+  __shared__ __align__(16) float dps[kFlRows][kProj];        // 36 KB (the k-tile-0 CTAs also stage the fuse_det columns)
   __shared__ __align__(16) float fsm[kFlRows][32];           // 8 KB
+  __shared__ __align__(16) float bxs[kFlRows][4];            // box x, y, z and 1 (bias column): k-tile-0 CTAs only
   const int T = M + 2;
   const long long nrows = (long long)B * T;
   const int side = blockIdx.z;
@@ -529,8 +530,9 @@ first_layer_bwd_kernel(int B, int M, const float* __restrict__ dproj_prev, const
   for (long long rr = r0; rr < min(nrows, r0 + kFlChunk); rr += kFlRows) {
     const int nr = (int)min((long long)kFlRows, nrows - rr);
     __syncthreads();
-    for (int v = threadIdx.x; v < kFlRows * (kProjShape / 4); v += 256) {
-      const int r = v / (kProjShape / 4), c4 = v % (kProjShape / 4);
+    const int ncol4 = (blockIdx.x == 0 ? kProj : kProjShape) / 4;
+    for (int v = threadIdx.x; v < kFlRows * ncol4; v += 256) {
+      const int r = v / ncol4, c4 = v % ncol4;
       reinterpret_cast<float4*>(&dps[r][0])[c4] =
           (r < nr) ? __ldg(reinterpret_cast<const float4*>(dproj + (size_t)(rr + r) * kProj) + c4)
                    : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -540,6 +542,12 @@ first_layer_bwd_kernel(int B, int M, const float* __restrict__ dproj_prev, const
       reinterpret_cast<float4*>(&fsm[r][0])[c4] =
           (r < nr) ? __ldg(reinterpret_cast<const float4*>(feat + (size_t)(rr + r) * kF + k0) + c4)
                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < kFlRows) {
+      const int r = threadIdx.x;
+      const float* bx = box + (size_t)(rr + r) * 8;
+      *reinterpret_cast<float4*>(&bxs[r][0]) = (r < nr) ? make_float4(__ldg(bx), __ldg(bx + 1), __ldg(bx + 2), 1.f)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
 #pragma unroll 4
@@ -559,10 +567,8 @@ first_layer_bwd_kernel(int B, int M, const float* __restrict__ dproj_prev, const
         if (c == 3 && side == 0) continue;
         if (j < 40 && c < 3) continue;     // fuse_shape.0 has no box columns
         float s = 0.f;
-        for (int r = 0; r < nr; ++r) {
-          const float dv = __ldg(dproj + (size_t)(rr + r) * kProj + j);
-          s = fmaf(dv, c < 3 ? __ldg(box + (size_t)(rr + r) * 8 + c) : 1.f, s);
-        }
+#pragma unroll 8
+        for (int r = 0; r < kFlRows; ++r) s = fmaf(dps[r][j], bxs[r][c], s);   // rows >= nr are staged as zeros
         float* dst;
         if (c == 3) dst = (j < 40) ? g.fs_b + j : (j < 112 ? g.rc_b + (j - 40) : g.fd_b + (j - 112));
         else if (j < 112) dst = g.rc_w + (size_t)(j - 40) * 646 + (side ? 643 : 320) + c;
