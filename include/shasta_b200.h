@@ -366,11 +366,12 @@ SHASTA_API int shasta_backward_maps_f32(const shasta_params_t* host_params, int 
 
 /* tools/nusc_shasta/train.py:146 optim.Adam(model.parameters(), lr, weight_decay): one update of one parameter tensor
  * with torch.optim.Adam semantics (L2 weight decay added to the gradient, bias-corrected first / second moments, no
- * amsgrad). `step` is the 1-based update count. All four arrays hold `count` floats, 16-byte aligned; param, exp_avg
+ * amsgrad). The hyper-parameters are doubles like torch's Python scalars (1 - beta and the bias corrections are formed
+ * in double and rounded to fp32 once). `step` is the 1-based update count. All four arrays hold `count` floats, 16-byte aligned; param, exp_avg
  * and exp_avg_sq are updated in place. Meant for the four 64 M-element aug_shape.i.0.weight tensors (a pure
  * 28-bytes-per-parameter stream); small tensors are better served by a multi-tensor optimizer. */
 SHASTA_API int shasta_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count,
-                                    float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                    double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                                     shasta_stream_t stream);
 
 /* Per-kernel timing for the roofline report (no reference counterpart). After shasta_profile_begin(n), every

@@ -120,8 +120,8 @@ SYMBOLS = {
     "shasta_backward_maps_scratch_bytes": (_sz, [_i, _i]),
     "shasta_backward_maps_f32": (_i, [ctypes.POINTER(ShastaParams), _i, ctypes.POINTER(ShastaGeom), _vp, _sz, _vp, _vp,
                                       _vp, _sz, _vp, _vp, _vp]),
-    "shasta_adam_step_f32": (_i, [_vp, _vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
-                                  ctypes.c_float, _i, _vp]),
+    "shasta_adam_step_f32": (_i, [_vp, _vp, _vp, _vp, _sz, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                  ctypes.c_double, ctypes.c_double, _i, _vp]),
     "shasta_profile_begin": (_i, [_i]),
     "shasta_profile_end": (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "shasta_decode_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -601,8 +601,8 @@ int shasta_backward_overlap_f32(const shasta_params_t* host_params, const shasta
                          gm1, gm2, (cudaStream_t)stream, (cudaEvent_t)aug_shape_grads_ready_event);
 }
 
-int shasta_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count, float lr,
-                         float beta1, float beta2, float eps, float weight_decay, int step, shasta_stream_t stream) {
+int shasta_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count, double lr,
+                         double beta1, double beta2, double eps, double weight_decay, int step, shasta_stream_t stream) {
   if (count == 0) return 0;
   NOT_NULL(param);
   NOT_NULL(grad);
@@ -612,7 +612,7 @@ int shasta_adam_step_f32(float* param, const float* grad, float* exp_avg, float*
   ALIGNED16(grad);
   ALIGNED16(exp_avg);
   ALIGNED16(exp_avg_sq);
-  if (step < 1 || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(eps >= 0.f)) {
+  if (step < 1 || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0)) {
     set_error("adam: step must be >= 1, betas in [0, 1), eps >= 0");
     return SHASTA_ERR_ARG;
   }

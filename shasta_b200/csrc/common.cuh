@@ -378,8 +378,8 @@ int launch_aff_softmax(const float* packed, int B, int M, float* ws, const WsLay
 int launch_backward(const shasta_params_t& p, const shasta_grads_t& g, const float* packed, int B, float* ws,
                     const WsLayout& L, const float* m1, const float* m2, const float* gm1, const float* gm2,
                     cudaStream_t s, cudaEvent_t anchor_grads_ready = nullptr);
-int launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
-                float weight_decay, int step, cudaStream_t s);
+int launch_adam(float* p, const float* g, float* m, float* v, size_t n, double lr, double beta1, double beta2, double eps,
+                double weight_decay, int step, cudaStream_t s);
 int launch_backward_maps(const shasta_params_t& p, int B, const shasta_geom_t& g, float* ws, const WsLayout& L,
                          const float* det_boxes, const float* prev_det_boxes, int box_stride, float* dfeat,
                          float* d_bev, float* d_prev_bev, cudaStream_t s);

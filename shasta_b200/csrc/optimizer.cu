@@ -9,8 +9,8 @@
 
 namespace shasta {
 
-struct AdamArgs {
-  float lr, beta1, beta2, eps, weight_decay, bias1, bias2_sqrt;
+struct AdamArgs {   // host-side scalars, formed in double like torch's and rounded once
+  float step_size, one_minus_beta1, beta2, one_minus_beta2, eps, weight_decay, bias2_sqrt;
 };
 
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
@@ -24,10 +24,10 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamArgs& a) {
   g = fmaf(a.weight_decay, p, g);                       // grad = grad + weight_decay * param
-  m = fmaf(1.f - a.beta1, g - m, m);                    // exp_avg.lerp_(grad, 1 - beta1)
-  v = fmaf(a.beta2, v, (1.f - a.beta2) * g * g);        // exp_avg_sq = beta2 * exp_avg_sq + (1 - beta2) * grad^2
+  m = fmaf(a.one_minus_beta1, g - m, m);                // exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(a.beta2, v, a.one_minus_beta2 * g * g);      // exp_avg_sq = beta2 * exp_avg_sq + (1 - beta2) * grad^2
   const float denom = sqrtf(v) / a.bias2_sqrt + a.eps;
-  p -= (a.lr / a.bias1) * (m / denom);
+  p -= a.step_size * (m / denom);                       // step_size = lr / (1 - beta1^step)
 }
 
 constexpr int kAdamUnroll = 2;
@@ -63,14 +63,16 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   if (t < n) adam_one(p[t], g[t], m[t], v[t], a);
 }
 
-int launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
-                float weight_decay, int step, cudaStream_t s) {
+int launch_adam(float* p, const float* g, float* m, float* v, size_t n, double lr, double beta1, double beta2, double eps,
+                double weight_decay, int step, cudaStream_t s) {
   if (n == 0) return 0;
   AdamArgs a;
-  a.lr = lr, a.beta1 = beta1, a.beta2 = beta2, a.eps = eps, a.weight_decay = weight_decay;
-  // bias corrections in double, like torch's host-side scalars
-  a.bias1 = (float)(1.0 - pow((double)beta1, (double)step));
-  a.bias2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  // torch forms 1 - beta, the bias corrections and lr / bias_correction1 from Python doubles and rounds the results to
+  // fp32 once (1 - 0.999 in fp32 would already be off by 1.3e-5 relative)
+  a.one_minus_beta1 = (float)(1.0 - beta1), a.beta2 = (float)beta2, a.one_minus_beta2 = (float)(1.0 - beta2);
+  a.eps = (float)eps, a.weight_decay = (float)weight_decay;
+  a.step_size = (float)(lr / (1.0 - pow(beta1, (double)step)));
+  a.bias2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
   int dev = 0, sm_count = 0;
   SHASTA_CUDA(cudaGetDevice(&dev));
   SHASTA_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
