@@ -146,7 +146,7 @@ class StreamAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _cabi.lib()
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = None
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:
@@ -154,6 +154,8 @@ class StreamAdam(torch.optim.Optimizer):
                     continue
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                     raise ValueError("StreamAdam: contiguous fp32 CUDA parameters only")
+                if stream is None:
+                    stream = ctypes.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 st = self.state[p]
                 if not st:

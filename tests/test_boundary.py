@@ -108,3 +108,24 @@ def test_cabi_host_side_queries(shasta_lib):
     # argument errors are reported, not crashed on (no launch happens before validation)
     assert lib.shasta_bilinear_f32(None, 4, 4, 8, None, None, 0, None, None) < 0
     assert b"NULL" in lib.shasta_last_error_string()
+
+
+def test_adam_entry_point_validates_on_the_host(shasta_lib):
+    """shasta_adam_step_f32 (train.py:146 optim.Adam): argument errors come back as codes before any launch, an empty
+    tensor is a no-op, and the torch-side wrapper refuses tensors the kernel cannot update."""
+    lib = shasta_lib
+    assert lib.shasta_adam_step_f32(None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, None) == 0
+    assert lib.shasta_adam_step_f32(None, None, None, None, 4, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, None) < 0
+    assert b"NULL" in lib.shasta_last_error_string()
+    buf = torch.zeros(16)
+    p = buf.data_ptr()
+    assert lib.shasta_adam_step_f32(p, p, p, p, 4, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, None) < 0      # step is 1-based
+    assert lib.shasta_adam_step_f32(p, p, p, p, 4, 1e-3, 1.0, 0.999, 1e-8, 0.0, 1, None) < 0      # beta1 < 1
+    assert b"adam" in lib.shasta_last_error_string()
+    from shasta_b200 import training
+    with pytest.raises(ValueError):
+        training.StreamAdam([torch.nn.Parameter(torch.zeros(4))], lr=-1.0)
+    w = torch.nn.Parameter(torch.zeros(4))
+    w.grad = torch.ones(4)
+    with pytest.raises(ValueError, match="CUDA"):
+        training.StreamAdam([w]).step()
